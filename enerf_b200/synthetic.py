@@ -1,0 +1,101 @@
+"""Seeded synthetic inputs shared by the tests, bench.py and the golden-vector script
+(SURVEY.md section 8d "Synthetic inputs").  No dataset or checkpoint is available offline, so the
+workload is: random-init weights of the reference architecture with randomised BN statistics,
+U(-1,1) source images, random pin-hole intrinsics, small random SE(3) source poses around an
+identity target, near_far = [2, 6], and full-frame target rays laid out exactly as the
+reference's ``lib/datasets/enerf_utils.py:60-71`` ('test' branch) produces them.
+"""
+import math
+
+import numpy as np
+import torch
+
+
+def randomize_bn_(module_or_sd, seed=1):
+    """Non-trivial BN so that folding bugs cannot hide behind the identity default."""
+    g = torch.Generator().manual_seed(seed)
+    sd = module_or_sd.state_dict() if hasattr(module_or_sd, "state_dict") else module_or_sd
+    with torch.no_grad():
+        for k in sorted(sd.keys()):
+            v = sd[k]
+            if k.endswith("running_mean"):
+                v.copy_(0.1 * torch.randn(v.shape, generator=g))
+            elif k.endswith("running_var"):
+                v.copy_(0.5 + torch.rand(v.shape, generator=g))
+            elif ".bn." in k or _is_deconv_bn(k):
+                if k.endswith(".weight"):
+                    v.copy_(0.5 + torch.rand(v.shape, generator=g))
+                elif k.endswith(".bias"):
+                    v.copy_(0.1 * torch.randn(v.shape, generator=g))
+    return module_or_sd
+
+
+def _is_deconv_bn(k):
+    # cost_reg_{i}.conv{7,9,11}.1.{weight,bias} are BatchNorm3d affine parameters
+    parts = k.split(".")
+    return len(parts) == 4 and parts[0].startswith("cost_reg_") and parts[1] in ("conv7", "conv9", "conv11") \
+        and parts[2] == "1"
+
+
+def _rodrigues(axis, angle):
+    axis = axis / np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + math.sin(angle) * K + (1 - math.cos(angle)) * (K @ K)
+
+
+def full_frame_rays(tar_ext, tar_ixt, H, W, scale=1.0, row0=0, row1=None):
+    """(Hs*Ws, 8) float32 rays at ``scale`` resolution: origin(3), un-normalised dir(3), u, v.
+    dir = [u, v, 1] @ (K^-1)^T @ R_c2w^T   (lib/datasets/enerf_utils.py:26-32, 60-70)."""
+    K = np.array(tar_ixt, dtype=np.float64).copy()
+    if scale != 1.0:
+        K[:2] *= scale
+    Hs, Ws = int(H * scale), int(W * scale)
+    row1 = Hs if row1 is None else row1
+    c2w = np.linalg.inv(np.asarray(tar_ext, dtype=np.float64))
+    X, Y = np.meshgrid(np.arange(Ws), np.arange(row0, row1))
+    pix = np.stack([X, Y, np.ones_like(X)], axis=-1).astype(np.float64)
+    dirs = pix @ (np.linalg.inv(K).T @ c2w[:3, :3].T)
+    orig = np.broadcast_to(c2w[:3, 3], dirs.shape)
+    rays = np.concatenate([orig, dirs, X[..., None], Y[..., None]], axis=-1)
+    return rays.astype(np.float32).reshape(-1, 8)
+
+
+def make_batch(H, W, S, cfg, seed=2, near_far=(2.0, 6.0), B=1):
+    """The reference ``batch`` dict as CPU fp32 tensors."""
+    assert B == 1, "inference batch is 1 (run.py:57-76)"
+    c = cfg.enerf.cas_config
+    g = torch.Generator().manual_seed(seed)
+    src_inps = 2.0 * torch.rand((B, S, 3, H, W), generator=g) - 1.0
+    rng = np.random.RandomState(seed + 1)
+    ixts = []
+    for _ in range(S + 1):
+        f = rng.uniform(1.0, 1.5) * W
+        cx = W / 2 * (1 + rng.uniform(-0.02, 0.02))
+        cy = H / 2 * (1 + rng.uniform(-0.02, 0.02))
+        ixts.append(np.array([[f, 0, cx], [0, f, cy], [0, 0, 1]], dtype=np.float64))
+    rng = np.random.RandomState(seed + 2)
+    exts = []
+    for _ in range(S):
+        R = _rodrigues(rng.normal(size=3), math.radians(rng.uniform(0, 5)))
+        t = rng.uniform(-0.15, 0.15, size=3) * near_far[0]
+        E = np.eye(4)
+        E[:3, :3], E[:3, 3] = R, t
+        exts.append(E)
+    tar_ext, tar_ixt = np.eye(4), ixts[S]
+    batch = {
+        "src_inps": src_inps,
+        "src_exts": torch.tensor(np.stack(exts)[None], dtype=torch.float32),
+        "src_ixts": torch.tensor(np.stack(ixts[:S])[None], dtype=torch.float32),
+        "tar_ext": torch.tensor(tar_ext[None], dtype=torch.float32),
+        "tar_ixt": torch.tensor(tar_ixt[None], dtype=torch.float32),
+        "near_far": torch.tensor([list(near_far)], dtype=torch.float32),
+    }
+    for i in range(c.num):
+        batch[f"rays_{i}"] = torch.from_numpy(full_frame_rays(tar_ext, tar_ixt, H, W, c.render_scale[i]))[None]
+    return batch
+
+
+def psnr(a, b):
+    """10*log10(1/MSE), data_range 1 (lib/evaluators/enerf.py:71 uses skimage psnr, data_range=1)."""
+    mse = torch.mean((a.double() - b.double()) ** 2).item()
+    return float("inf") if mse == 0 else 10.0 * math.log10(1.0 / mse)

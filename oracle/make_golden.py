@@ -1,0 +1,94 @@
+"""TEST INFRASTRUCTURE -- mint tests/golden/*.pt by running the UNMODIFIED reference on CPU.
+
+Usage (authoring container only; needs /root/reference or $ENERF_REF):
+    python oracle/make_golden.py            # writes every case listed in CASES
+    python oracle/make_golden.py c1_nocascade
+
+The reference's cfg is a process-global built at import (lib/config/config.py:191-201), hence one
+subprocess per case.  Each fixture holds: the cfg overrides, the weights (state_dict of the
+reference's own Network under torch.manual_seed(0) + randomised BN), the synthetic batch, the
+reference outputs (Network.forward, network.py:76-113) and a few per-stage intermediates obtained
+by calling the reference's own functions in the order forward() does.
+"""
+import os
+import subprocess
+import sys
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _ROOT)
+
+# name -> (yaml, cfg opts, make_cfg kind + overrides, H, W, S)
+CASES = {
+    # BASELINE.json configs[0]: 64x80 crop, 2 src views, 8 planes, 1 cascade level
+    "c1_nocascade": dict(yaml="configs/enerf/dtu_pretrain_nocascade.yaml",
+                         opts=["enerf.cas_config.volume_planes", "8,"],
+                         kind="nocascade", over=dict(volume_planes=[8]), H=64, W=80, S=2),
+    # reduced configs[1]: 2-level cascade, both levels rendered (exercises nerf_0 with Ns=8, fc=35)
+    "c2_small_cascade": dict(yaml="configs/enerf/dtu_pretrain.yaml",
+                             opts=["enerf.cas_config.volume_planes", "8,8"],
+                             kind="cascade", over=dict(volume_planes=[8, 8]), H=64, W=96, S=3),
+    # reduced headline run (README.md:114: render_if False,True), 4 source views
+    "c2_headline_small": dict(yaml="configs/enerf/dtu_pretrain.yaml",
+                              opts=["enerf.cas_config.volume_planes", "16,8", "enerf.cas_config.render_if", "False,True"],
+                              kind="cascade", over=dict(volume_planes=[16, 8], render_if=[False, True]), H=96, W=64, S=4),
+}
+
+
+def run_case(name):
+    import torch
+    from oracle.ref_loader import load_reference
+    from enerf_b200 import config as bcfg
+    from enerf_b200 import synthetic
+
+    case = CASES[name]
+    cfg, mods = load_reference(case["yaml"], case["opts"])
+    utils = mods["utils"]
+    torch.manual_seed(0)
+    net = mods["network"].Network().eval()
+    synthetic.randomize_bn_(net, seed=1)
+    my_cfg = (bcfg.nocascade_cfg if case["kind"] == "nocascade" else bcfg.make_cfg)(**case["over"])
+    batch = synthetic.make_batch(case["H"], case["W"], case["S"], my_cfg, seed=2)
+    # cross-check the ray generator against the reference's own (lib/datasets/enerf_utils.py:25-71)
+    import numpy as np
+    for i in range(cfg.enerf.cas_config.num):
+        r, _, _ = mods["enerf_utils"].build_rays(np.zeros((case["H"], case["W"], 3), np.float32),
+                                                 batch["tar_ext"][0].numpy().astype(np.float64),
+                                                 batch["tar_ixt"][0].numpy().astype(np.float64),
+                                                 np.ones((case["H"], case["W"]), np.uint8), i, "test")
+        assert np.abs(r - batch[f"rays_{i}"][0].numpy()).max() < 1e-5, "ray generator mismatch"
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        out = net({k: v.clone() for k, v in batch.items()})
+        mid = {}
+        feats = net.forward_feat(batch["src_inps"])
+        mid["feat_level_0"] = feats["level_0"]
+        depth = std = nf = None
+        for i in range(cfg.enerf.cas_config.num):
+            var, dv, nf = utils.build_feature_volume(feats[f"level_{i}"], batch, D=cfg.enerf.cas_config.volume_planes[i],
+                                                     depth=depth, std=std, near_far=nf, level=i)
+            vol, prob = getattr(net, f"cost_reg_{i}")(var)
+            depth, std = utils.depth_regression(prob, dv, i, batch)
+            if i == 0:
+                mid["variance_0"] = var
+            mid.update({f"near_far_{i}": nf, f"depth_prob_{i}": prob, f"depth_{i}": depth, f"std_{i}": std})
+            if i == cfg.enerf.cas_config.num - 1:
+                mid[f"feat_volume_{i}"] = vol
+    fixture = {
+        "case": name, "cfg_kind": case["kind"], "cfg_over": case["over"], "H": case["H"], "W": case["W"], "S": case["S"],
+        "state_dict": {k: v.clone() for k, v in net.state_dict().items()},
+        "batch": batch,
+        "out": {k: v.clone() for k, v in out.items()},
+        "mid": {k: v.clone() for k, v in mid.items()},
+        "reference_commit": "5a084e9", "torch": torch.__version__,
+    }
+    path = os.path.join(_ROOT, "tests", "golden", name + ".pt")
+    torch.save(fixture, path)
+    print(name, "->", path, os.path.getsize(path) // 1024, "KiB;", {k: tuple(v.shape) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "--one":
+        run_case(sys.argv[2])
+    else:
+        for n in (sys.argv[1:] or list(CASES)):
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), "--one", n])
