@@ -1,0 +1,151 @@
+"""ctypes binding of libenerf_b200.so (include/enerf_b200.h).  Thin on purpose: unpack torch tensors
+to raw device pointers, pass the current CUDA stream, turn error codes into Python exceptions.
+
+There is no fallback of any kind: if the library is missing or cannot be loaded the import of the
+compute path raises (ImportError), and every entry point raises on a non-CUDA tensor.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libenerf_b200.so")
+
+MAX_VIEWS, MAX_LEVELS = 8, 4
+CAM_FLOATS = MAX_LEVELS * MAX_VIEWS * 12 + MAX_VIEWS * 12 + MAX_LEVELS * MAX_VIEWS * 9 + MAX_VIEWS * 3 + 3 + 2
+
+ERRORS = {-1: ValueError, -2: RuntimeError, -3: RuntimeError, -4: NotImplementedError}
+
+_lib = None
+
+_vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+_SIGS = {
+    "enerf_abi_version": (_i, []),
+    "enerf_last_error": (ctypes.c_char_p, []),
+    "enerf_camera_setup": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, ctypes.POINTER(ctypes.c_float), _vp, _vp]),
+    "enerf_feature_net_workspace_bytes": (_sz, [_i, _i, _i]),
+    "enerf_feature_net": (_i, [ctypes.POINTER(_vp), _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "enerf_pack_img_feat": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "enerf_depth_hypotheses": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "enerf_cost_volume": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "enerf_cost_reg_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "enerf_cost_reg": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "enerf_depth_regress": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "enerf_render_rays": (_i, [_vp, _i, ctypes.POINTER(_vp), _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i,
+                               _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+}
+EXPORTS = tuple(_SIGS)
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises ImportError when the CUDA library is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not found: build it with `python -m enerf_b200.build` "
+                              "(there is no CPU fallback for the render path)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        if handle.enerf_abi_version() != 1:
+            raise ImportError("libenerf_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = lib().enerf_last_error().decode("utf-8", "replace")
+        raise ERRORS.get(rc, RuntimeError)(f"{what} failed ({rc}): {msg}")
+
+
+def ptr(t, allow_none=False):
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError("null tensor")
+    if not t.is_cuda:
+        raise ValueError("enerf_b200 kernels take CUDA tensors only (no CPU fallback)")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise ValueError(f"expected contiguous float32, got {t.dtype} contiguous={t.is_contiguous()}")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr_array(tensors):
+    arr = (_vp * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = ptr(t, allow_none=True)
+    return arr
+
+
+# ---- one wrapper per entry point -------------------------------------------------------------
+def camera_setup(src_exts, src_ixts, tar_ext, tar_ixt, near_far, scales, cam):
+    S = src_exts.shape[0]
+    n_levels = len(scales)
+    flat = (ctypes.c_float * (n_levels * 3))(*[float(x) for lv in scales for x in lv])
+    _check(lib().enerf_camera_setup(ptr(src_exts), ptr(src_ixts), ptr(tar_ext), ptr(tar_ixt), ptr(near_far), S, n_levels,
+                                    flat, ptr(cam), stream()), "enerf_camera_setup")
+
+
+def feature_net_workspace_bytes(S, H, W):
+    return lib().enerf_feature_net_workspace_bytes(S, H, W)
+
+
+def feature_net(weights, src_inps, feat_l0, feat_l1, feat_l2, workspace):
+    S, _, H, W = src_inps.shape
+    _check(lib().enerf_feature_net(ptr_array(weights), len(weights), ptr(src_inps), S, H, W, ptr(feat_l0), ptr(feat_l1),
+                                   ptr(feat_l2), workspace.data_ptr(), workspace.numel() * workspace.element_size(), stream()),
+           "enerf_feature_net")
+
+
+def pack_img_feat(feat, src_inps, out):
+    S, Hr, Wr, C = feat.shape
+    H, W = src_inps.shape[-2:]
+    _check(lib().enerf_pack_img_feat(ptr(feat), C, ptr(src_inps), S, H, W, Hr, Wr, ptr(out), stream()), "enerf_pack_img_feat")
+
+
+def depth_hypotheses(cam, prev_depth, prev_std, prev_nf, h, w, D, depth_inv, ends, nf_out):
+    hp, wp = (prev_depth.shape[-2:] if prev_depth is not None else (0, 0))
+    _check(lib().enerf_depth_hypotheses(ptr(cam), ptr(prev_depth, True), ptr(prev_std, True), ptr(prev_nf, True), hp, wp, h, w, D,
+                                        int(depth_inv), ptr(ends), ptr(nf_out), stream()), "enerf_depth_hypotheses")
+
+
+def cost_volume(cam, level, feat, ends, D, h, w, depth_inv, variance):
+    S, hs, ws, C = feat.shape
+    _check(lib().enerf_cost_volume(ptr(cam), level, ptr(feat), S, C, hs, ws, ptr(ends), D, h, w, int(depth_inv), ptr(variance),
+                                   stream()), "enerf_cost_volume")
+
+
+def cost_reg_workspace_bytes(deep, D, h, w):
+    return lib().enerf_cost_reg_workspace_bytes(int(deep), D, h, w)
+
+
+def cost_reg(weights, deep, variance, feat_vol, depth_prob, workspace):
+    D, h, w, C = variance.shape
+    _check(lib().enerf_cost_reg(ptr_array(weights), len(weights), int(deep), C, ptr(variance), D, h, w, ptr(feat_vol, True),
+                                ptr(depth_prob), workspace.data_ptr(), workspace.numel() * workspace.element_size(), stream()),
+           "enerf_cost_reg")
+
+
+def depth_regress(depth_prob, ends, depth_inv, depth, std, depth_mvs):
+    D, h, w = depth_prob.shape
+    _check(lib().enerf_depth_regress(ptr(depth_prob), ptr(ends), D, h, w, int(depth_inv), ptr(depth), ptr(std), ptr(depth_mvs, True),
+                                     stream()), "enerf_depth_regress")
+
+
+def render_rays(cam, level, weights, rays, depth, std, near_far, feat_vol, img_feat_rgb, feat_ch, num_samples, depth_inv,
+                white_bkgd, viewdir_agg, out_rgb, out_depth, out_weights):
+    n_rays = rays.shape[0]
+    hv, wv = depth.shape[-2:]
+    D = feat_vol.shape[0]
+    S, Hr, Wr, _ = img_feat_rgb.shape
+    _check(lib().enerf_render_rays(ptr(cam), level, ptr_array(weights), len(weights), ptr(rays), n_rays, ptr(depth), ptr(std),
+                                   ptr(near_far), hv, wv, ptr(feat_vol), D, ptr(img_feat_rgb), S, Hr, Wr, feat_ch, num_samples,
+                                   int(depth_inv), int(white_bkgd), int(viewdir_agg), ptr(out_rgb), ptr(out_depth),
+                                   ptr(out_weights), stream()), "enerf_render_rays")

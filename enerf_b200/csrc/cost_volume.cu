@@ -1,0 +1,205 @@
+// cost_volume.cu -- depth hypotheses, fused homography-warp + variance cost volume, depth regression.
+//
+//  enerf_depth_hypotheses : get_depth_values      /root/reference/lib/networks/enerf/utils.py:98-151
+//  enerf_cost_volume      : build_feature_volume  utils.py:322-349  (homo_warp :57-95 x S, variance :337-345)
+//  enerf_depth_regress    : depth_regression      utils.py:658-663
+//
+// The cost volume is a pure gather: per target voxel, S bilinear 4-tap reads of a C-channel source
+// pixel (zeros padding, align_corners=True).  Channels-last sources make every tap one contiguous
+// C*4-byte read; C/4 adjacent lanes share a voxel and read the float4 slices of the same tap, so a
+// warp issues full 128-byte (C=32) or 64-byte (C=16) segments.  Sum and sum of squares live in
+// registers; the S warped volumes and the sampling grid of the reference are never materialised.
+// Roofline: L2/HBM (AI ~ 1 FLOP/B); algorithmic bytes per launch = S*hs*ws*C*4 (read once) +
+// D*h*w*C*4 (written once).
+#include "common.cuh"
+
+namespace enerf {
+
+// plane i of D between end points (a,b): linear in disparity when depth_inv, else linear in depth
+// (utils.py:104-111 level 0, :135-146 level >0)
+__device__ __forceinline__ float plane_depth(float a, float b, int i, int D, bool depth_inv) {
+  const float t = linspace01(i, D);
+  if (depth_inv) {
+    const float ia = 1.0f / a, ib = 1.0f / b;
+    return 1.0f / (ia + t * (ib - ia));
+  }
+  return a + t * (b - a);
+}
+
+__global__ void depth_hypotheses_kernel(const EnerfCam* __restrict__ cam, const float* __restrict__ prev_depth,
+                                        const float* __restrict__ prev_std, const float* __restrict__ prev_nf, int hp,
+                                        int wp, int h, int w, int D, int depth_inv, float* __restrict__ ends,
+                                        float* __restrict__ nf_out) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= h * w) return;
+  const int x = pix % w, y = pix / w;
+  float a, b;
+  if (prev_depth == nullptr) {
+    a = cam->near_far[0];
+    b = cam->near_far[1];
+  } else {
+    const float d = bilinear_ac(prev_depth, hp, wp, h, w, y, x);
+    const float s = bilinear_ac(prev_std, hp, wp, h, w, y, x);
+    const float n0 = bilinear_ac(prev_nf, hp, wp, h, w, y, x);
+    const float n1 = bilinear_ac(prev_nf + (size_t)hp * wp, hp, wp, h, w, y, x);
+    // previous level lives in disparity space: [d+s, d-s] clamped into its near_far, then inverted
+    const float lo = fminf(d + s, n0), hi = fmaxf(d - s, n1);
+    a = 1.0f / lo;
+    b = 1.0f / hi;
+  }
+  ends[pix] = a;
+  ends[(size_t)h * w + pix] = b;
+  float v0 = plane_depth(a, b, 0, D, depth_inv), v1 = plane_depth(a, b, D - 1, D, depth_inv);
+  if (depth_inv) {
+    v0 = 1.0f / fmaxf(v0, 1e-6f);
+    v1 = 1.0f / fmaxf(v1, 1e-6f);
+  }
+  nf_out[pix] = v0;
+  nf_out[(size_t)h * w + pix] = v1;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) cost_volume_kernel(const EnerfCam* __restrict__ cam, int level,
+                                                          const float* __restrict__ feat, int S, int hs, int ws,
+                                                          const float* __restrict__ ends, int D, int h, int w,
+                                                          int depth_inv, float* __restrict__ var_out) {
+  constexpr int CG = C / 4;
+  __shared__ float Hm[ENERF_MAX_VIEWS * 12];
+  for (int e = threadIdx.x; e < S * 12; e += blockDim.x) Hm[e] = cam->homo[level][e / 12][e % 12];
+  __syncthreads();
+  const long long total = (long long)D * h * w * CG;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int g = (int)(t % CG);
+  const long long vox = t / CG;
+  const int x = (int)(vox % w), y = (int)((vox / w) % h), d = (int)(vox / ((long long)w * h));
+  const int pix = y * w + x;
+  const float depth = plane_depth(__ldg(ends + pix), __ldg(ends + (size_t)h * w + pix), d, D, depth_inv);
+  const float fx = (float)x, fy = (float)y;
+  const float wsm1 = (float)(ws - 1), hsm1 = (float)(hs - 1);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < S; ++s) {
+    const float* M = Hm + s * 12;
+    const float q0 = (M[0] * fx + M[1] * fy + M[2]) + M[3] / depth;
+    const float q1 = (M[4] * fx + M[5] * fy + M[6]) + M[7] / depth;
+    const float q2 = (M[8] * fx + M[9] * fy + M[10]) + M[11] / depth;
+    const float qz = fmaxf(q2, 1e-6f);
+    const float xs = q0 / qz, ys = q1 / qz;
+    // normalise to [-1,1] (utils.py:83-84) and un-normalise as grid_sample(align_corners=True) does
+    const float gx = xs / (wsm1 / 2.0f) - 1.0f, gy = ys / (hsm1 / 2.0f) - 1.0f;
+    const float ix = ((gx + 1.0f) / 2.0f) * wsm1, iy = ((gy + 1.0f) / 2.0f) * hsm1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ix > -1.0f && ix < (float)ws && iy > -1.0f && iy < (float)hs) {  // false for NaN
+      const float fx0 = floorf(ix), fy0 = floorf(iy);
+      const int x0 = (int)fx0, y0 = (int)fy0;
+      // ATen grid_sampler weights: nw = (x_se - x)(y_se - y), ne = (x - x_sw)(y_sw - y), ...
+      const float txr = (fx0 + 1.f) - ix, txl = ix - fx0, tyb = (fy0 + 1.f) - iy, tyt = iy - fy0;
+      const float w_nw = txr * tyb, w_ne = txl * tyb, w_sw = txr * tyt, w_se = txl * tyt;
+      const float* base = feat + ((size_t)s * hs * ws) * C + g * 4;
+      const bool xl = x0 >= 0, xr = x0 + 1 < ws, yt = y0 >= 0, yb = y0 + 1 < hs;
+      if (yt && xl) {
+        const float4 p = ldg4(base + ((size_t)y0 * ws + x0) * C);
+        v.x = fmaf(p.x, w_nw, v.x), v.y = fmaf(p.y, w_nw, v.y), v.z = fmaf(p.z, w_nw, v.z), v.w = fmaf(p.w, w_nw, v.w);
+      }
+      if (yt && xr) {
+        const float4 p = ldg4(base + ((size_t)y0 * ws + x0 + 1) * C);
+        v.x = fmaf(p.x, w_ne, v.x), v.y = fmaf(p.y, w_ne, v.y), v.z = fmaf(p.z, w_ne, v.z), v.w = fmaf(p.w, w_ne, v.w);
+      }
+      if (yb && xl) {
+        const float4 p = ldg4(base + ((size_t)(y0 + 1) * ws + x0) * C);
+        v.x = fmaf(p.x, w_sw, v.x), v.y = fmaf(p.y, w_sw, v.y), v.z = fmaf(p.z, w_sw, v.z), v.w = fmaf(p.w, w_sw, v.w);
+      }
+      if (yb && xr) {
+        const float4 p = ldg4(base + ((size_t)(y0 + 1) * ws + x0 + 1) * C);
+        v.x = fmaf(p.x, w_se, v.x), v.y = fmaf(p.y, w_se, v.y), v.z = fmaf(p.z, w_se, v.z), v.w = fmaf(p.w, w_se, v.w);
+      }
+    }
+    s1.x += v.x, s1.y += v.y, s1.z += v.z, s1.w += v.w;
+    s2.x += v.x * v.x, s2.y += v.y * v.y, s2.z += v.z * v.z, s2.w += v.w * v.w;
+  }
+  const float fS = (float)S;
+  float4 o;
+  {
+    float m;
+    m = s1.x / fS, o.x = s2.x / fS - m * m;
+    m = s1.y / fS, o.y = s2.y / fS - m * m;
+    m = s1.z / fS, o.z = s2.z / fS - m * m;
+    m = s1.w / fS, o.w = s2.w / fS - m * m;
+  }
+  *reinterpret_cast<float4*>(var_out + (size_t)vox * C + g * 4) = o;
+}
+
+__global__ void depth_regress_kernel(const float* __restrict__ prob, const float* __restrict__ ends, int D, int h, int w,
+                                     int depth_inv, float* __restrict__ depth_out, float* __restrict__ std_out,
+                                     float* __restrict__ mvs_out) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hw = h * w;
+  if (pix >= hw) return;
+  const float a = ends[pix], b = ends[(size_t)hw + pix];
+  float mx = -INFINITY;
+  for (int d = 0; d < D; ++d) mx = fmaxf(mx, __ldg(prob + (size_t)d * hw + pix));
+  float den = 0.f;
+  for (int d = 0; d < D; ++d) den += expf(__ldg(prob + (size_t)d * hw + pix) - mx);
+  float mean = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float p = expf(__ldg(prob + (size_t)d * hw + pix) - mx) / den;
+    float v = plane_depth(a, b, d, D, depth_inv);
+    if (depth_inv) v = 1.0f / fmaxf(v, 1e-6f);
+    mean += p * v;
+  }
+  float var = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float p = expf(__ldg(prob + (size_t)d * hw + pix) - mx) / den;
+    float v = plane_depth(a, b, d, D, depth_inv);
+    if (depth_inv) v = 1.0f / fmaxf(v, 1e-6f);
+    const float e = v - mean;
+    var += p * (e * e);
+  }
+  depth_out[pix] = mean;
+  std_out[pix] = sqrtf(fmaxf(var, 1e-10f));
+  if (mvs_out) mvs_out[pix] = depth_inv ? 1.0f / mean : mean;
+}
+
+}  // namespace enerf
+
+extern "C" int enerf_depth_hypotheses(const EnerfCam* cam, const float* prev_depth, const float* prev_std,
+                                      const float* prev_near_far, int hp, int wp, int h, int w, int D, int depth_inv,
+                                      float* ends, float* near_far_out, void* stream) {
+  using namespace enerf;
+  ENERF_REQUIRE(cam && ends && near_far_out, ENERF_EINVAL, "depth_hypotheses: null pointer");
+  ENERF_REQUIRE(h > 0 && w > 0 && D >= 1, ENERF_EINVAL, "depth_hypotheses: bad dims h=%d w=%d D=%d", h, w, D);
+  if (prev_depth) ENERF_REQUIRE(prev_std && prev_near_far && hp > 0 && wp > 0, ENERF_EINVAL, "depth_hypotheses: prev level incomplete");
+  depth_hypotheses_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(cam, prev_depth, prev_std, prev_near_far,
+                                                                                 hp, wp, h, w, D, depth_inv, ends, near_far_out);
+  ENERF_CHECK_LAUNCH("depth_hypotheses");
+  return ENERF_OK;
+}
+
+extern "C" int enerf_cost_volume(const EnerfCam* cam, int level, const float* feat, int S, int C, int hs, int ws,
+                                 const float* ends, int D, int h, int w, int depth_inv, float* variance, void* stream_) {
+  using namespace enerf;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ENERF_REQUIRE(cam && feat && ends && variance, ENERF_EINVAL, "cost_volume: null pointer");
+  ENERF_REQUIRE(level >= 0 && level < ENERF_MAX_LEVELS, ENERF_EINVAL, "cost_volume: level %d", level);
+  ENERF_REQUIRE(S >= 1 && S <= ENERF_MAX_VIEWS, ENERF_EINVAL, "cost_volume: n_views %d not in [1,%d]", S, ENERF_MAX_VIEWS);
+  const long long total = (long long)D * h * w * (C / 4);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  switch (C) {
+    case 8: cost_volume_kernel<8><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance); break;
+    case 16: cost_volume_kernel<16><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance); break;
+    case 32: cost_volume_kernel<32><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance); break;
+    default: ENERF_REQUIRE(false, ENERF_EUNSUPPORTED, "cost_volume: C=%d not in {8,16,32}", C);
+  }
+  ENERF_CHECK_LAUNCH("cost_volume");
+  return ENERF_OK;
+}
+
+extern "C" int enerf_depth_regress(const float* depth_prob, const float* ends, int D, int h, int w, int depth_inv,
+                                   float* depth, float* std, float* depth_mvs, void* stream) {
+  using namespace enerf;
+  ENERF_REQUIRE(depth_prob && ends && depth && std, ENERF_EINVAL, "depth_regress: null pointer");
+  depth_regress_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
+                                                                              depth_mvs);
+  ENERF_CHECK_LAUNCH("depth_regress");
+  return ENERF_OK;
+}

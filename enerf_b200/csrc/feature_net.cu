@@ -1,0 +1,203 @@
+// feature_net.cu -- FeatureNet.forward (/root/reference/lib/networks/enerf/feature_net.py:27-36)
+// as 11 launches of hand-written kernels: 8 direct convolutions (conv.cuh) + toplayer 1x1 +
+// two fused {lateral 1x1 conv + bilinear x2 up-sample (align_corners) + add} kernels
+// (feature_net.py:24-25,32-33).  The S source images ride on the depth axis of the conv template.
+#include "conv.cuh"
+
+namespace enerf {
+
+//            CIN COUT KD KH ST  TZ TY  TX PY PX COT CCH  RELU  PLANAR
+using Conv00 = ConvTraits<3, 8, 1, 3, 1, 1, 32, 32, 2, 4, 8, 3, true, true>;
+using Conv01 = ConvTraits<8, 8, 1, 3, 1, 1, 32, 32, 2, 4, 8, 8, true, false>;
+using Conv10 = ConvTraits<8, 16, 1, 5, 2, 1, 16, 32, 1, 4, 8, 8, true, false>;
+using Conv11 = ConvTraits<16, 16, 1, 3, 1, 1, 32, 32, 2, 4, 8, 8, true, false>;
+using Conv20 = ConvTraits<16, 32, 1, 5, 2, 1, 8, 32, 1, 4, 8, 8, true, false>;
+using Conv21 = ConvTraits<32, 32, 1, 3, 1, 1, 16, 32, 2, 4, 8, 8, true, false>;
+using Top = ConvTraits<32, 32, 1, 1, 1, 1, 16, 32, 2, 4, 8, 8, false, false>;
+using Smooth1 = ConvTraits<32, 16, 1, 3, 1, 1, 32, 32, 2, 4, 8, 8, false, false>;
+using Smooth0 = ConvTraits<32, 8, 1, 3, 1, 1, 32, 32, 2, 4, 8, 8, false, false>;
+
+// out (N,H,W,32) = bias + W[CIN][32] . lat_in (N,H,W,CIN)  +  bilinear_x2(up_in (N,H/2,W/2,32))
+// thread = (pixel, group of 8 output channels)
+template <int CIN>
+__global__ void __launch_bounds__(256) lateral_upadd_kernel(const float* __restrict__ lat_in, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, const float* __restrict__ up_in,
+                                                            float* __restrict__ out, int N, int H, int W) {
+  __shared__ __align__(16) float w_s[CIN * 32];
+  __shared__ float b_s[32];
+  for (int e = threadIdx.x; e < CIN * 32; e += blockDim.x) w_s[e] = w[e];
+  if (threadIdx.x < 32) b_s[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long long total = (long long)N * H * W * 4;
+  const int hi = H / 2, wi = W / 2;
+  const float rh = (H > 1) ? (float)(hi - 1) / (float)(H - 1) : 0.f;
+  const float rw = (W > 1) ? (float)(wi - 1) / (float)(W - 1) : 0.f;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t & 3);
+    const long long pix = t >> 2;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = b_s[g * 8 + c];
+    const float* ip = lat_in + pix * CIN;
+#pragma unroll
+    for (int q = 0; q < CIN / 4; ++q) {
+      const float4 v = ldg4(ip + 4 * q);
+      const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w0 = *reinterpret_cast<const float4*>(w_s + (4 * q + j) * 32 + g * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(w_s + (4 * q + j) * 32 + g * 8 + 4);
+        acc[0] = fmaf(xv[j], w0.x, acc[0]);
+        acc[1] = fmaf(xv[j], w0.y, acc[1]);
+        acc[2] = fmaf(xv[j], w0.z, acc[2]);
+        acc[3] = fmaf(xv[j], w0.w, acc[3]);
+        acc[4] = fmaf(xv[j], w1.x, acc[4]);
+        acc[5] = fmaf(xv[j], w1.y, acc[5]);
+        acc[6] = fmaf(xv[j], w1.z, acc[6]);
+        acc[7] = fmaf(xv[j], w1.w, acc[7]);
+      }
+    }
+    // bilinear x2 with align_corners=True (ATen upsample_bilinear2d lambdas)
+    const float h1r = rh * (float)y, w1r = rw * (float)x;
+    const int h1 = (int)h1r, w1 = (int)w1r;
+    const int h1p = (h1 < hi - 1) ? 1 : 0, w1p = (w1 < wi - 1) ? 1 : 0;
+    const float h1l = h1r - (float)h1, h0l = 1.f - h1l, w1l = w1r - (float)w1, w0l = 1.f - w1l;
+    const float* u00 = up_in + (((size_t)n * hi + h1) * wi + w1) * 32 + g * 8;
+    const float* u01 = u00 + (size_t)w1p * 32;
+    const float* u10 = u00 + (size_t)h1p * wi * 32;
+    const float* u11 = u10 + (size_t)w1p * 32;
+    float up[8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float4 a = ldg4(u00 + 4 * q), b = ldg4(u01 + 4 * q), c = ldg4(u10 + 4 * q), dd = ldg4(u11 + 4 * q);
+      up[4 * q + 0] = h0l * (w0l * a.x + w1l * b.x) + h1l * (w0l * c.x + w1l * dd.x);
+      up[4 * q + 1] = h0l * (w0l * a.y + w1l * b.y) + h1l * (w0l * c.y + w1l * dd.y);
+      up[4 * q + 2] = h0l * (w0l * a.z + w1l * b.z) + h1l * (w0l * c.z + w1l * dd.z);
+      up[4 * q + 3] = h0l * (w0l * a.w + w1l * b.w) + h1l * (w0l * c.w + w1l * dd.w);
+    }
+    float4* o = reinterpret_cast<float4*>(out + pix * 32 + g * 8);
+    // reference order: interpolate(x) + lateral(y)   (feature_net.py:25)
+    o[0] = make_float4(up[0] + acc[0], up[1] + acc[1], up[2] + acc[2], up[3] + acc[3]);
+    o[1] = make_float4(up[4] + acc[4], up[5] + acc[5], up[6] + acc[6], up[7] + acc[7]);
+  }
+}
+
+// cat(feat, unpreprocess(src)) -> (S,Hr,Wr,C+4); thread per output pixel
+__global__ void pack_img_feat_kernel(const float* __restrict__ feat, int C, const float* __restrict__ src, int S, int H,
+                                     int W, int Hr, int Wr, float* __restrict__ out) {
+  const long long total = (long long)S * Hr * Wr;
+  const int CP = C + 4;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(t % Wr), y = (int)((t / Wr) % Hr), s = (int)(t / ((long long)Wr * Hr));
+    const float* f = feat + t * C;
+    float* o = out + t * CP;
+    for (int q = 0; q < C / 4; ++q) reinterpret_cast<float4*>(o)[q] = ldg4(f + 4 * q);
+    float rgb[3];
+    for (int c = 0; c < 3; ++c) {
+      const float* plane = src + ((size_t)s * 3 + c) * H * W;
+      if (Hr == H && Wr == W) {
+        rgb[c] = __ldg(plane + (size_t)y * W + x) * 0.5f + 0.5f;
+      } else {
+        // unpreprocess does the affine map first, then resizes (utils.py:609-611); the map is
+        // affine so interpolating first differs only by fp32 rounding of the 4-tap blend.
+        const float rh = (Hr > 1) ? (float)(H - 1) / (float)(Hr - 1) : 0.f;
+        const float rw = (Wr > 1) ? (float)(W - 1) / (float)(Wr - 1) : 0.f;
+        const float h1r = rh * (float)y, w1r = rw * (float)x;
+        const int h1 = (int)h1r, w1 = (int)w1r;
+        const int h1p = (h1 < H - 1) ? 1 : 0, w1p = (w1 < W - 1) ? 1 : 0;
+        const float h1l = h1r - (float)h1, h0l = 1.f - h1l, w1l = w1r - (float)w1, w0l = 1.f - w1l;
+        const float* r0 = plane + (size_t)h1 * W + w1;
+        const float* r1 = r0 + (size_t)h1p * W;
+        const float a = __ldg(r0) * 0.5f + 0.5f, b = __ldg(r0 + w1p) * 0.5f + 0.5f;
+        const float cc = __ldg(r1) * 0.5f + 0.5f, dd = __ldg(r1 + w1p) * 0.5f + 0.5f;
+        rgb[c] = h0l * (w0l * a + w1l * b) + h1l * (w0l * cc + w1l * dd);
+      }
+    }
+    reinterpret_cast<float4*>(o + C)[0] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+  }
+}
+
+struct FeatWs {
+  float *c0a, *c0, *c1a, *c1, *c2a, *c2, *f1, *f0;
+  size_t bytes;
+};
+
+static FeatWs carve(void* base, int S, int H, int W) {
+  FeatWs ws;
+  size_t off = 0;
+  auto take = [&](size_t n_floats) {
+    float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+    off += align_up(n_floats * sizeof(float), 256);
+    return p;
+  };
+  const size_t n1 = (size_t)S * H * W, n2 = n1 / 4, n4 = n1 / 16;
+  ws.c0a = take(n1 * 8);
+  ws.c0 = take(n1 * 8);
+  ws.c1a = take(n2 * 16);
+  ws.c1 = take(n2 * 16);
+  ws.c2a = take(n4 * 32);
+  ws.c2 = take(n4 * 32);
+  ws.f1 = take(n2 * 32);
+  ws.f0 = take(n1 * 32);
+  ws.bytes = off;
+  return ws;
+}
+
+}  // namespace enerf
+
+extern "C" size_t enerf_feature_net_workspace_bytes(int n_views, int H, int W) {
+  return enerf::carve(nullptr, n_views, H, W).bytes;
+}
+
+extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const float* src_inps, int S, int H, int W,
+                                 float* feat_l0, float* feat_l1, float* feat_l2, void* workspace, size_t workspace_bytes,
+                                 void* stream_) {
+  using namespace enerf;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ENERF_REQUIRE(wts && n_weights == 22, ENERF_EINVAL, "feature_net: expected 22 weight pointers, got %d", n_weights);
+  ENERF_REQUIRE(src_inps && feat_l0 && feat_l1 && feat_l2 && workspace, ENERF_EINVAL, "feature_net: null pointer");
+  ENERF_REQUIRE(S >= 1 && H > 0 && W > 0 && H % 4 == 0 && W % 4 == 0, ENERF_EINVAL,
+                "feature_net: H=%d W=%d must be positive multiples of 4 (S=%d)", H, W, S);
+  FeatWs ws = carve(workspace, S, H, W);
+  ENERF_REQUIRE(workspace_bytes >= ws.bytes, ENERF_EWORKSPACE, "feature_net: workspace %zu < %zu", workspace_bytes, ws.bytes);
+  const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
+  int rc;
+#define RUN(call)                 \
+  if ((rc = (call)) != ENERF_OK) return rc
+  RUN(launch_conv<Conv00>("feature_net.conv0.0", src_inps, wts[0], wts[1], ws.c0a, nullptr, S, H, W, 8, 0, stream));
+  RUN(launch_conv<Conv01>("feature_net.conv0.1", ws.c0a, wts[2], wts[3], ws.c0, nullptr, S, H, W, 8, 0, stream));
+  RUN(launch_conv<Conv10>("feature_net.conv1.0", ws.c0, wts[4], wts[5], ws.c1a, nullptr, S, H, W, 16, 0, stream));
+  RUN(launch_conv<Conv11>("feature_net.conv1.1", ws.c1a, wts[6], wts[7], ws.c1, nullptr, S, H2, W2, 16, 0, stream));
+  RUN(launch_conv<Conv20>("feature_net.conv2.0", ws.c1, wts[8], wts[9], ws.c2a, nullptr, S, H2, W2, 32, 0, stream));
+  RUN(launch_conv<Conv21>("feature_net.conv2.1", ws.c2a, wts[10], wts[11], ws.c2, nullptr, S, H4, W4, 32, 0, stream));
+  RUN(launch_conv<Top>("feature_net.toplayer", ws.c2, wts[12], wts[13], feat_l0, nullptr, S, H4, W4, 32, 0, stream));
+  {
+    const long long total = (long long)S * H2 * W2 * 4;
+    const int blocks = (int)((total + 255) / 256);
+    lateral_upadd_kernel<16><<<blocks, 256, 0, stream>>>(ws.c1, wts[14], wts[15], feat_l0, ws.f1, S, H2, W2);
+    ENERF_CHECK_LAUNCH("feature_net.lat1");
+  }
+  {
+    const long long total = (long long)S * H * W * 4;
+    const int blocks = (int)((total + 255) / 256);
+    lateral_upadd_kernel<8><<<blocks, 256, 0, stream>>>(ws.c0, wts[16], wts[17], ws.f1, ws.f0, S, H, W);
+    ENERF_CHECK_LAUNCH("feature_net.lat0");
+  }
+  RUN(launch_conv<Smooth1>("feature_net.smooth1", ws.f1, wts[18], wts[19], feat_l1, nullptr, S, H2, W2, 16, 0, stream));
+  RUN(launch_conv<Smooth0>("feature_net.smooth0", ws.f0, wts[20], wts[21], feat_l2, nullptr, S, H, W, 8, 0, stream));
+#undef RUN
+  return ENERF_OK;
+}
+
+extern "C" int enerf_pack_img_feat(const float* feat, int C, const float* src_inps, int S, int H, int W, int Hr, int Wr,
+                                   float* out, void* stream) {
+  using namespace enerf;
+  ENERF_REQUIRE(feat && src_inps && out, ENERF_EINVAL, "pack_img_feat: null pointer");
+  ENERF_REQUIRE(C % 4 == 0 && C > 0, ENERF_EINVAL, "pack_img_feat: C=%d must be a multiple of 4", C);
+  const long long total = (long long)S * Hr * Wr;
+  const int blocks = (int)((total + 255) / 256);
+  pack_img_feat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(feat, C, src_inps, S, H, W, Hr, Wr, out);
+  ENERF_CHECK_LAUNCH("pack_img_feat");
+  return ENERF_OK;
+}

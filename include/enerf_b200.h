@@ -1,0 +1,151 @@
+/* enerf_b200.h -- C ABI of libenerf_b200.so: the B200 (sm_100a) render-time hot path of ENeRF.
+ *
+ * The reference (zju3dv/ENeRF) is pure Python/PyTorch and has NO FFI; its seam for this path is the
+ * Python plugin `lib/networks/make_network.py:5-9` -> `Network.forward(batch)`
+ * (`lib/networks/enerf/network.py:76-113`).  This header is the new native seam underneath that
+ * plugin: one entry point per stage of `Network.forward`, each citing the reference lines it
+ * replaces.  The Python mirror of the plugin (enerf_b200/network.py) binds these with ctypes; the
+ * stub a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked [host].
+ *  - all tensors are fp32, dense.  Activations are channels-last: images (N,H,W,C), volumes
+ *    (D,H,W,C).  The batch inputs keep the reference's layouts (src_inps NCHW, rays (N,8), ...).
+ *  - batch size is 1 (the reference's inference loop, run.py:57-76); callers loop for B > 1.
+ *  - no allocation, no host synchronisation, no exceptions inside: work is enqueued on `stream`
+ *    (a cudaStream_t passed as void*), memory is caller-owned, workspace sizes come from the
+ *    *_workspace_bytes functions.
+ *  - return 0 on success, a negative ENERF_E* code otherwise; enerf_last_error() gives the text.
+ *  - weights are passed as a [host] array of device pointers in the order documented per stage;
+ *    they are BN-folded / re-laid-out copies produced by enerf_b200/packing.py.
+ */
+#ifndef ENERF_B200_H
+#define ENERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ENERF_API __attribute__((visibility("default")))
+#else
+#define ENERF_API
+#endif
+
+#define ENERF_ABI_VERSION 1
+#define ENERF_MAX_VIEWS 8
+#define ENERF_MAX_LEVELS 4
+
+#define ENERF_OK 0
+#define ENERF_EINVAL (-1) /* bad argument (shape not divisible, S out of range, null pointer) */
+#define ENERF_ECUDA (-2)  /* a CUDA runtime call / kernel launch failed                          */
+#define ENERF_EWORKSPACE (-3) /* workspace too small                                             */
+#define ENERF_EUNSUPPORTED (-4) /* configuration outside what the kernels were built for         */
+
+/* Per-frame camera quantities, derived ON DEVICE from the batch tensors by enerf_camera_setup so
+ * that forward() never synchronises with the host (the reference calls torch.inverse 8x per frame,
+ * utils.py:49,707,708).  Lives in device memory; 4-byte floats, no padding surprises. */
+typedef struct EnerfCam {
+  /* homo[l][s] = row-major 3x4  (K_s * diag(im_feat_scale_l,..,1)) E_s[:3] * inv([K_t*volume_scale_l E_t[:3]; 0 0 0 1])
+   * -- get_proj_mats, utils.py:35-55 */
+  float homo[ENERF_MAX_LEVELS][ENERF_MAX_VIEWS][12];
+  float src_ext[ENERF_MAX_VIEWS][12];                 /* E_s rows 0..2 (world -> source camera)          */
+  float src_ixt[ENERF_MAX_LEVELS][ENERF_MAX_VIEWS][9]; /* K_s with rows 0,1 * render_scale_l, utils.py:700-701 */
+  float src_center[ENERF_MAX_VIEWS][3];               /* inv(E_s)[:3,3], utils.py:708                    */
+  float tar_center[3];                                /* inv(E_t)[:3,3], utils.py:707                    */
+  float near_far[2];                                  /* batch['near_far'][0]                            */
+} EnerfCam;
+
+ENERF_API int enerf_abi_version(void);
+ENERF_API const char* enerf_last_error(void);
+
+/* Replaces get_proj_mats (utils.py:35-55) and the per-view torch.inverse calls of get_img_feat
+ * (utils.py:707-708).  scales [host] = n_levels x {im_feat_scale, volume_scale, render_scale}. */
+ENERF_API int enerf_camera_setup(const float* src_exts /*S,4,4*/, const float* src_ixts /*S,3,3*/,
+                       const float* tar_ext /*4,4*/, const float* tar_ixt /*3,3*/,
+                       const float* near_far /*2*/, int n_views, int n_levels,
+                       const float* scales /*[host] n_levels*3*/, EnerfCam* cam_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * FeatureNet.forward (feature_net.py:27-36) + Network.forward_feat (network.py:58-67).
+ * src_inps (S,3,H,W) NCHW in [-1,1].  H, W multiples of 4.
+ * Outputs (channels-last): feat_l0 (S,H/4,W/4,32), feat_l1 (S,H/2,W/2,16), feat_l2 (S,H,W,8).
+ * weights [host array, 22 device pointers], each conv as {w [tap][cin][cout] BN-folded, bias[cout]}:
+ *   conv0.0, conv0.1, conv1.0, conv1.1, conv2.0, conv2.1, toplayer, lat1, lat0, smooth1, smooth0.
+ */
+ENERF_API size_t enerf_feature_net_workspace_bytes(int n_views, int H, int W);
+ENERF_API int enerf_feature_net(const float* const* weights, int n_weights, const float* src_inps, int n_views,
+                      int H, int W, float* feat_l0, float* feat_l1, float* feat_l2, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* cat(im_feat, unpreprocess(src_inps)) of render_rays (network.py:28-34, utils.py:605-612):
+ * out (S,Hr,Wr,Cpad) with channels [0,C) = feat (must already be at Hr x Wr), [C,C+3) = rgb*0.5+0.5
+ * bilinearly resized (align_corners) from (H,W) to (Hr,Wr), remaining channels 0.  Cpad = C+4. */
+ENERF_API int enerf_pack_img_feat(const float* feat /*S,Hr,Wr,C*/, int C, const float* src_inps /*S,3,H,W*/,
+                        int n_views, int H, int W, int Hr, int Wr, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * get_depth_values (utils.py:98-151): per-pixel plane end points of a level.
+ *   level 0 (prev_depth == NULL): ends = batch near_far broadcast.
+ *   level >0: bilinear (align_corners) up-sampling of the previous level's depth/std/near_far
+ *             (hp,wp)->(h,w), [d+s, d-s] clamped into prev near_far and inverted (prev level is in
+ *             disparity space, utils.py:122-128).
+ * Writes ends (2,h,w) = metric depth of plane 0 / plane D-1 BEFORE the linspace evaluation, and
+ * near_far_out (2,h,w) = what the reference returns as near_far (utils.py:148-150). */
+ENERF_API int enerf_depth_hypotheses(const EnerfCam* cam, const float* prev_depth /*hp,wp or NULL*/,
+                           const float* prev_std, const float* prev_near_far /*2,hp,wp*/, int hp, int wp,
+                           int h, int w, int D, int depth_inv, float* ends, float* near_far_out, void* stream);
+
+/* build_feature_volume (utils.py:322-349) = homo_warp (utils.py:57-95) over S views fused with
+ * the variance (utils.py:337-345); the S warped volumes and the sampling grid are never stored.
+ * feat (S,hs,ws,C) channels-last, C in {8,16,32}; variance out (D,h,w,C). */
+ENERF_API int enerf_cost_volume(const EnerfCam* cam, int level, const float* feat, int n_views, int C, int hs, int ws,
+                      const float* ends /*2,h,w*/, int D, int h, int w, int depth_inv, float* variance,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MinCostRegNet.forward (cost_reg_net.py:75-86; deep=0) / CostRegNet.forward (:35-48; deep=1).
+ * variance (D,h,w,in_ch) -> feat_vol (D,h,w,8) [skipped when NULL], depth_prob (D,h,w).
+ * D % 4 == 0 (deep: % 8), h,w likewise.  weights [host array]: for each layer in the order
+ * conv0..conv4[,conv5,conv6,conv7],conv9,conv11 : {w, bias}; then ONE head tensor (no bias):
+ * w [tap][8][9] with output channel 8 = depth_conv and 0..7 = feat_conv when feat_vol != NULL, or
+ * w [tap][8][1] (depth_conv only) when feat_vol == NULL.  Forward convs: w [tap][cin][cout];
+ * transposed convs: w [tap][cin][cout] with tap = (kz*3+ky)*3+kx of the ConvTranspose3d kernel. */
+ENERF_API size_t enerf_cost_reg_workspace_bytes(int deep, int D, int h, int w);
+ENERF_API int enerf_cost_reg(const float* const* weights, int n_weights, int deep, int in_ch, const float* variance,
+                   int D, int h, int w, float* feat_vol, float* depth_prob, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* depth_regression (utils.py:658-663): softmax over D, expectation and std of the plane values
+ * (in disparity when depth_inv).  depth_mvs = 1/depth when depth_inv else depth (network.py:105-108). */
+ENERF_API int enerf_depth_regress(const float* depth_prob /*D,h,w*/, const float* ends /*2,h,w*/, int D, int h, int w,
+                        int depth_inv, float* depth, float* std, float* depth_mvs, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The fused ray stage: build_rays (utils.py:390-420) + sample_along_depth (:422-441) +
+ * get_vox_feat (:456-458) + get_img_feat (:689-722) + NeRF/Agg MLP (nerf.py:29-43,74-89) +
+ * raw2outputs (utils.py:571-603), i.e. Network.render_rays (network.py:24-43) without any of the
+ * (N,Ns,S,C) intermediates.  Rays are independent: a rank renders any contiguous slice.
+ *   rays (n_rays,8): origin, dir (un-normalised), u, v at render resolution (Hr,Wr).
+ *   depth/std (hv,wv), near_far (2,hv,wv): level outputs at volume resolution.
+ *   feat_vol (D,hv,wv,8); img_feat_rgb (S,Hr,Wr,feat_ch+4) from enerf_pack_img_feat.
+ *   weights [host array, 16 device pointers]: view_fc{w[4][fc],b}, global_fc{w[3fc][32],b},
+ *     agg_w_fc{w[32],b}, fc{w[32][16],b}, lr0{w[24][64],b}, sigma{w[64],b},
+ *     color0{w[88+fc+4][64],b}, color2{w[64],b}   (all transposed to [in][out]).
+ *   outputs: rgb (n_rays,3), depth (n_rays), weights (n_rays,num_samples).
+ * feat_ch (without the 3 rgb channels) in {8,32}; n_views in [2,ENERF_MAX_VIEWS];
+ * num_samples in [1,8]. */
+ENERF_API int enerf_render_rays(const EnerfCam* cam, int level, const float* const* weights, int n_weights,
+                      const float* rays, int n_rays, const float* depth, const float* std,
+                      const float* near_far, int hv, int wv, const float* feat_vol, int D,
+                      const float* img_feat_rgb, int n_views, int Hr, int Wr, int feat_ch,
+                      int num_samples, int depth_inv, int white_bkgd, int viewdir_agg, float* out_rgb,
+                      float* out_depth, float* out_weights, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENERF_B200_H */

@@ -1,0 +1,20 @@
+"""Shared test helpers (golden-fixture loader)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+GOLDEN_CASES = ["c1_nocascade", "c2_small_cascade", "c2_headline_small"]
+
+
+def load_golden(name):
+    import torch
+    from enerf_b200 import config as bcfg
+
+    fx = torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+    mk = bcfg.nocascade_cfg if fx["cfg_kind"] == "nocascade" else bcfg.make_cfg
+    fx["cfg"] = mk(**fx["cfg_over"])
+    return fx

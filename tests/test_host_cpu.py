@@ -1,0 +1,109 @@
+"""CPU-side tests: parameter tree / state_dict compatibility, BN folding + packing, C-ABI symbols."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from enerf_b200 import capi, packing, synthetic
+from enerf_b200 import config as bcfg
+from _helpers import ROOT, load_golden
+
+
+def _net(cfg):
+    from enerf_b200.network import Network
+    bcfg.set_cfg(cfg)
+    torch.manual_seed(0)
+    return Network()
+
+
+def test_state_dict_keys_and_init_match_reference_golden():
+    """tests/golden holds the reference's own state_dict (seed 0 + randomised BN): same keys, same
+    shapes, and -- since the holders replay the reference's construction order -- same values."""
+    for name in ("c1_nocascade", "c2_small_cascade"):
+        fx = load_golden(name)
+        net = _net(fx["cfg"])
+        synthetic.randomize_bn_(net, seed=1)
+        sd = net.state_dict()
+        assert list(sd.keys()) == list(fx["state_dict"].keys())
+        for k, v in fx["state_dict"].items():
+            assert sd[k].shape == v.shape, k
+            assert torch.equal(sd[k], v), k
+        net.load_state_dict(fx["state_dict"], strict=True)
+    assert len(load_golden("c2_small_cascade")["state_dict"]) == 184
+
+
+def test_bn_folding_matches_conv_bn():
+    fx = load_golden("c2_small_cascade")
+    sd = fx["state_dict"]
+    import torch.nn.functional as F
+    x = torch.randn(1, 8, 9, 10, generator=torch.Generator().manual_seed(0))
+    q = "feature_net.conv1.0"
+    ref = F.relu(F.batch_norm(F.conv2d(x, sd[q + ".conv.weight"], None, 2, 2), sd[q + ".bn.running_mean"], sd[q + ".bn.running_var"],
+                              sd[q + ".bn.weight"], sd[q + ".bn.bias"], False, 0.0, 1e-5))
+    pk = packing.pack_feature_net(sd, "cpu")
+    w, b = pk[4], pk[5]  # conv1.0: [25][8][16]
+    w_t = w.view(5, 5, 8, 16).permute(3, 2, 0, 1)
+    out = F.relu(F.conv2d(x, w_t, b, 2, 2))
+    assert (out - ref).abs().max() < 1e-5
+    # transposed conv: scale runs along dim 1
+    x3 = torch.randn(1, 32, 2, 3, 4, generator=torch.Generator().manual_seed(1))
+    q = "cost_reg_1.conv9"
+    ref = F.batch_norm(F.conv_transpose3d(x3, sd[q + ".0.weight"], None, 2, 1, 1), sd[q + ".1.running_mean"], sd[q + ".1.running_var"],
+                       sd[q + ".1.weight"], sd[q + ".1.bias"], False, 0.0, 1e-5)
+    pr = packing.pack_cost_reg(sd, "cost_reg_1", 16, True, "cpu", True)
+    w, b = pr[16], pr[17]  # conv9 after conv0..6 (14) + conv7 (2)
+    w_t = w.view(3, 3, 3, 32, 16).permute(3, 4, 0, 1, 2)
+    out = F.conv_transpose3d(x3, w_t, b, 2, 1, 1)
+    assert (out - ref).abs().max() < 1e-5
+    assert pr[-1].shape == (27, 8, 9) and len(pr) == 21
+    assert packing.pack_cost_reg(sd, "cost_reg_0", 32, False, "cpu", False)[-1].shape == (27, 8, 1)
+    pn = packing.pack_nerf(sd, "nerf_1", 11, True, "cpu")
+    assert [tuple(t.shape) for t in pn[::2]] == [(4, 11), (33, 32), (32, 1), (32, 16), (24, 64), (64, 1), (103, 64), (64, 1)]
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports exactly what include/enerf_b200.h declares (no compute)."""
+    if not os.path.exists(capi.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    hdr = open(os.path.join(ROOT, "include", "enerf_b200.h")).read()
+    declared = set(re.findall(r"ENERF_API\s+[\w\s\*]+?\b(enerf_\w+)\s*\(", hdr))
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    handle = ctypes.CDLL(capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert capi.lib().enerf_abi_version() == 1
+    # the EnerfCam struct size the Python side assumes
+    m = re.search(r"typedef struct EnerfCam \{(.*?)\} EnerfCam;", hdr, re.S)
+    dims = re.findall(r"float \w+((?:\[\w+\])+);", m.group(1))
+    consts = {"ENERF_MAX_LEVELS": 4, "ENERF_MAX_VIEWS": 8}
+    total = 0
+    for d in dims:
+        n = 1
+        for tok in re.findall(r"\[(\w+)\]", d):
+            n *= consts.get(tok, None) or int(tok)
+        total += n
+    assert total == capi.CAM_FLOATS
+
+
+def test_no_cpu_fallback():
+    cfg = bcfg.make_cfg(volume_planes=[8, 8])
+    net = _net(cfg).eval()
+    batch = synthetic.make_batch(64, 96, 3, cfg)
+    with pytest.raises(ValueError, match="CUDA"):
+        net(batch)
+    with pytest.raises(ValueError):
+        capi.ptr(torch.zeros(4))
+
+
+def test_cfg_snapshot_and_ray_layout():
+    cfg = bcfg.make_cfg(volume_planes=[48, 8], render_if=[False, True])
+    lv = bcfg.snapshot(cfg)
+    assert [l.planes for l in lv] == [48, 8] and [l.render_if for l in lv] == [False, True]
+    assert lv[1].prev_depth_inv and not lv[1].depth_inv and lv[1].feat_ch == 8
+    b = synthetic.make_batch(64, 96, 3, cfg)
+    assert b["rays_1"].shape == (1, 64 * 96, 8) and b["rays_0"].shape == (1, 16 * 24, 8)
+    r = b["rays_1"][0].view(64, 96, 8)
+    assert r[5, 7, 6] == 7 and r[5, 7, 7] == 5  # u, v are pixel coordinates, row-major
