@@ -19,6 +19,10 @@ ERRORS = {-1: ValueError, -2: RuntimeError, -3: RuntimeError, -4: NotImplemented
 
 _lib = None
 
+# kernels launched by this process through the library (each wrapper adds what its entry point
+# launches; bench.py reports the per-step count as `gpu_launches`)
+LAUNCHES = 0
+
 _vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
 _SIGS = {
     "enerf_abi_version": (_i, []),
@@ -55,7 +59,9 @@ def lib():
     return _lib
 
 
-def _check(rc, what):
+def _check(rc, what, launches=1):
+    global LAUNCHES
+    LAUNCHES += launches
     if rc != 0:
         msg = lib().enerf_last_error().decode("utf-8", "replace")
         raise ERRORS.get(rc, RuntimeError)(f"{what} failed ({rc}): {msg}")
@@ -101,7 +107,7 @@ def feature_net(weights, src_inps, feat_l0, feat_l1, feat_l2, workspace):
     S, _, H, W = src_inps.shape
     _check(lib().enerf_feature_net(ptr_array(weights), len(weights), ptr(src_inps), S, H, W, ptr(feat_l0), ptr(feat_l1),
                                    ptr(feat_l2), workspace.data_ptr(), workspace.numel() * workspace.element_size(), stream()),
-           "enerf_feature_net")
+           "enerf_feature_net", launches=11)
 
 
 def pack_img_feat(feat, src_inps, out):
@@ -130,7 +136,7 @@ def cost_reg(weights, deep, variance, feat_vol, depth_prob, workspace):
     D, h, w, C = variance.shape
     _check(lib().enerf_cost_reg(ptr_array(weights), len(weights), int(deep), C, ptr(variance), D, h, w, ptr(feat_vol, True),
                                 ptr(depth_prob), workspace.data_ptr(), workspace.numel() * workspace.element_size(), stream()),
-           "enerf_cost_reg")
+           "enerf_cost_reg", launches=(11 if deep else 8))
 
 
 def depth_regress(depth_prob, ends, depth_inv, depth, std, depth_mvs):

@@ -39,6 +39,9 @@ class Network(nn.Module):
         self._packed = None
         self._packed_key = None
         self._buffers_cache = {}
+        self.output_views = None   # {level: {"rgb","depth","weights"}} pre-allocated ray outputs (enerf_b200/dist.py)
+        self.profile = False       # when True, CUDA events bracket every stage (see stage_times_ms)
+        self._events = []
 
     # ---------------------------------------------------------------- packed weights (BN folded)
     def _fingerprint(self, want_feat):
@@ -78,6 +81,20 @@ class Network(nn.Module):
             self._buffers_cache[name] = t
         return t[:numel]
 
+    # ---------------------------------------------------------------- per-stage CUDA-event timing
+    def _mark(self, name):
+        if self.profile:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._events.append((name, ev))
+
+    def stage_times_ms(self):
+        """{stage: ms} of the last profiled forward (call after torch.cuda.synchronize())."""
+        out = {}
+        for (n0, e0), (n1, e1) in zip(self._events[:-1], self._events[1:]):
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
     # ---------------------------------------------------------------- forward
     def forward(self, batch):
         if self.training:
@@ -103,6 +120,8 @@ class Network(nn.Module):
             raise NotImplementedError(f"at most {capi.MAX_LEVELS} cascade levels")
         pk = self.packed_weights(levels)
         f32 = dict(device=dev, dtype=torch.float32)
+        self._events = []
+        self._mark("start")
 
         cam = self._scratch("cam", capi.CAM_FLOATS, dev)
         scales = [(lv.im_feat_scale, lv.volume_scale, lv.render_scale) for lv in levels]
@@ -115,7 +134,9 @@ class Network(nn.Module):
         feats = {0: torch.empty((S, H // 4, W // 4, 32), **f32), 1: torch.empty((S, H // 2, W // 2, 16), **f32),
                  2: torch.empty((S, H, W, 8), **f32)}
         ws = self._scratch("feat_ws", capi.feature_net_workspace_bytes(S, H, W) // 4, dev)
+        self._mark("camera_setup")
         capi.feature_net(pk["feature"], src, feats[0], feats[1], feats[2], ws)
+        self._mark("feature_net")
 
         ret = {}
         depth = std = nf = None
@@ -133,15 +154,19 @@ class Network(nn.Module):
             capi.depth_hypotheses(cam, depth, std, nf, h, w, D, lv.depth_inv, ends, nf_new)
             nf = nf_new
             var = self._scratch(f"var{i}", D * h * w * feat.shape[-1], dev).view(D, h, w, feat.shape[-1])
+            self._mark(f"depth_hypotheses_{i}")
             capi.cost_volume(cam, i, feat, ends, D, h, w, lv.depth_inv, var)
+            self._mark(f"cost_volume_{i}")
             vol = torch.empty((D, h, w, 8), **f32) if lv.render_if else None
             prob = self._scratch(f"prob{i}", D * h * w, dev).view(D, h, w)
             rws = self._scratch(f"reg_ws{i}", capi.cost_reg_workspace_bytes(deep, D, h, w) // 4, dev)
             capi.cost_reg(pk[f"reg{i}"], deep, var, vol, prob, rws)
+            self._mark(f"cost_reg_{i}")
             depth = torch.empty((h, w), **f32)
             std = torch.empty((h, w), **f32)
             mvs = torch.empty((h, w), **f32)
             capi.depth_regress(prob, ends, lv.depth_inv, depth, std, mvs)
+            self._mark(f"depth_regress_{i}")
             if not lv.render_if:
                 continue
             if lv.render_scale != lv.im_ibr_scale:
@@ -153,13 +178,21 @@ class Network(nn.Module):
                 raise ValueError(f"level {i}: image features {tuple(imf.shape)} do not match render size {Hr}x{Wr}x{lv.feat_ch}")
             img = self._scratch(f"img{i}", S * Hr * Wr * (lv.feat_ch + 4), dev).view(S, Hr, Wr, lv.feat_ch + 4)
             capi.pack_img_feat(imf, src, img)
+            self._mark(f"pack_img_feat_{i}")
             rays = batch[f"rays_{i}"][b].float().contiguous()
             N = rays.shape[0]
-            rgb = torch.empty((N, 3), **f32)
-            dmap = torch.empty((N,), **f32)
-            wts = torch.empty((N, lv.num_samples), **f32)
+            views = (self.output_views or {}).get(i)
+            if views is not None:   # write straight into the caller's (gather) buffer
+                rgb, dmap, wts = views["rgb"], views["depth"], views["weights"]
+                if rgb.shape != (N, 3) or dmap.shape != (N,) or wts.shape != (N, lv.num_samples):
+                    raise ValueError("output_views shapes do not match the ray batch")
+            else:
+                rgb = torch.empty((N, 3), **f32)
+                dmap = torch.empty((N,), **f32)
+                wts = torch.empty((N, lv.num_samples), **f32)
             capi.render_rays(cam, i, pk[f"nerf{i}"], rays, depth, std, nf, vol, img, lv.feat_ch, lv.num_samples, lv.depth_inv,
                              bool(cfg.enerf.white_bkgd), bool(cfg.enerf.viewdir_agg), rgb, dmap, wts)
+            self._mark(f"render_rays_{i}")
             ret.update({f"rgb_level{i}": rgb[None], f"depth_level{i}": dmap[None], f"weights_level{i}": wts[None],
                         f"depth_mvs_level{i}": mvs[None], f"std_level{i}": std[None]})
         return ret
