@@ -38,6 +38,7 @@ _SIGS = {
     "enerf_depth_regress": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "enerf_render_rays": (_i, [_vp, _i, ctypes.POINTER(_vp), _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i,
                                _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "enerf_tc_selftest": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -155,3 +156,8 @@ def render_rays(cam, level, weights, rays, depth, std, near_far, feat_vol, img_f
                                    ptr(near_far), hv, wv, ptr(feat_vol), D, ptr(img_feat_rgb), S, Hr, Wr, feat_ch, num_samples,
                                    int(depth_inv), int(white_bkgd), int(viewdir_agg), ptr(out_rgb), ptr(out_depth),
                                    ptr(out_weights), stream()), "enerf_render_rays")
+
+
+def tc_selftest(A, B, D):
+    """D[128,N] = A[128,K] @ B[N,K]^T on tcgen05 (TF32 operands, fp32 accumulate in TMEM)."""
+    _check(lib().enerf_tc_selftest(ptr(A), ptr(B), A.shape[1], B.shape[0], ptr(D), stream()), "enerf_tc_selftest")

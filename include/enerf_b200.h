@@ -145,6 +145,11 @@ ENERF_API int enerf_render_rays(const EnerfCam* cam, int level, const float* con
                       int num_samples, int depth_inv, int white_bkgd, int viewdir_agg, float* out_rgb,
                       float* out_depth, float* out_weights, void* stream);
 
+/* Diagnostic: D[128 x N] = A[128 x K] * B[N x K]^T on the tensor cores (tcgen05.mma kind::tf32,
+ * accumulator in TMEM) through the same descriptor helpers the fused kernels use (csrc/tc.cuh).
+ * K multiple of 8 (<=128), N multiple of 16 (<=256); A, B row-major.  No reference counterpart. */
+ENERF_API int enerf_tc_selftest(const float* A, const float* B, int K, int N, float* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

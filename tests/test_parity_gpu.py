@@ -105,3 +105,27 @@ def test_errors_are_loud(harness):
         net(bad)
     with pytest.raises(NotImplementedError):
         net.train()(bad)
+
+
+def _tf32_rna(x):
+    """cvt.rna.tf32.f32: round to nearest (ties away) keeping 10 mantissa bits."""
+    b = x.contiguous().view(torch.int32)
+    return ((b + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("K,N", [(8, 16), (16, 32), (24, 64), (32, 16), (88, 64), (104, 64), (128, 256)])
+def test_tcgen05_selftest_gemm(K, N):
+    """Pins the UMMA shared-memory / instruction descriptor encodings and the TMEM row mapping
+    of csrc/tc.cuh: D = A B^T with TF32 operands must match an fp64 product of the rounded inputs."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from enerf_b200 import capi
+    g = torch.Generator().manual_seed(K * 1000 + N)
+    A = torch.randn(128, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    D = torch.full((128, N), float("nan"), device="cuda")
+    capi.tc_selftest(A.cuda(), B.cuda(), D)
+    torch.cuda.synchronize()
+    ref = (_tf32_rna(A).double() @ _tf32_rna(B).double().t()).float()
+    err = (D.cpu() - ref).abs().max().item()
+    assert err < 1e-4 * max(1.0, ref.abs().max().item()), f"K={K} N={N}: max abs err {err}"
