@@ -38,6 +38,8 @@ _SIGS = {
     "enerf_depth_regress": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "enerf_render_rays": (_i, [_vp, _i, ctypes.POINTER(_vp), _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i,
                                _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "enerf_render_rays_tc": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i,
+                                  _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "enerf_tc_selftest": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
@@ -161,3 +163,19 @@ def render_rays(cam, level, weights, rays, depth, std, near_far, feat_vol, img_f
 def tc_selftest(A, B, D):
     """D[128,N] = A[128,K] @ B[N,K]^T on tcgen05 (TF32 operands, fp32 accumulate in TMEM)."""
     _check(lib().enerf_tc_selftest(ptr(A), ptr(B), A.shape[1], B.shape[0], ptr(D), stream()), "enerf_tc_selftest")
+
+
+def render_rays_tc(cam, level, wblob, rays, depth, std, near_far, feat_vol, img_feat_rgb, feat_ch, num_samples, depth_inv,
+                   white_bkgd, viewdir_agg, out_rgb, out_depth, out_weights):
+    n_rays = rays.shape[0]
+    hv, wv = depth.shape[-2:]
+    D = feat_vol.shape[0]
+    S, Hr, Wr, _ = img_feat_rgb.shape
+    _check(lib().enerf_render_rays_tc(ptr(cam), level, ptr(wblob), ptr(rays), n_rays, ptr(depth), ptr(std), ptr(near_far), hv, wv,
+                                      ptr(feat_vol), D, ptr(img_feat_rgb), S, Hr, Wr, feat_ch, num_samples, int(depth_inv),
+                                      int(white_bkgd), int(viewdir_agg), ptr(out_rgb), ptr(out_depth), ptr(out_weights), stream()),
+           "enerf_render_rays_tc")
+
+
+def tc_ray_kernel_supports(feat_ch, n_views, num_samples):
+    return feat_ch == 8 and 2 <= n_views <= 4 and num_samples in (1, 2, 4, 8)

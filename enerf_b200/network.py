@@ -39,6 +39,9 @@ class Network(nn.Module):
         self._packed = None
         self._packed_key = None
         self._buffers_cache = {}
+        # "tf32": MLP contractions on tcgen05 tensor cores (TF32 operands, fp32 accumulate) where the
+        # tensor-core kernel is built for the configuration; "fp32": FP32-pipe kernels everywhere.
+        self.precision = os.environ.get("ENERF_B200_PRECISION", "tf32")
         self.output_views = None   # {level: {"rgb","depth","weights"}} pre-allocated ray outputs (enerf_b200/dist.py)
         self.profile = False       # when True, CUDA events bracket every stage (see stage_times_ms)
         self._events = []
@@ -51,7 +54,7 @@ class Network(nn.Module):
             ver += t._version
             if first is None:
                 first = (t.data_ptr(), t.device)
-        return (ver, first, tuple(want_feat))
+        return (ver, first, tuple(want_feat), self.precision)
 
     def packed_weights(self, levels):
         want_feat = [lv.render_if for lv in levels]
@@ -62,7 +65,10 @@ class Network(nn.Module):
             pk = {"feature": packing.pack_feature_net(sd, dev)}
             for i, lv in enumerate(levels):
                 pk[f"reg{i}"] = packing.pack_cost_reg(sd, f"cost_reg_{i}", int(32 * (2 ** (-i))), i != 0, dev, lv.render_if)
-                pk[f"nerf{i}"] = packing.pack_nerf(sd, f"nerf_{i}", lv.feat_ch + 3, hasattr(getattr(self, f"nerf_{i}").agg, "view_fc"), dev)
+                vd = hasattr(getattr(self, f"nerf_{i}").agg, "view_fc")
+                pk[f"nerf{i}"] = packing.pack_nerf(sd, f"nerf_{i}", lv.feat_ch + 3, vd, dev)
+                if lv.feat_ch == 8:
+                    pk[f"nerf_tc{i}"] = packing.pack_nerf_tc(sd, f"nerf_{i}", lv.feat_ch + 3, vd, dev)
             self._packed, self._packed_key = pk, key
         return self._packed
 
@@ -190,8 +196,12 @@ class Network(nn.Module):
                 rgb = torch.empty((N, 3), **f32)
                 dmap = torch.empty((N,), **f32)
                 wts = torch.empty((N, lv.num_samples), **f32)
-            capi.render_rays(cam, i, pk[f"nerf{i}"], rays, depth, std, nf, vol, img, lv.feat_ch, lv.num_samples, lv.depth_inv,
-                             bool(cfg.enerf.white_bkgd), bool(cfg.enerf.viewdir_agg), rgb, dmap, wts)
+            if self.precision == "tf32" and capi.tc_ray_kernel_supports(lv.feat_ch, S, lv.num_samples):
+                capi.render_rays_tc(cam, i, pk[f"nerf_tc{i}"], rays, depth, std, nf, vol, img, lv.feat_ch, lv.num_samples,
+                                    lv.depth_inv, bool(cfg.enerf.white_bkgd), bool(cfg.enerf.viewdir_agg), rgb, dmap, wts)
+            else:
+                capi.render_rays(cam, i, pk[f"nerf{i}"], rays, depth, std, nf, vol, img, lv.feat_ch, lv.num_samples, lv.depth_inv,
+                                 bool(cfg.enerf.white_bkgd), bool(cfg.enerf.viewdir_agg), rgb, dmap, wts)
             self._mark(f"render_rays_{i}")
             ret.update({f"rgb_level{i}": rgb[None], f"depth_level{i}": dmap[None], f"weights_level{i}": wts[None],
                         f"depth_mvs_level{i}": mvs[None], f"std_level{i}": std[None]})

@@ -78,3 +78,53 @@ def pack_nerf(sd, p, feat_ch, viewdir_agg, device):
     for q in ("agg.global_fc.0", "agg.agg_w_fc.0", "agg.fc.0", "lr0.0", "sigma.0", "color.0", "color.2"):
         out += lin(f"{p}.{q}")
     return out
+
+
+def tf32_round(x):
+    """cvt.rna.tf32.f32 on the host: round to nearest (ties away from zero) to a 10-bit mantissa."""
+    b = x.to(torch.float32).contiguous().view(torch.int32)
+    return ((b + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _b_chunks(wt, K, N):
+    """W^T [k][n] (zero padded to K x N) -> tcgen05 K-major no-swizzle chunk layout [K/4][N][4], TF32."""
+    full = torch.zeros(K, N, dtype=torch.float32)
+    full[: wt.shape[0], : wt.shape[1]] = wt
+    return tf32_round(full.view(K // 4, 4, N).permute(0, 2, 1).contiguous()).reshape(-1)
+
+
+def pack_nerf_tc(sd, p, feat_ch, viewdir_agg, device):
+    """One 10,392-float blob for enerf_render_rays_tc (layout: struct TcW in csrc/render_rays_tc.cu)."""
+    fc = feat_ch
+    assert fc == 11, "tensor-core ray kernel is built for feat_ch 8 (+3 rgb)"
+    cpu = {k: v.detach().float().cpu() for k, v in sd.items() if k.startswith(p + ".")}
+    gw = cpu[f"{p}.agg.global_fc.0.weight"]            # (32, 3*fc): [f | var | mean]
+    cw = cpu[f"{p}.color.0.weight"]                    # (64, 88 + fc + 4)
+    shared = torch.zeros(24, 32)
+    shared[0:fc] = gw[:, fc:2 * fc].t()
+    shared[12:12 + fc] = gw[:, 2 * fc:3 * fc].t()
+    parts = [
+        _b_chunks(gw[:, :fc].t(), 16, 32),
+        _b_chunks(shared, 24, 32),
+        _b_chunks(cpu[f"{p}.agg.fc.0.weight"].t(), 32, 16),
+        _b_chunks(cpu[f"{p}.lr0.0.weight"].t(), 24, 64),
+        _b_chunks(cw[:, :88].t(), 88, 64),
+        _b_chunks(cw[:, 88:88 + fc + 4].t(), 16, 64),
+    ]
+    view_w, view_b = torch.zeros(4, 12), torch.zeros(12)
+    if viewdir_agg:
+        view_w[:, :fc] = cpu[f"{p}.agg.view_fc.0.weight"].t()
+        view_b[:fc] = cpu[f"{p}.agg.view_fc.0.bias"]
+
+    def pad4(t):
+        out = torch.zeros(4)
+        out[: t.numel()] = t.reshape(-1)
+        return out
+
+    parts += [view_w.reshape(-1), view_b, cpu[f"{p}.agg.global_fc.0.bias"], cpu[f"{p}.agg.agg_w_fc.0.weight"].reshape(-1),
+              pad4(cpu[f"{p}.agg.agg_w_fc.0.bias"]), cpu[f"{p}.agg.fc.0.bias"], cpu[f"{p}.lr0.0.bias"],
+              cpu[f"{p}.sigma.0.weight"].reshape(-1), pad4(cpu[f"{p}.sigma.0.bias"]), cpu[f"{p}.color.0.bias"],
+              cpu[f"{p}.color.2.weight"].reshape(-1), pad4(cpu[f"{p}.color.2.bias"])]
+    blob = torch.cat([t.reshape(-1).float() for t in parts])
+    assert blob.numel() == 10392, blob.numel()
+    return blob.to(device).contiguous()

@@ -145,6 +145,18 @@ ENERF_API int enerf_render_rays(const EnerfCam* cam, int level, const float* con
                       int num_samples, int depth_inv, int white_bkgd, int viewdir_agg, float* out_rgb,
                       float* out_depth, float* out_weights, void* stream);
 
+/* Tensor-core variant of enerf_render_rays (same stage, same arguments, same outputs): the MLP
+ * contractions run as tcgen05.mma kind::tf32 with accumulators in TMEM, 128 sample points per CTA.
+ * feat_ch == 8, n_views in [2,4], num_samples in {1,2,4,8}.  wblob = one packed device buffer of
+ * 10,392 floats (enerf_b200/packing.py::pack_nerf_tc: TF32-rounded B operands in the K-major
+ * 16-byte-chunk layout of csrc/tc.cuh, followed by the fp32 bias / 1-wide vectors). */
+ENERF_API int enerf_render_rays_tc(const EnerfCam* cam, int level, const float* wblob, const float* rays, int n_rays,
+                                   const float* depth, const float* std, const float* near_far, int hv, int wv,
+                                   const float* feat_vol, int D, const float* img_feat_rgb, int n_views, int Hr,
+                                   int Wr, int feat_ch, int num_samples, int depth_inv, int white_bkgd,
+                                   int viewdir_agg, float* out_rgb, float* out_depth, float* out_weights,
+                                   void* stream);
+
 /* Diagnostic: D[128 x N] = A[128 x K] * B[N x K]^T on the tensor cores (tcgen05.mma kind::tf32,
  * accumulator in TMEM) through the same descriptor helpers the fused kernels use (csrc/tc.cuh).
  * K multiple of 8 (<=128), N multiple of 16 (<=256); A, B row-major.  No reference counterpart. */

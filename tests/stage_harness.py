@@ -43,7 +43,7 @@ def make_case(H, W, S, cfg, seed=2):
     return sd, batch
 
 
-def stage_report(sd, cfg, batch, oracle_out=None, oracle_mid=None):
+def stage_report(sd, cfg, batch, oracle_out=None, oracle_mid=None, precision="fp32"):
     """Returns {stage: err-dict}.  Needs a CUDA device."""
     from enerf_b200.network import Network
     bcfg.set_cfg(cfg)
@@ -136,11 +136,20 @@ def stage_report(sd, cfg, batch, oracle_out=None, oracle_mid=None):
         rep[f"render_rays.rgb_{i}"] = err(rgb, oracle_out[f"rgb_level{i}"][0])
         rep[f"render_rays.depth_{i}"] = err(dmap, oracle_out[f"depth_level{i}"][0])
         rep[f"render_rays.weights_{i}"] = err(wts, oracle_out[f"weights_level{i}"][0])
+        if capi.tc_ray_kernel_supports(lv.feat_ch, S, lv.num_samples):
+            blob = packing.pack_nerf_tc(sd, f"nerf_{i}", lv.feat_ch + 3, bool(cfg.enerf.viewdir_agg), dev)
+            rgb2, d2, w2 = torch.full_like(rgb, float("nan")), torch.full_like(dmap, float("nan")), torch.full_like(wts, float("nan"))
+            capi.render_rays_tc(cam, i, blob, rays, o_depth, o_std, o_nf, ndhwc(mid[f"feat_volume_{i}"][0]), img, lv.feat_ch,
+                                lv.num_samples, lv.depth_inv, bool(cfg.enerf.white_bkgd), bool(cfg.enerf.viewdir_agg), rgb2, d2, w2)
+            rep[f"render_rays_tc.rgb_{i}"] = err(rgb2, oracle_out[f"rgb_level{i}"][0])
+            rep[f"render_rays_tc.depth_{i}"] = err(d2, oracle_out[f"depth_level{i}"][0])
+            rep[f"render_rays_tc.weights_{i}"] = err(w2, oracle_out[f"weights_level{i}"][0])
 
     # end to end through the drop-in Network
     net = Network()
     net.load_state_dict(sd, strict=True)
     net = net.cuda().eval()
+    net.precision = precision
     with torch.no_grad():
         out = net(gb)
     torch.cuda.synchronize()

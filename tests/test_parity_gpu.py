@@ -13,10 +13,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 STAGE_TOL = 1e-4
+# tensor-core (TF32 operand) stages: the reference's own sensitivity to TF32 MLP operands is
+# max|d rgb| 2.8e-4; bound = 2e-3 abs on rgb / weights, 2e-3 rel on depth
+TC_STAGE_TOL = 2e-3
 E2E_TOL = {"rgb": 5e-4, "depth": 2e-3, "weights": 2e-3, "depth_mvs": 2e-3, "std": 2e-3}
+E2E_TOL_TF32 = {"rgb": 2e-3, "depth": 4e-3, "weights": 4e-3, "depth_mvs": 2e-3, "std": 2e-3}
 
 
-def _check_report(rep):
+def _check_report(rep, e2e_tol=E2E_TOL):
     bad = []
     for k, v in rep.items():
         if "max_abs" not in v:
@@ -27,7 +31,9 @@ def _check_report(rep):
             bad.append((k, v))
             continue
         if k.startswith("e2e."):
-            tol = E2E_TOL[k[4:].split("_level")[0]] * max(1.0, v["ref_max"])
+            tol = e2e_tol[k[4:].split("_level")[0]] * max(1.0, v["ref_max"])
+        elif k.startswith("render_rays_tc."):
+            tol = TC_STAGE_TOL * max(1.0, v["ref_max"])
         else:
             tol = STAGE_TOL * max(1.0, v["ref_max"])
         if v["max_abs"] > tol:
@@ -129,3 +135,10 @@ def test_tcgen05_selftest_gemm(K, N):
     ref = (_tf32_rna(A).double() @ _tf32_rna(B).double().t()).float()
     err = (D.cpu() - ref).abs().max().item()
     assert err < 1e-4 * max(1.0, ref.abs().max().item()), f"K={K} N={N}: max abs err {err}"
+
+
+def test_e2e_tf32_tensor_core_path(harness, golden):
+    """Default precision: the ray-stage MLP runs on tcgen05 (TF32 operands).  Same oracle, wider
+    element-wise bound, same |dPSNR| < 0.01 dB criterion."""
+    rep, out = harness.stage_report(golden["state_dict"], golden["cfg"], golden["batch"], precision="tf32")
+    _check_report({k: v for k, v in rep.items() if k.startswith("e2e.")}, E2E_TOL_TF32)
