@@ -40,6 +40,7 @@ _SIGS = {
                                _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "enerf_render_rays_tc": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i,
                                   _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "enerf_tc_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "enerf_tc_selftest": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
@@ -179,3 +180,11 @@ def render_rays_tc(cam, level, wblob, rays, depth, std, near_far, feat_vol, img_
 
 def tc_ray_kernel_supports(feat_ch, n_views, num_samples):
     return feat_ch == 8 and 2 <= n_views <= 4 and num_samples in (1, 2, 4, 8)
+
+
+def tc_conv(kind, KD, KH, cout, mode, relu, x, wpack, bias, skip, out, out2=None, out_cstride=None, out_coff=0):
+    """x (D,H,W,cin) channels-last.  See enerf_tc_conv in include/enerf_b200.h."""
+    D, H, W, cin = x.shape
+    _check(lib().enerf_tc_conv(kind, KD, KH, cin, cout, mode, int(relu), ptr(x), D, H, W, ptr(wpack), ptr(bias, True), ptr(skip, True),
+                               ptr(out), ptr(out2, True), out_cstride if out_cstride is not None else cout, out_coff, stream()),
+           "enerf_tc_conv")

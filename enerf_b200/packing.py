@@ -128,3 +128,31 @@ def pack_nerf_tc(sd, p, feat_ch, viewdir_agg, device):
     blob = torch.cat([t.reshape(-1).float() for t in parts])
     assert blob.numel() == 10392, blob.numel()
     return blob.to(device).contiguous()
+
+
+def pack_tc_conv(w_taps, n_pad=None):
+    """[tap][cin][cout] (BN-folded, fp32) -> tcgen05 stage layout [cin/8][tap][2][N][4], TF32 (RNA)."""
+    taps, cin, cout = w_taps.shape
+    N = n_pad or (cout + 15) // 16 * 16
+    full = torch.zeros(taps, cin, N, dtype=torch.float32)
+    full[:, :, :cout] = w_taps.float().cpu()
+    # cin = st*8 + j*4 + i
+    return tf32_round(full.view(taps, cin // 8, 2, 4, N).permute(1, 0, 2, 4, 3).contiguous()).reshape(-1)
+
+
+def pack_tc_deconv(w_taps):
+    """ConvTranspose3d(k3,s2,p1,op1) [27][cin][cout] -> sub-pixel conv: 8 input offsets d in {0,1}^3,
+    N = 8 parities x cout.  Per dimension: offset 0 feeds parity 0 through k=1 and parity 1 through
+    k=2; offset 1 feeds parity 1 through k=0 (o = 2i - 1 + k)."""
+    taps, cin, cout = w_taps.shape
+    assert taps == 27
+    w = w_taps.float().cpu().view(3, 3, 3, cin, cout)
+    kmap = {(0, 0): 1, (0, 1): 2, (1, 1): 0}
+    full = torch.zeros(8, cin, 8, cout, dtype=torch.float32)      # [offset][cin][parity][cout]
+    for d in range(8):
+        dz, dy, dx = (d >> 2) & 1, (d >> 1) & 1, d & 1
+        for e in range(8):
+            ez, ey, ex = (e >> 2) & 1, (e >> 1) & 1, e & 1
+            if (dz, ez) in kmap and (dy, ey) in kmap and (dx, ex) in kmap:
+                full[d, :, e, :] = w[kmap[(dz, ez)], kmap[(dy, ey)], kmap[(dx, ex)]]
+    return pack_tc_conv(full.view(8, cin, 8 * cout))

@@ -157,6 +157,18 @@ ENERF_API int enerf_render_rays_tc(const EnerfCam* cam, int level, const float* 
                                    int viewdir_agg, float* out_rgb, float* out_depth, float* out_weights,
                                    void* stream);
 
+/* One convolution layer on the tensor cores (tcgen05 implicit GEMM, csrc/tc_conv.cuh): the building
+ * block enerf_feature_net / enerf_cost_reg use in TF32 mode, exported for layer-level parity tests.
+ *   kind 0: stride-1 convolution KD x KH x KH (KD in {1,3}, KH in {1,3}), zero padding K/2.
+ *   kind 1: ConvTranspose3d(k3, s2, p1, output_padding 1) in sub-pixel form; (D,H,W) is the INPUT grid.
+ *   mode 0: out[pix][out_coff..+cout) = act(acc + bias);  1: head (8 feat -> out, 1 prob -> out2);
+ *        2: transposed conv, out = skip + acc + bias;     3: single channel -> out.
+ * in (D,H,W,cin) channels-last, cin % 8 == 0.  wpack: enerf_b200/packing.py::pack_tc_conv /
+ * pack_tc_deconv ([cin/8][tap][2][N][4], TF32-rounded, N = cout (x8 for kind 1) padded to 16). */
+ENERF_API int enerf_tc_conv(int kind, int KD, int KH, int cin, int cout, int mode, int relu, const float* in, int D, int H,
+                            int W, const float* wpack, const float* bias, const float* skip, float* out, float* out2,
+                            int out_cstride, int out_coff, void* stream);
+
 /* Diagnostic: D[128 x N] = A[128 x K] * B[N x K]^T on the tensor cores (tcgen05.mma kind::tf32,
  * accumulator in TMEM) through the same descriptor helpers the fused kernels use (csrc/tc.cuh).
  * K multiple of 8 (<=128), N multiple of 16 (<=256); A, B row-major.  No reference counterpart. */

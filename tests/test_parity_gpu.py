@@ -142,3 +142,72 @@ def test_e2e_tf32_tensor_core_path(harness, golden):
     element-wise bound, same |dPSNR| < 0.01 dB criterion."""
     rep, out = harness.stage_report(golden["state_dict"], golden["cfg"], golden["batch"], precision="tf32")
     _check_report({k: v for k, v in rep.items() if k.startswith("e2e.")}, E2E_TOL_TF32)
+
+
+TC_CONV_CASES = [
+    # kind, KD, KH, cin, cout, mode, relu, (D, H, W)
+    (0, 3, 3, 16, 8, 0, 1, (8, 32, 48)),     # CostRegNet conv0
+    (0, 3, 3, 32, 8, 0, 1, (4, 16, 40)),     # MinCostRegNet conv0
+    (0, 3, 3, 16, 16, 0, 1, (4, 16, 24)),    # conv2
+    (0, 3, 3, 32, 32, 0, 1, (2, 8, 12)),     # conv4
+    (0, 3, 3, 64, 64, 0, 1, (1, 4, 6)),      # conv6 (8 K-stages through the 2-deep ring)
+    (0, 3, 3, 8, 9, 1, 0, (8, 32, 48)),      # head: feat_conv + depth_conv
+    (0, 3, 3, 8, 1, 3, 0, (8, 16, 24)),      # depth_conv only
+    (0, 1, 3, 32, 8, 0, 0, (3, 64, 96)),     # FeatureNet smooth0 (2-D: images on the depth axis)
+    (0, 1, 3, 32, 32, 0, 1, (2, 16, 24)),    # conv2.1
+    (0, 1, 1, 32, 32, 0, 0, (3, 16, 24)),    # toplayer 1x1
+    (1, 3, 3, 16, 8, 2, 0, (4, 16, 24)),     # conv11 (transposed)
+    (1, 3, 3, 32, 16, 2, 0, (2, 8, 12)),     # conv9
+    (1, 3, 3, 64, 32, 2, 0, (1, 4, 6)),      # conv7
+]
+
+
+@pytest.mark.parametrize("kind,KD,KH,cin,cout,mode,relu,dims", TC_CONV_CASES)
+def test_tc_conv_layer(kind, KD, KH, cin, cout, mode, relu, dims):
+    """tcgen05 implicit-GEMM convolution vs torch's fp32 conv on the same (TF32-rounded) operands.
+    Bound: 2e-3 * max|ref| (TF32 operand rounding of activations; weights are pre-rounded)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import torch.nn.functional as F
+    from enerf_b200 import capi, packing
+    D, H, W = dims
+    g = torch.Generator().manual_seed(cin * 100 + cout + kind)
+    x = torch.randn(1, cin, D, H, W, generator=g)
+    if kind == 0:
+        w = torch.randn(cout, cin, KD, KH, KH, generator=g) / (cin * KD * KH * KH) ** 0.5
+        b = torch.randn(cout, generator=g) * 0.1 if mode == 0 else None
+        ref = F.conv3d(x, w, b, 1, (KD // 2, KH // 2, KH // 2))
+        if relu:
+            ref = F.relu(ref)
+        wp = packing.pack_tc_conv(packing._taps_cin_cout(w)).cuda()
+        skip = None
+    else:
+        w = torch.randn(cin, cout, 3, 3, 3, generator=g) / (cin * 27 / 8) ** 0.5
+        b = torch.randn(cout, generator=g) * 0.1
+        skip_t = torch.randn(1, cout, 2 * D, 2 * H, 2 * W, generator=g)
+        ref = skip_t + F.conv_transpose3d(x, w, b, stride=2, padding=1, output_padding=1)
+        wp = packing.pack_tc_deconv(w.permute(2, 3, 4, 0, 1).reshape(27, cin, cout)).cuda()
+        skip = skip_t[0].permute(1, 2, 3, 0).contiguous().cuda()
+    xin = x[0].permute(1, 2, 3, 0).contiguous().cuda()
+    Do, Ho, Wo = ref.shape[2:]
+    out2 = None
+    if mode == 1:
+        out = torch.full((Do, Ho, Wo, 8), float("nan"), device="cuda")
+        out2 = torch.full((Do, Ho, Wo), float("nan"), device="cuda")
+    elif mode == 3:
+        out = torch.full((Do, Ho, Wo), float("nan"), device="cuda")
+    else:
+        out = torch.full((Do, Ho, Wo, cout), float("nan"), device="cuda")
+    capi.tc_conv(kind, KD, KH, cout, mode, relu, xin, wp, b.cuda() if b is not None else None, skip, out, out2,
+                 out_cstride=(8 if mode == 1 else cout))
+    torch.cuda.synchronize()
+    refc = ref[0].permute(1, 2, 3, 0)
+    if mode == 1:
+        got = torch.cat([out.cpu(), out2.cpu()[..., None]], dim=-1)
+    elif mode == 3:
+        got = out.cpu()[..., None]
+    else:
+        got = out.cpu()
+    err = (got - refc).abs().max().item()
+    assert not torch.isnan(got).any()
+    assert err < 2e-3 * max(1.0, refc.abs().max().item()), f"max abs err {err} (ref max {refc.abs().max().item()})"
