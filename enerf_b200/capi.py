@@ -29,12 +29,12 @@ _SIGS = {
     "enerf_last_error": (ctypes.c_char_p, []),
     "enerf_camera_setup": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, ctypes.POINTER(ctypes.c_float), _vp, _vp]),
     "enerf_feature_net_workspace_bytes": (_sz, [_i, _i, _i]),
-    "enerf_feature_net": (_i, [ctypes.POINTER(_vp), _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "enerf_feature_net": (_i, [ctypes.POINTER(_vp), _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "enerf_pack_img_feat": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "enerf_depth_hypotheses": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "enerf_cost_volume": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "enerf_cost_reg_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "enerf_cost_reg": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "enerf_cost_reg": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "enerf_depth_regress": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "enerf_render_rays": (_i, [_vp, _i, ctypes.POINTER(_vp), _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i,
                                _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
@@ -107,10 +107,11 @@ def feature_net_workspace_bytes(S, H, W):
     return lib().enerf_feature_net_workspace_bytes(S, H, W)
 
 
-def feature_net(weights, src_inps, feat_l0, feat_l1, feat_l2, workspace):
+def feature_net(weights, src_inps, feat_l0, feat_l1, feat_l2, workspace, tensor_cores=False):
     S, _, H, W = src_inps.shape
     _check(lib().enerf_feature_net(ptr_array(weights), len(weights), ptr(src_inps), S, H, W, ptr(feat_l0), ptr(feat_l1),
-                                   ptr(feat_l2), workspace.data_ptr(), workspace.numel() * workspace.element_size(), stream()),
+                                   ptr(feat_l2), workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                                   int(tensor_cores), stream()),
            "enerf_feature_net", launches=11)
 
 
@@ -136,10 +137,11 @@ def cost_reg_workspace_bytes(deep, D, h, w):
     return lib().enerf_cost_reg_workspace_bytes(int(deep), D, h, w)
 
 
-def cost_reg(weights, deep, variance, feat_vol, depth_prob, workspace):
+def cost_reg(weights, deep, variance, feat_vol, depth_prob, workspace, tensor_cores=False):
     D, h, w, C = variance.shape
     _check(lib().enerf_cost_reg(ptr_array(weights), len(weights), int(deep), C, ptr(variance), D, h, w, ptr(feat_vol, True),
-                                ptr(depth_prob), workspace.data_ptr(), workspace.numel() * workspace.element_size(), stream()),
+                                ptr(depth_prob), workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                                int(tensor_cores), stream()),
            "enerf_cost_reg", launches=(11 if deep else 8))
 
 

@@ -11,6 +11,7 @@
 //    a thread owns a 2x2x2 output block (all 8 parities => exactly the 27 (tap,input) pairs of
 //    the 2x2x2 input neighbourhood), no divergence, skip-add fused.
 #include "conv.cuh"
+#include "tc_conv.cuh"
 
 namespace enerf {
 
@@ -224,7 +225,7 @@ extern "C" size_t enerf_cost_reg_workspace_bytes(int deep, int D, int h, int w) 
 
 extern "C" int enerf_cost_reg(const float* const* wts, int n_weights, int deep, int in_ch, const float* variance, int D,
                               int h, int w, float* feat_vol, float* depth_prob, void* workspace, size_t workspace_bytes,
-                              void* stream_) {
+                              int tensor_cores, void* stream_) {
   using namespace enerf;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int expect = deep ? 21 : 15;
@@ -240,34 +241,66 @@ extern "C" int enerf_cost_reg(const float* const* wts, int n_weights, int deep, 
   int rc;
 #define RUN(call)                 \
   if ((rc = (call)) != ENERF_OK) return rc
-  if (in_ch == 32) {
+  const int D2 = D / 2, h2 = h / 2, w2 = w / 2, D4 = D / 4, h4 = h / 4, w4 = w / 4, D8 = D / 8, h8 = h / 8, w8 = w / 8;
+  // tcgen05 path for every stride-1 and transposed layer (stride-2 layers stay on the FP32 pipe)
+  auto tc_cbr = [&](int cin, int cout, const float* in, int d_, int h_, int w_, const float* wp, const float* b, float* o) {
+    TcConvLayer L{0, 3, 3, cin, cout, TC_PLAIN, 1};
+    return tc_conv_launch(L, in, d_, h_, w_, wp, b, nullptr, o, nullptr, cout, 0, stream);
+  };
+  auto tc_dec = [&](int cin, int cout, const float* in, int d_, int h_, int w_, const float* wp, const float* b, const float* skip,
+                    float* o) {
+    TcConvLayer L{1, 3, 3, cin, cout, TC_DECONV, 0};
+    return tc_conv_launch(L, in, d_, h_, w_, wp, b, skip, o, nullptr, cout, 0, stream);
+  };
+  if (tensor_cores) {
+    RUN(tc_cbr(in_ch, 8, variance, D, h, w, wts[0], wts[1], ws.c0));
+  } else if (in_ch == 32) {
     RUN(launch_conv<C0_32>("cost_reg.conv0", variance, wts[0], wts[1], ws.c0, nullptr, D, h, w, 8, 0, stream));
   } else if (in_ch == 16) {
     RUN(launch_conv<C0_16>("cost_reg.conv0", variance, wts[0], wts[1], ws.c0, nullptr, D, h, w, 8, 0, stream));
   } else {
     RUN(launch_conv<C0_8>("cost_reg.conv0", variance, wts[0], wts[1], ws.c0, nullptr, D, h, w, 8, 0, stream));
   }
-  const int D2 = D / 2, h2 = h / 2, w2 = w / 2, D4 = D / 4, h4 = h / 4, w4 = w / 4, D8 = D / 8, h8 = h / 8, w8 = w / 8;
   RUN((launch_small<8, 16, 2>("cost_reg.conv1", ws.c0, wts[2], wts[3], ws.c1, D, h, w, stream)));
-  RUN((launch_small<16, 16, 1>("cost_reg.conv2", ws.c1, wts[4], wts[5], ws.c2, D2, h2, w2, stream)));
+  if (tensor_cores) {
+    RUN(tc_cbr(16, 16, ws.c1, D2, h2, w2, wts[4], wts[5], ws.c2));
+  } else {
+    RUN((launch_small<16, 16, 1>("cost_reg.conv2", ws.c1, wts[4], wts[5], ws.c2, D2, h2, w2, stream)));
+  }
   RUN((launch_small<16, 32, 2>("cost_reg.conv3", ws.c2, wts[6], wts[7], ws.c3, D2, h2, w2, stream)));
-  RUN((launch_small<32, 32, 1>("cost_reg.conv4", ws.c3, wts[8], wts[9], ws.c4, D4, h4, w4, stream)));
+  if (tensor_cores) {
+    RUN(tc_cbr(32, 32, ws.c3, D4, h4, w4, wts[8], wts[9], ws.c4));
+  } else {
+    RUN((launch_small<32, 32, 1>("cost_reg.conv4", ws.c3, wts[8], wts[9], ws.c4, D4, h4, w4, stream)));
+  }
   const float* x4 = ws.c4;
   int wi = 10;
   if (deep) {
     RUN((launch_small<32, 64, 2>("cost_reg.conv5", ws.c4, wts[10], wts[11], ws.c5, D4, h4, w4, stream)));
-    RUN((launch_small<64, 64, 1>("cost_reg.conv6", ws.c5, wts[12], wts[13], ws.c6, D8, h8, w8, stream)));
-    RUN((launch_deconv<64, 32>("cost_reg.conv7", ws.c6, wts[14], wts[15], ws.c4, ws.y4, D8, h8, w8, stream)));
+    if (tensor_cores) {
+      RUN(tc_cbr(64, 64, ws.c5, D8, h8, w8, wts[12], wts[13], ws.c6));
+      RUN(tc_dec(64, 32, ws.c6, D8, h8, w8, wts[14], wts[15], ws.c4, ws.y4));
+    } else {
+      RUN((launch_small<64, 64, 1>("cost_reg.conv6", ws.c5, wts[12], wts[13], ws.c6, D8, h8, w8, stream)));
+      RUN((launch_deconv<64, 32>("cost_reg.conv7", ws.c6, wts[14], wts[15], ws.c4, ws.y4, D8, h8, w8, stream)));
+    }
     x4 = ws.y4;
     wi = 16;
   }
-  RUN((launch_deconv<32, 16>("cost_reg.conv9", x4, wts[wi], wts[wi + 1], ws.c2, ws.y2, D4, h4, w4, stream)));
-  RUN((launch_deconv<16, 8>("cost_reg.conv11", ws.y2, wts[wi + 2], wts[wi + 3], ws.c0, ws.y0, D2, h2, w2, stream)));
-  if (feat_vol) {
-    RUN(launch_conv<Head9>("cost_reg.head9", ws.y0, wts[wi + 4], nullptr, feat_vol, depth_prob, D, h, w, 8, 0, stream));
+  if (tensor_cores) {
+    RUN(tc_dec(32, 16, x4, D4, h4, w4, wts[wi], wts[wi + 1], ws.c2, ws.y2));
+    RUN(tc_dec(16, 8, ws.y2, D2, h2, w2, wts[wi + 2], wts[wi + 3], ws.c0, ws.y0));
+    TcConvLayer Lh{0, 3, 3, 8, feat_vol ? 9 : 1, feat_vol ? TC_HEAD : TC_SINGLE, 0};
+    RUN(tc_conv_launch(Lh, ws.y0, D, h, w, wts[wi + 4], nullptr, nullptr, feat_vol ? feat_vol : depth_prob, depth_prob, 8, 0, stream));
   } else {
-    // depth_conv only: the caller passes the head as a [27][8][1] tensor (see enerf_b200.h)
-    RUN(launch_conv<Head1>("cost_reg.head1", ws.y0, wts[wi + 4], nullptr, depth_prob, nullptr, D, h, w, 1, 0, stream));
+    RUN((launch_deconv<32, 16>("cost_reg.conv9", x4, wts[wi], wts[wi + 1], ws.c2, ws.y2, D4, h4, w4, stream)));
+    RUN((launch_deconv<16, 8>("cost_reg.conv11", ws.y2, wts[wi + 2], wts[wi + 3], ws.c0, ws.y0, D2, h2, w2, stream)));
+    if (feat_vol) {
+      RUN(launch_conv<Head9>("cost_reg.head9", ws.y0, wts[wi + 4], nullptr, feat_vol, depth_prob, D, h, w, 8, 0, stream));
+    } else {
+      // depth_conv only: the caller passes the head as a [27][8][1] tensor (see enerf_b200.h)
+      RUN(launch_conv<Head1>("cost_reg.head1", ws.y0, wts[wi + 4], nullptr, depth_prob, nullptr, D, h, w, 1, 0, stream));
+    }
   }
 #undef RUN
   return ENERF_OK;

@@ -3,6 +3,7 @@
 // two fused {lateral 1x1 conv + bilinear x2 up-sample (align_corners) + add} kernels
 // (feature_net.py:24-25,32-33).  The S source images ride on the depth axis of the conv template.
 #include "conv.cuh"
+#include "tc_conv.cuh"
 
 namespace enerf {
 
@@ -152,7 +153,7 @@ extern "C" size_t enerf_feature_net_workspace_bytes(int n_views, int H, int W) {
 
 extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const float* src_inps, int S, int H, int W,
                                  float* feat_l0, float* feat_l1, float* feat_l2, void* workspace, size_t workspace_bytes,
-                                 void* stream_) {
+                                 int tensor_cores, void* stream_) {
   using namespace enerf;
   cudaStream_t stream = (cudaStream_t)stream_;
   ENERF_REQUIRE(wts && n_weights == 22, ENERF_EINVAL, "feature_net: expected 22 weight pointers, got %d", n_weights);
@@ -165,13 +166,33 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
   int rc;
 #define RUN(call)                 \
   if ((rc = (call)) != ENERF_OK) return rc
+  // stride-1 3x3 / 1x1 layers: tcgen05 implicit GEMM when tensor_cores != 0, FP32-pipe direct conv otherwise
+  auto tc = [&](const char* name, int KH, int cin, int cout, int relu, const float* in, int h, int w, const float* wp,
+                const float* b, float* o) {
+    (void)name;
+    TcConvLayer L{0, 1, KH, cin, cout, TC_PLAIN, relu};
+    return tc_conv_launch(L, in, S, h, w, wp, b, nullptr, o, nullptr, cout, 0, stream);
+  };
   RUN(launch_conv<Conv00>("feature_net.conv0.0", src_inps, wts[0], wts[1], ws.c0a, nullptr, S, H, W, 8, 0, stream));
-  RUN(launch_conv<Conv01>("feature_net.conv0.1", ws.c0a, wts[2], wts[3], ws.c0, nullptr, S, H, W, 8, 0, stream));
+  if (tensor_cores) {
+    RUN(tc("feature_net.conv0.1", 3, 8, 8, 1, ws.c0a, H, W, wts[2], wts[3], ws.c0));
+  } else {
+    RUN(launch_conv<Conv01>("feature_net.conv0.1", ws.c0a, wts[2], wts[3], ws.c0, nullptr, S, H, W, 8, 0, stream));
+  }
   RUN(launch_conv<Conv10>("feature_net.conv1.0", ws.c0, wts[4], wts[5], ws.c1a, nullptr, S, H, W, 16, 0, stream));
-  RUN(launch_conv<Conv11>("feature_net.conv1.1", ws.c1a, wts[6], wts[7], ws.c1, nullptr, S, H2, W2, 16, 0, stream));
+  if (tensor_cores) {
+    RUN(tc("feature_net.conv1.1", 3, 16, 16, 1, ws.c1a, H2, W2, wts[6], wts[7], ws.c1));
+  } else {
+    RUN(launch_conv<Conv11>("feature_net.conv1.1", ws.c1a, wts[6], wts[7], ws.c1, nullptr, S, H2, W2, 16, 0, stream));
+  }
   RUN(launch_conv<Conv20>("feature_net.conv2.0", ws.c1, wts[8], wts[9], ws.c2a, nullptr, S, H2, W2, 32, 0, stream));
-  RUN(launch_conv<Conv21>("feature_net.conv2.1", ws.c2a, wts[10], wts[11], ws.c2, nullptr, S, H4, W4, 32, 0, stream));
-  RUN(launch_conv<Top>("feature_net.toplayer", ws.c2, wts[12], wts[13], feat_l0, nullptr, S, H4, W4, 32, 0, stream));
+  if (tensor_cores) {
+    RUN(tc("feature_net.conv2.1", 3, 32, 32, 1, ws.c2a, H4, W4, wts[10], wts[11], ws.c2));
+    RUN(tc("feature_net.toplayer", 1, 32, 32, 0, ws.c2, H4, W4, wts[12], wts[13], feat_l0));
+  } else {
+    RUN(launch_conv<Conv21>("feature_net.conv2.1", ws.c2a, wts[10], wts[11], ws.c2, nullptr, S, H4, W4, 32, 0, stream));
+    RUN(launch_conv<Top>("feature_net.toplayer", ws.c2, wts[12], wts[13], feat_l0, nullptr, S, H4, W4, 32, 0, stream));
+  }
   {
     const long long total = (long long)S * H2 * W2 * 4;
     const int blocks = (int)((total + 255) / 256);
@@ -184,8 +205,13 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
     lateral_upadd_kernel<8><<<blocks, 256, 0, stream>>>(ws.c0, wts[16], wts[17], ws.f1, ws.f0, S, H, W);
     ENERF_CHECK_LAUNCH("feature_net.lat0");
   }
-  RUN(launch_conv<Smooth1>("feature_net.smooth1", ws.f1, wts[18], wts[19], feat_l1, nullptr, S, H2, W2, 16, 0, stream));
-  RUN(launch_conv<Smooth0>("feature_net.smooth0", ws.f0, wts[20], wts[21], feat_l2, nullptr, S, H, W, 8, 0, stream));
+  if (tensor_cores) {
+    RUN(tc("feature_net.smooth1", 3, 32, 16, 0, ws.f1, H2, W2, wts[18], wts[19], feat_l1));
+    RUN(tc("feature_net.smooth0", 3, 32, 8, 0, ws.f0, H, W, wts[20], wts[21], feat_l2));
+  } else {
+    RUN(launch_conv<Smooth1>("feature_net.smooth1", ws.f1, wts[18], wts[19], feat_l1, nullptr, S, H2, W2, 16, 0, stream));
+    RUN(launch_conv<Smooth0>("feature_net.smooth0", ws.f0, wts[20], wts[21], feat_l2, nullptr, S, H, W, 8, 0, stream));
+  }
 #undef RUN
   return ENERF_OK;
 }

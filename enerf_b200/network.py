@@ -62,9 +62,11 @@ class Network(nn.Module):
         if self._packed is None or self._packed_key != key:
             sd = {k: v.detach() for k, v in self.state_dict().items()}
             dev = next(self.parameters()).device
-            pk = {"feature": packing.pack_feature_net(sd, dev)}
+            tcs = self.precision == "tf32"
+            pk = {"feature": packing.pack_feature_net(sd, dev, tensor_cores=tcs)}
             for i, lv in enumerate(levels):
-                pk[f"reg{i}"] = packing.pack_cost_reg(sd, f"cost_reg_{i}", int(32 * (2 ** (-i))), i != 0, dev, lv.render_if)
+                pk[f"reg{i}"] = packing.pack_cost_reg(sd, f"cost_reg_{i}", int(32 * (2 ** (-i))), i != 0, dev, lv.render_if,
+                                                      tensor_cores=tcs)
                 vd = hasattr(getattr(self, f"nerf_{i}").agg, "view_fc")
                 pk[f"nerf{i}"] = packing.pack_nerf(sd, f"nerf_{i}", lv.feat_ch + 3, vd, dev)
                 if lv.feat_ch == 8:
@@ -141,7 +143,8 @@ class Network(nn.Module):
                  2: torch.empty((S, H, W, 8), **f32)}
         ws = self._scratch("feat_ws", capi.feature_net_workspace_bytes(S, H, W) // 4, dev)
         self._mark("camera_setup")
-        capi.feature_net(pk["feature"], src, feats[0], feats[1], feats[2], ws)
+        tcs = self.precision == "tf32"
+        capi.feature_net(pk["feature"], src, feats[0], feats[1], feats[2], ws, tensor_cores=tcs)
         self._mark("feature_net")
 
         ret = {}
@@ -166,7 +169,7 @@ class Network(nn.Module):
             vol = torch.empty((D, h, w, 8), **f32) if lv.render_if else None
             prob = self._scratch(f"prob{i}", D * h * w, dev).view(D, h, w)
             rws = self._scratch(f"reg_ws{i}", capi.cost_reg_workspace_bytes(deep, D, h, w) // 4, dev)
-            capi.cost_reg(pk[f"reg{i}"], deep, var, vol, prob, rws)
+            capi.cost_reg(pk[f"reg{i}"], deep, var, vol, prob, rws, tensor_cores=tcs)
             self._mark(f"cost_reg_{i}")
             depth = torch.empty((h, w), **f32)
             std = torch.empty((h, w), **f32)

@@ -31,37 +31,47 @@ def _dev(t, device):
     return t.to(device=device, dtype=torch.float32).contiguous()
 
 
-def pack_feature_net(sd, device, p="feature_net"):
-    """22 tensors: {w,b} for conv0.0 conv0.1 conv1.0 conv1.1 conv2.0 conv2.1 toplayer lat1 lat0 smooth1 smooth0."""
+TC_FEATURE_LAYERS = ("conv0.1", "conv1.1", "conv2.1", "toplayer", "smooth1", "smooth0")   # stride-1, cin % 8 == 0
+
+
+def pack_feature_net(sd, device, p="feature_net", tensor_cores=False):
+    """22 tensors: {w,b} for conv0.0 conv0.1 conv1.0 conv1.1 conv2.0 conv2.1 toplayer lat1 lat0 smooth1 smooth0.
+    tensor_cores: the layers in TC_FEATURE_LAYERS get the tcgen05 stage layout (pack_tc_conv)."""
+    def lay(name, w_taps):
+        if tensor_cores and name in TC_FEATURE_LAYERS:
+            return pack_tc_conv(w_taps).to(device)
+        return _dev(w_taps, device)
+
     out = []
     for name, pair in FEATURE_CBR:
         for j in range(len(pair)):
             q = f"{p}.{name}.{j}"
             w, b = _fold(sd[q + ".conv.weight"], sd, q + ".bn", 0)
-            out += [_dev(_taps_cin_cout(w), device), _dev(b, device)]
+            out += [lay(f"{name}.{j}", _taps_cin_cout(w)), _dev(b, device)]
     for name, *_ in FEATURE_PLAIN:
-        out += [_dev(_taps_cin_cout(sd[f"{p}.{name}.weight"].double()), device), _dev(sd[f"{p}.{name}.bias"], device)]
+        out += [lay(name, _taps_cin_cout(sd[f"{p}.{name}.weight"].double())), _dev(sd[f"{p}.{name}.bias"], device)]
     return out
 
 
-def pack_cost_reg(sd, p, in_ch, deep, device, with_feat):
-    """{w,b} per layer (conv0..conv11) + one head tensor ([27][8][9] feat+depth, or [27][8][1] depth only)."""
+def pack_cost_reg(sd, p, in_ch, deep, device, with_feat, tensor_cores=False):
+    """{w,b} per layer (conv0..conv11) + one head tensor ([27][8][9] feat+depth, or [27][8][1] depth only).
+    tensor_cores: stride-1 and transposed layers + head in the tcgen05 stage layout."""
     out = []
     head = {}
     for name, kind, cin, cout, stride in cost_reg_layers(in_ch, deep):
         q = f"{p}.{name}"
         if kind == "cbr":
             w, b = _fold(sd[q + ".conv.weight"], sd, q + ".bn", 0)
-            out += [_dev(_taps_cin_cout(w), device), _dev(b, device)]
+            wt = _taps_cin_cout(w)
+            out += [pack_tc_conv(wt).to(device) if (tensor_cores and stride == 1) else _dev(wt, device), _dev(b, device)]
         elif kind == "deconv":
             w, b = _fold(sd[q + ".0.weight"], sd, q + ".1", 1)      # (Cin,Cout,kz,ky,kx)
-            out += [_dev(w.permute(2, 3, 4, 0, 1).reshape(27, cin, cout), device), _dev(b, device)]
+            wt = w.permute(2, 3, 4, 0, 1).reshape(27, cin, cout)
+            out += [pack_tc_deconv(wt).to(device) if tensor_cores else _dev(wt, device), _dev(b, device)]
         else:
             head[name] = _taps_cin_cout(sd[q + ".0.weight"].double())   # [27][8][cout]
-    if with_feat:
-        out.append(_dev(torch.cat([head["feat_conv"], head["depth_conv"]], dim=2), device))
-    else:
-        out.append(_dev(head["depth_conv"], device))
+    hw = torch.cat([head["feat_conv"], head["depth_conv"]], dim=2) if with_feat else head["depth_conv"]
+    out.append(pack_tc_conv(hw).to(device) if tensor_cores else _dev(hw, device))
     return out
 
 

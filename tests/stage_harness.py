@@ -77,6 +77,12 @@ def stage_report(sd, cfg, batch, oracle_out=None, oracle_mid=None, precision="fp
     capi.feature_net(pk_feat, gb["src_inps"][0].contiguous(), f0, f1, f2, ws)
     for i, t in enumerate((f0, f1, f2)):
         rep[f"feature_net.level_{i}"] = err(t.permute(0, 3, 1, 2), mid[f"feat_level_{i}"][0])
+    # same stage with the stride-1 layers on the tensor cores (TF32)
+    pk_feat_tc = packing.pack_feature_net(sd, dev, tensor_cores=True)
+    g0, g1, g2 = torch.full_like(f0, float("nan")), torch.full_like(f1, float("nan")), torch.full_like(f2, float("nan"))
+    capi.feature_net(pk_feat_tc, gb["src_inps"][0].contiguous(), g0, g1, g2, ws, tensor_cores=True)
+    for i, t in enumerate((g0, g1, g2)):
+        rep[f"feature_net_tc.level_{i}"] = err(t.permute(0, 3, 1, 2), mid[f"feat_level_{i}"][0])
 
     prev = None
     for i, lv in enumerate(levels):
@@ -108,6 +114,16 @@ def stage_report(sd, cfg, batch, oracle_out=None, oracle_mid=None, precision="fp
         prob1 = torch.empty((D, h, w), **f32)
         capi.cost_reg(pk_reg1, deep, ndhwc(mid[f"variance_{i}"][0]), None, prob1, rws)
         rep[f"cost_reg.depth_prob_only_{i}"] = err(prob1, mid[f"depth_prob_{i}"][0])
+        for with_feat in (True, False):
+            pk_tc = packing.pack_cost_reg(sd, f"cost_reg_{i}", int(32 * 2 ** (-i)), deep, dev, with_feat, tensor_cores=True)
+            vol_t = torch.full((D, h, w, 8), float("nan"), **f32) if with_feat else None
+            prob_t = torch.full((D, h, w), float("nan"), **f32)
+            capi.cost_reg(pk_tc, deep, ndhwc(mid[f"variance_{i}"][0]), vol_t, prob_t, rws, tensor_cores=True)
+            if with_feat:
+                rep[f"cost_reg_tc.feat_volume_{i}"] = err(vol_t.permute(3, 0, 1, 2), mid[f"feat_volume_{i}"][0])
+                rep[f"cost_reg_tc.depth_prob_{i}"] = err(prob_t, mid[f"depth_prob_{i}"][0])
+            else:
+                rep[f"cost_reg_tc.depth_prob_only_{i}"] = err(prob_t, mid[f"depth_prob_{i}"][0])
         # depth regression fed with oracle prob (and the oracle-equivalent ends computed above)
         depth = torch.empty((h, w), **f32)
         std = torch.empty((h, w), **f32)

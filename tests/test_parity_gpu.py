@@ -32,7 +32,7 @@ def _check_report(rep, e2e_tol=E2E_TOL):
             continue
         if k.startswith("e2e."):
             tol = e2e_tol[k[4:].split("_level")[0]] * max(1.0, v["ref_max"])
-        elif k.startswith("render_rays_tc."):
+        elif k.split(".")[0] in ("render_rays_tc", "feature_net_tc", "cost_reg_tc"):
             tol = TC_STAGE_TOL * max(1.0, v["ref_max"])
         else:
             tol = STAGE_TOL * max(1.0, v["ref_max"])
