@@ -1,8 +1,5 @@
-// tc_conv.cu -- host side of the tcgen05 implicit-GEMM convolution (kernel + design: tc_conv.cuh):
-// tile selection, TMA tensor-map encoding (cuTensorMapEncodeTiled through the runtime's driver
-// entry point -- no link-time dependency on libcuda), launch, and the C-ABI test/diagnostic entry.
-#include <cudaTypedefs.h>
-
+// tc_conv.cu -- the tcgen05 implicit-GEMM convolution kernel (design: tc_conv.cuh), tile selection,
+// launch, and the C-ABI test/diagnostic entry.
 #include "tc_conv.cuh"
 
 namespace enerf {
@@ -28,7 +25,25 @@ struct TcConvParams {
   float* out2;           // TC_HEAD: depth_prob
 };
 
-__global__ void __launch_bounds__(128) tc_conv_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams P) {
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+// Activation staging: the halo tile of 8 input channels is copied global (channels-last) -> shared
+// ([chunk][pixel][16 B]) with 16-byte cp.async; lanes 2p, 2p+1 fetch the two chunks of pixel p, so a
+// warp instruction reads 16 complete 32-byte sectors.  (A 5-D TMA box can express the same scatter,
+// but its inner row is only 16 bytes and the TMA unit then delivers ~1 B/clk/SM -- measured 3-5x
+// slower than the FP32 kernels; see DESIGN.md.)  Out-of-volume pixels are zero-filled (src-size 0)
+// = the convolution's zero padding.  The stage's weights arrive by one TMA bulk copy.
+__global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ in, int cin, const TcConvParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], done_bar;
   __shared__ uint32_t tmem_base_s;
@@ -38,56 +53,86 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const __grid_constant__ CU
   const uint32_t w_bytes = (uint32_t)P.n_taps * (uint32_t)P.N * 32u;
   const uint32_t stage_bytes = (a_bytes + w_bytes + 127u) & ~127u;
   unsigned char* stage0 = smem_raw;
+  int* pix_off = reinterpret_cast<int*>(smem_raw + 2 * (size_t)stage_bytes);   // [npix] global pixel index or -1
 
   if (t == 0) {
-    tc::prefetch_tmap(&tmap);
-    tc::mbar_init(&full_bar[0], 1);
-    tc::mbar_init(&full_bar[1], 1);
+    tc::mbar_init(&full_bar[0], 129);   // 128 copier threads + the weight copy's expect_tx arrival
+    tc::mbar_init(&full_bar[1], 129);
     tc::mbar_init(&empty_bar[0], 1);
     tc::mbar_init(&empty_bar[1], 1);
     tc::mbar_init(&done_bar, 1);
     tc::fence_mbar_init();
   }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, P.tmem_cols);
+  const int x0 = blockIdx.x * P.TX, y0 = blockIdx.y * P.TY, z0 = blockIdx.z * P.TZ;
+  {
+    const int plane = P.IY * P.IX;
+    for (int p = t; p < npix; p += 128) {
+      const int z = p / plane, rem = p - z * plane, y = rem / P.IX, x = rem - y * P.IX;
+      const int gz = z0 - P.oz + z, gy = y0 - P.oy + y, gx = x0 - P.ox + x;
+      const bool ok = gz >= 0 && gz < P.Dn && gy >= 0 && gy < P.Hn && gx >= 0 && gx < P.Wn;
+      pix_off[p] = ok ? (gz * P.Hn + gy) * P.Wn + gx : -1;
+    }
+  }
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
 
-  const int x0 = blockIdx.x * P.TX, y0 = blockIdx.y * P.TY, z0 = blockIdx.z * P.TZ;
-
-  if (t == 32) {
-    // ---------------- TMA producer ----------------
-    for (int st = 0; st < P.n_stages; ++st) {
-      const int slot = st & 1;
-      if (st >= 2) tc::mbar_wait(&empty_bar[slot], (uint32_t)(((st - 2) >> 1) & 1));
-      unsigned char* sa = stage0 + (size_t)slot * stage_bytes;
-      tc::mbar_expect_tx(&full_bar[slot], a_bytes + w_bytes);
-      tc::tma_load_5d(sa, &tmap, 0, x0 - P.ox, y0 - P.oy, z0 - P.oz, 2 * st, &full_bar[slot]);
+  auto issue_stage = [&](int st) {
+    const int slot = st & 1;
+    unsigned char* sa = stage0 + (size_t)slot * stage_bytes;
+    if (t == 32) {
+      tc::mbar_expect_tx(&full_bar[slot], w_bytes);
       tc::tma_load_1d(sa + a_bytes, P.wpack + (size_t)st * (w_bytes / 4), w_bytes, &full_bar[slot]);
     }
-  } else if (t == 0) {
-    // ---------------- MMA issuer ----------------
-    const uint32_t idesc = tc::idesc_tf32(128, P.N);
-    const uint32_t lbo_a = (uint32_t)npix * 16u, lbo_b = (uint32_t)P.N * 16u;
-    for (int st = 0; st < P.n_stages; ++st) {
-      const int slot = st & 1;
+    const uint32_t sa_u = tc::smem_u32(sa);
+    const float* src0 = in + 8 * st;
+    for (int e = t; e < 2 * npix; e += 128) {
+      const int j = e & 1, p = e >> 1;
+      const int off = pix_off[p];
+      const float* src = src0 + (off >= 0 ? (size_t)off * cin + 4 * j : 0);
+      cp_async16_zfill(sa_u + (uint32_t)j * (uint32_t)npix * 16u + (uint32_t)p * 16u, src, off >= 0 ? 16u : 0u);
+    }
+    cp_async_commit();
+  };
+
+  issue_stage(0);
+  if (P.n_stages > 1) issue_stage(1);
+  const uint32_t idesc = tc::idesc_tf32(128, P.N);
+  const uint32_t lbo_a = (uint32_t)npix * 16u, lbo_b = (uint32_t)P.N * 16u;
+  int tap_r[27];                                   // tap offsets in registers (MMA issuer only uses them)
+#pragma unroll
+  for (int tp = 0; tp < 27; ++tp) tap_r[tp] = P.tap_off[tp < P.n_taps ? tp : 0];
+  for (int st = 0; st < P.n_stages; ++st) {
+    const int slot = st & 1;
+    if (st + 1 < P.n_stages) cp_async_wait<1>(); else cp_async_wait<0>();
+    tc::fence_proxy_async();                      // my copies -> visible to the tensor core
+    mbar_arrive(&full_bar[slot]);
+    if (t == 0) {
       tc::mbar_wait(&full_bar[slot], (uint32_t)((st >> 1) & 1));
       tc::tc_fence_after_sync();
       const uint32_t sa = tc::smem_u32(stage0 + (size_t)slot * stage_bytes);
-      const uint32_t sb = sa + a_bytes;
+      // descriptors differ only in their 14-bit start-address field: build the constant part once
+      const uint64_t a_hi = tc::smem_desc(0, lbo_a, 128u), b_hi = tc::smem_desc(0, lbo_b, 128u);
+      const uint32_t a0 = sa >> 4, b0 = (sa + a_bytes) >> 4, b_step = (2u * lbo_b) >> 4;
       for (int m = 0; m < P.n_mt; ++m) {
-        for (int tp = 0; tp < P.n_taps; ++tp) {
-          const uint64_t ad = tc::smem_desc(sa + (uint32_t)(m * 128 + P.tap_off[tp]) * 16u, lbo_a, 128u);
-          const uint64_t bd = tc::smem_desc(sb + (uint32_t)tp * 2u * lbo_b, lbo_b, 128u);
-          tc::mma_tf32(tmem + (uint32_t)(m * P.N), ad, bd, idesc, (st > 0 || tp > 0) ? 1u : 0u);
+        const uint32_t am = a0 + (uint32_t)(m * 128), td = tmem + (uint32_t)(m * P.N);
+#pragma unroll
+        for (int tp = 0; tp < 27; ++tp) {
+          if (tp < P.n_taps)
+            tc::mma_tf32_stream(td, a_hi | (uint64_t)((am + (uint32_t)tap_r[tp]) & 0x3FFFu), b_hi | (uint64_t)((b0 + (uint32_t)tp * b_step) & 0x3FFFu),
+                                idesc, (st > 0 || tp > 0) ? 1u : 0u);
         }
       }
-      tc::mma_commit(&empty_bar[slot]);   // frees the smem slot once these MMAs have read it
+      tc::mma_commit(&empty_bar[slot]);           // frees the slot once these MMAs have read it
+      if (st + 1 == P.n_stages) tc::mma_commit(&done_bar);
     }
-    tc::mma_commit(&done_bar);
+    if (st + 2 < P.n_stages) {
+      tc::mbar_wait(&empty_bar[slot], (uint32_t)((st >> 1) & 1));
+      issue_stage(st + 2);
+    }
   }
-  __syncwarp();
 
   // ---------------- epilogue: 128 threads = 128 accumulator rows ----------------
   tc::mbar_wait(&done_bar, 0);
@@ -152,17 +197,6 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const __grid_constant__ CU
   if (warp == 0) tc::tmem_dealloc(tmem, P.tmem_cols);
 }
 
-static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-  }
-  return fn;
-}
-
 int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias,
                    const float* skip, float* out, float* out2, int out_cstride, int out_coff, cudaStream_t stream) {
   ENERF_REQUIRE(L.cin % 8 == 0 && L.cin >= 8, ENERF_EUNSUPPORTED, "tc_conv: cin %d must be a multiple of 8", L.cin);
@@ -204,7 +238,10 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
     const int npix = P.IZ * P.IY * P.IX;
     stage_bytes = ((uint32_t)npix * 32u + (uint32_t)P.n_taps * (uint32_t)P.N * 32u + 127u) & ~127u;
     const int max_off = P.tap_off[P.n_taps - 1];
-    smem = 2 * (size_t)stage_bytes + (size_t)(P.n_mt * 128 + max_off + 8) * 16;
+    // [stage 0][stage 1][pixel table][tail]: rows past the end of the second plane of the last
+    // slot (only the dropped garbage rows read them) must stay inside the allocation
+    const int overflow_rows = P.n_mt * 128 + max_off - npix;
+    smem = 2 * (size_t)stage_bytes + (size_t)npix * 4 + 64 + (overflow_rows > 0 ? (size_t)overflow_rows * 16 : 0);
     if (P.n_mt * P.N <= 512 && smem <= 200 * 1024) break;
     if (P.TY > 2) P.TY /= 2;
     else if (P.TZ > 1) P.TZ /= 2;
@@ -214,19 +251,6 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
   while ((int)cols < P.n_mt * P.N) cols <<= 1;
   P.tmem_cols = cols;
 
-  PFN_cuTensorMapEncodeTiled_v12000 encode = get_encode();
-  ENERF_REQUIRE(encode != nullptr, ENERF_ECUDA, "tc_conv: cuTensorMapEncodeTiled entry point unavailable");
-  CUtensorMap tmap;
-  const cuuint64_t dims[5] = {4, (cuuint64_t)Wn, (cuuint64_t)Hn, (cuuint64_t)Dn, (cuuint64_t)(L.cin / 4)};
-  const cuuint64_t strides[4] = {(cuuint64_t)L.cin * 4, (cuuint64_t)Wn * L.cin * 4, (cuuint64_t)Hn * Wn * L.cin * 4, 16};
-  const cuuint32_t box[5] = {4, (cuuint32_t)P.IX, (cuuint32_t)P.IY, (cuuint32_t)P.IZ, 2};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(in), dims, strides, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  ENERF_REQUIRE(cr == CUDA_SUCCESS, ENERF_ECUDA, "tc_conv: cuTensorMapEncodeTiled failed (%d) dims %dx%dx%dx%d box %dx%dx%d", (int)cr,
-                Dn, Hn, Wn, L.cin, P.IZ, P.IY, P.IX);
-
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -234,7 +258,7 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
     smem_set = smem;
   }
   dim3 grid(ceil_div(Wn, P.TX), ceil_div(Hn, P.TY), ceil_div(Dn, P.TZ));
-  tc_conv_kernel<<<grid, 128, smem, stream>>>(tmap, P);
+  tc_conv_kernel<<<grid, 128, smem, stream>>>(in, L.cin, P);
   ENERF_CHECK_LAUNCH("tc_conv");
   return ENERF_OK;
 }

@@ -2,17 +2,17 @@
 // accumulation in TMEM) for the channels-last CNNs of ENeRF: every stride-1 convolution of
 // FeatureNet / (Min)CostRegNet, and the ConvTranspose3d layers in 8-phase sub-pixel form.
 //
-// Formulation.  A CTA owns a TZ x TY x TX tile of positions.  TMA (cp.async.bulk.tensor.5d) stages
-// the tile PLUS its halo, 8 input channels at a time, as two planes [c4][z][y][x][4 floats]; the
-// volume's zero padding is TMA's out-of-bounds fill.  In that layout "pixel p, channels 4c..4c+3"
+// Formulation.  A CTA owns a TZ x TY x TX tile of positions.  The tile PLUS its halo is staged in
+// shared memory 8 input channels at a time as two planes [c4][z][y][x][4 floats] (16-byte cp.async
+// with zero fill = the volume's zero padding).  In that layout "pixel p, channels 4c..4c+3"
 // sits at  c*PLANE + p*16 bytes, which is exactly the K-major / no-swizzle UMMA operand layout
 // (tc.cuh) with rows = consecutive LINEAR halo positions.  So the A operand of filter tap
 // (kz,ky,kx) for the 128 positions p0..p0+127 is the SAME buffer with its start address advanced
 // by ((kz*IY+ky)*IX+kx)*16 bytes: the 27 taps are 27 descriptors, no im2col copy exists anywhere.
 // Rows whose linear position falls in the halo columns compute garbage and are dropped in the
 // epilogue (73-84 % of the issued rows are real outputs; the tensor pipe is far from the limit).
-//   K loop : Cin/8 stages, 2-deep TMA ring (full/empty mbarriers), weights of the stage arrive by
-//            a 1-D bulk copy next to the activations.
+//   K loop : Cin/8 stages, 2-deep ring (full/empty mbarriers); the stage's weights arrive by one
+//            TMA bulk copy (cp.async.bulk) next to the activations.
 //   MMA    : one thread issues n_stages * n_mtiles * n_taps tcgen05.mma (M=128, N=Cout padded to
 //            16, K=8); accumulators of all M-tiles of the CTA live in TMEM (n_mtiles*N columns).
 //   Epilogue: 128 threads = 128 TMEM lanes; tcgen05.ld, bias / ReLU / skip add, coalesced
