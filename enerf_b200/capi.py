@@ -41,6 +41,7 @@ _SIGS = {
     "enerf_render_rays_tc": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i,
                                   _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "enerf_tc_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "enerf_tc_conv_debug": (_i, [_vp]),
     "enerf_tc_selftest": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
@@ -190,3 +191,8 @@ def tc_conv(kind, KD, KH, cout, mode, relu, x, wpack, bias, skip, out, out2=None
     _check(lib().enerf_tc_conv(kind, KD, KH, cin, cout, mode, int(relu), ptr(x), D, H, W, ptr(wpack), ptr(bias, True), ptr(skip, True),
                                ptr(out), ptr(out2, True), out_cstride if out_cstride is not None else cout, out_coff, stream()),
            "enerf_tc_conv")
+
+
+def tc_conv_debug(buf):
+    """buf: int64 CUDA tensor of 64 elements (or None to switch the phase stamps off)."""
+    _check(lib().enerf_tc_conv_debug(buf.data_ptr() if buf is not None else None), "enerf_tc_conv_debug", launches=0)

@@ -25,6 +25,18 @@ struct TcConvParams {
   float* out2;           // TC_HEAD: depth_prob
 };
 
+// Optional phase timestamps (ns, %globaltimer) of CTA (0,0,0): set through enerf_tc_conv_debug.
+__device__ unsigned long long* g_tc_dbg = nullptr;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(slot_)                                                                         \
+  do {                                                                                          \
+    if (dbg && (slot_) < 64) dbg[(slot_)] = gtime();                                            \
+  } while (0)
+
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -48,6 +60,8 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
   __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], done_bar;
   __shared__ uint32_t tmem_base_s;
   const int t = threadIdx.x, warp = t >> 5;
+  unsigned long long* dbg = (g_tc_dbg && t == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_tc_dbg : nullptr;
+  TC_STAMP(0);
   const int npix = P.IZ * P.IY * P.IX;
   const uint32_t a_bytes = (uint32_t)npix * 32u;                   // two 4-channel planes
   const uint32_t w_bytes = (uint32_t)P.n_taps * (uint32_t)P.N * 32u;
@@ -78,6 +92,7 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
+  TC_STAMP(1);
 
   auto issue_stage = [&](int st) {
     const int slot = st & 1;
@@ -99,6 +114,7 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
 
   issue_stage(0);
   if (P.n_stages > 1) issue_stage(1);
+  TC_STAMP(2);
   const uint32_t idesc = tc::idesc_tf32(128, P.N);
   const uint32_t lbo_a = (uint32_t)npix * 16u, lbo_b = (uint32_t)P.N * 16u;
   int tap_r[27];                                   // tap offsets in registers (MMA issuer only uses them)
@@ -107,10 +123,13 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
   for (int st = 0; st < P.n_stages; ++st) {
     const int slot = st & 1;
     if (st + 1 < P.n_stages) cp_async_wait<1>(); else cp_async_wait<0>();
+    TC_STAMP(4 + 6 * st);                         // my copies of this stage have landed
     tc::fence_proxy_async();                      // my copies -> visible to the tensor core
     mbar_arrive(&full_bar[slot]);
+    TC_STAMP(5 + 6 * st);
     if (t == 0) {
       tc::mbar_wait(&full_bar[slot], (uint32_t)((st >> 1) & 1));
+      TC_STAMP(6 + 6 * st);                       // everyone's copies + weights visible
       tc::tc_fence_after_sync();
       const uint32_t sa = tc::smem_u32(stage0 + (size_t)slot * stage_bytes);
       // descriptors differ only in their 14-bit start-address field: build the constant part once
@@ -127,15 +146,19 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
       }
       tc::mma_commit(&empty_bar[slot]);           // frees the slot once these MMAs have read it
       if (st + 1 == P.n_stages) tc::mma_commit(&done_bar);
+      TC_STAMP(7 + 6 * st);                       // MMAs of this stage issued
     }
     if (st + 2 < P.n_stages) {
       tc::mbar_wait(&empty_bar[slot], (uint32_t)((st >> 1) & 1));
+      TC_STAMP(8 + 6 * st);                       // MMAs of this stage complete (slot free)
       issue_stage(st + 2);
+      TC_STAMP(9 + 6 * st);
     }
   }
 
   // ---------------- epilogue: 128 threads = 128 accumulator rows ----------------
   tc::mbar_wait(&done_bar, 0);
+  TC_STAMP(60);
   tc::tc_fence_after_sync();
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
   const int plane = P.IY * P.IX;
@@ -192,9 +215,11 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
       }
     }
   }
+  TC_STAMP(61);
   tc::tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, P.tmem_cols);
+  TC_STAMP(62);
 }
 
 int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias,
@@ -274,4 +299,15 @@ extern "C" int enerf_tc_conv(int kind, int KD, int KH, int cin, int cout, int mo
   ENERF_REQUIRE((KD == 1 || KD == 3) && (KH == 1 || KH == 3), ENERF_EUNSUPPORTED, "tc_conv: kernel %dx%dx%d", KD, KH, KH);
   TcConvLayer L{kind, KD, KH, cin, cout, mode, relu};
   return tc_conv_launch(L, in, D, H, W, wpack, bias, skip, out, out2, out_cstride, out_coff, (cudaStream_t)stream);
+}
+
+// Diagnostic: phase timestamps (64 x u64, ns) of CTA (0,0,0) of subsequent tc_conv launches are
+// written to `buf` (device memory); pass NULL to switch off.
+extern "C" int enerf_tc_conv_debug(unsigned long long* buf) {
+  cudaError_t e = cudaMemcpyToSymbol(enerf::g_tc_dbg, &buf, sizeof(buf));
+  if (e != cudaSuccess) {
+    enerf::set_error("tc_conv_debug: %s", cudaGetErrorString(e));
+    return ENERF_ECUDA;
+  }
+  return ENERF_OK;
 }

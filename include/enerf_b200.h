@@ -175,6 +175,10 @@ ENERF_API int enerf_tc_conv(int kind, int KD, int KH, int cin, int cout, int mod
                             int W, const float* wpack, const float* bias, const float* skip, float* out, float* out2,
                             int out_cstride, int out_coff, void* stream);
 
+/* Diagnostic: when buf != NULL, CTA (0,0,0) of every later enerf_tc_conv-family launch writes 64
+ * %globaltimer phase stamps (ns) into buf (device memory, 64 x u64).  NULL switches it off. */
+ENERF_API int enerf_tc_conv_debug(unsigned long long* buf);
+
 /* Diagnostic: D[128 x N] = A[128 x K] * B[N x K]^T on the tensor cores (tcgen05.mma kind::tf32,
  * accumulator in TMEM) through the same descriptor helpers the fused kernels use (csrc/tc.cuh).
  * K multiple of 8 (<=128), N multiple of 16 (<=256); A, B row-major.  No reference counterpart. */
