@@ -42,6 +42,7 @@ _SIGS = {
                                   _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "enerf_tc_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "enerf_tc_conv_debug": (_i, [_vp]),
+    "enerf_tc_mma_bench": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "enerf_tc_selftest": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
@@ -196,3 +197,10 @@ def tc_conv(kind, KD, KH, cout, mode, relu, x, wpack, bias, skip, out, out2=None
 def tc_conv_debug(buf):
     """buf: int64 CUDA tensor of 64 elements (or None to switch the phase stamps off)."""
     _check(lib().enerf_tc_conv_debug(buf.data_ptr() if buf is not None else None), "enerf_tc_conv_debug", launches=0)
+
+
+def tc_mma_bench(layout, N, n_mma, accs=1):
+    out = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _check(lib().enerf_tc_mma_bench(layout, N, n_mma, accs, out.data_ptr(), stream()), "enerf_tc_mma_bench")
+    torch.cuda.synchronize()
+    return int(out.item())

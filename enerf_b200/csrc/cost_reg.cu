@@ -252,10 +252,9 @@ extern "C" int enerf_cost_reg(const float* const* wts, int n_weights, int deep, 
     TcConvLayer L{1, 3, 3, cin, cout, TC_DECONV, 0};
     return tc_conv_launch(L, in, d_, h_, w_, wp, b, skip, o, nullptr, cout, 0, stream);
   };
-  // conv0 and the head run at full volume resolution with Cout <= 9: their implicit GEMMs have
-  // N = 16 and are bound by the tensor core's operand fetch, not by math -- the FP32-pipe direct
-  // convolution (45-58 % FMA utilisation) is faster there (143 vs 200 us, 82 vs 111 us measured).
-  if (in_ch == 32) {
+  if (tensor_cores) {
+    RUN(tc_cbr(in_ch, 8, variance, D, h, w, wts[0], wts[1], ws.c0));
+  } else if (in_ch == 32) {
     RUN(launch_conv<C0_32>("cost_reg.conv0", variance, wts[0], wts[1], ws.c0, nullptr, D, h, w, 8, 0, stream));
   } else if (in_ch == 16) {
     RUN(launch_conv<C0_16>("cost_reg.conv0", variance, wts[0], wts[1], ws.c0, nullptr, D, h, w, 8, 0, stream));
@@ -295,7 +294,10 @@ extern "C" int enerf_cost_reg(const float* const* wts, int n_weights, int deep, 
     RUN((launch_deconv<32, 16>("cost_reg.conv9", x4, wts[wi], wts[wi + 1], ws.c2, ws.y2, D4, h4, w4, stream)));
     RUN((launch_deconv<16, 8>("cost_reg.conv11", ws.y2, wts[wi + 2], wts[wi + 3], ws.c0, ws.y0, D2, h2, w2, stream)));
   }
-  {
+  if (tensor_cores) {
+    TcConvLayer Lh{0, 3, 3, 8, feat_vol ? 9 : 1, feat_vol ? TC_HEAD : TC_SINGLE, 0};
+    RUN(tc_conv_launch(Lh, ws.y0, D, h, w, wts[wi + 4], nullptr, nullptr, feat_vol ? feat_vol : depth_prob, depth_prob, 8, 0, stream));
+  } else {
     if (feat_vol) {
       RUN(launch_conv<Head9>("cost_reg.head9", ws.y0, wts[wi + 4], nullptr, feat_vol, depth_prob, D, h, w, 8, 0, stream));
     } else {

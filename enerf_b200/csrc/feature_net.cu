@@ -174,9 +174,11 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
     return tc_conv_launch(L, in, S, h, w, wp, b, nullptr, o, nullptr, cout, 0, stream);
   };
   RUN(launch_conv<Conv00>("feature_net.conv0.0", src_inps, wts[0], wts[1], ws.c0a, nullptr, S, H, W, 8, 0, stream));
-  // conv0.1 (8->8 at full resolution) stays on the FP32 pipe: one K-stage of 9 tiny MMAs per tile
-  // does not amortise the tensor-core hand-off (measured 51 us FP32 vs 58 us tcgen05)
-  RUN(launch_conv<Conv01>("feature_net.conv0.1", ws.c0a, wts[2], wts[3], ws.c0, nullptr, S, H, W, 8, 0, stream));
+  if (tensor_cores) {
+    RUN(tc("feature_net.conv0.1", 3, 8, 8, 1, ws.c0a, H, W, wts[2], wts[3], ws.c0));
+  } else {
+    RUN(launch_conv<Conv01>("feature_net.conv0.1", ws.c0a, wts[2], wts[3], ws.c0, nullptr, S, H, W, 8, 0, stream));
+  }
   RUN(launch_conv<Conv10>("feature_net.conv1.0", ws.c0, wts[4], wts[5], ws.c1a, nullptr, S, H, W, 16, 0, stream));
   if (tensor_cores) {
     RUN(tc("feature_net.conv1.1", 3, 16, 16, 1, ws.c1a, H2, W2, wts[6], wts[7], ws.c1));
@@ -186,10 +188,11 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
   RUN(launch_conv<Conv20>("feature_net.conv2.0", ws.c1, wts[8], wts[9], ws.c2a, nullptr, S, H2, W2, 32, 0, stream));
   if (tensor_cores) {
     RUN(tc("feature_net.conv2.1", 3, 32, 32, 1, ws.c2a, H4, W4, wts[10], wts[11], ws.c2));
+    RUN(tc("feature_net.toplayer", 1, 32, 32, 0, ws.c2, H4, W4, wts[12], wts[13], feat_l0));
   } else {
     RUN(launch_conv<Conv21>("feature_net.conv2.1", ws.c2a, wts[10], wts[11], ws.c2, nullptr, S, H4, W4, 32, 0, stream));
+    RUN(launch_conv<Top>("feature_net.toplayer", ws.c2, wts[12], wts[13], feat_l0, nullptr, S, H4, W4, 32, 0, stream));
   }
-  RUN(launch_conv<Top>("feature_net.toplayer", ws.c2, wts[12], wts[13], feat_l0, nullptr, S, H4, W4, 32, 0, stream));  // 1x1: FP32 (16 us)
   {
     const long long total = (long long)S * H2 * W2 * 4;
     const int blocks = (int)((total + 255) / 256);

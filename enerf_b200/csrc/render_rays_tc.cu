@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
   tc::tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);     // warp-uniform copy for the MMA issue
   const uint32_t a_addr = tc::smem_u32(a_s), w_addr = tc::smem_u32(sw);
   uint32_t phase = 0;
 
@@ -293,16 +294,19 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
 
     // ================= G1: global_fc =================
     sync_then_issue();
-    if (t == 0) {
+    if (warp == 0) {   // converged warp, uniform operands, one elected lane issues (tc::mma_tf32_elect)
+     {
       const uint32_t id = tc::idesc_tf32(128, 32);
 #pragma unroll
       for (int s = 0; s < S; ++s) {
 #pragma unroll
-        for (int kk = 0; kk < 3; ++kk) tc::mma_tf32(tmem + s * 32, a_desc(4 * S + 2 * kk), b_desc(TcW::bg_shared, 2 * kk, 32), id, kk > 0);
+        for (int kk = 0; kk < 3; ++kk) tc::mma_tf32_elect(tmem_u + s * 32, a_desc(4 * S + 2 * kk), b_desc(TcW::bg_shared, 2 * kk, 32), id, kk > 0);
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) tc::mma_tf32(tmem + s * 32, a_desc(4 * s + 2 * kk), b_desc(TcW::bg_view, 2 * kk, 32), id, 1);
+        for (int kk = 0; kk < 2; ++kk) tc::mma_tf32_elect(tmem_u + s * 32, a_desc(4 * s + 2 * kk), b_desc(TcW::bg_view, 2 * kk, 32), id, 1);
       }
-      tc::mma_commit(&bar);
+      tc::mma_commit_elect(&bar);
+     }
+     __syncwarp();
     }
     wait_mma();
     // ---- E1: ReLU, agg_w_fc logits, softmax over views, weighted pooling ----
@@ -343,11 +347,14 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
     }
     // ================= G2: fc 32 -> 16 =================
     sync_then_issue();
-    if (t == 0) {
+    if (warp == 0) {   // converged warp, uniform operands, one elected lane issues (tc::mma_tf32_elect)
+     {
       const uint32_t id = tc::idesc_tf32(128, 16);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) tc::mma_tf32(tmem, a_desc(2 * kk), b_desc(TcW::bfc, 2 * kk, 16), id, kk > 0);
-      tc::mma_commit(&bar);
+      for (int kk = 0; kk < 4; ++kk) tc::mma_tf32_elect(tmem_u, a_desc(2 * kk), b_desc(TcW::bfc, 2 * kk, 16), id, kk > 0);
+      tc::mma_commit_elect(&bar);
+     }
+     __syncwarp();
     }
     wait_mma();
     {
@@ -364,11 +371,14 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
     }
     // ================= G3: lr0 24 -> 64 =================
     sync_then_issue();
-    if (t == 0) {
+    if (warp == 0) {   // converged warp, uniform operands, one elected lane issues (tc::mma_tf32_elect)
+     {
       const uint32_t id = tc::idesc_tf32(128, 64);
 #pragma unroll
-      for (int kk = 0; kk < 3; ++kk) tc::mma_tf32(tmem, a_desc(16 + 2 * kk), b_desc(TcW::b0, 2 * kk, 64), id, kk > 0);
-      tc::mma_commit(&bar);
+      for (int kk = 0; kk < 3; ++kk) tc::mma_tf32_elect(tmem_u, a_desc(16 + 2 * kk), b_desc(TcW::b0, 2 * kk, 64), id, kk > 0);
+      tc::mma_commit_elect(&bar);
+     }
+     __syncwarp();
     }
     wait_mma();
     float sigma;
@@ -391,16 +401,19 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
     }
     // ================= G5: color.0 =================
     sync_then_issue();
-    if (t == 0) {
+    if (warp == 0) {   // converged warp, uniform operands, one elected lane issues (tc::mma_tf32_elect)
+     {
       const uint32_t id = tc::idesc_tf32(128, 64);
 #pragma unroll
       for (int s = 0; s < S; ++s) {
 #pragma unroll
-        for (int kk = 0; kk < 11; ++kk) tc::mma_tf32(tmem + s * 64, a_desc(2 * kk), b_desc(TcW::bc_shared, 2 * kk, 64), id, kk > 0);
+        for (int kk = 0; kk < 11; ++kk) tc::mma_tf32_elect(tmem_u + s * 64, a_desc(2 * kk), b_desc(TcW::bc_shared, 2 * kk, 64), id, kk > 0);
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) tc::mma_tf32(tmem + s * 64, a_desc(22 + 4 * s + 2 * kk), b_desc(TcW::bc_view, 2 * kk, 64), id, 1);
+        for (int kk = 0; kk < 2; ++kk) tc::mma_tf32_elect(tmem_u + s * 64, a_desc(22 + 4 * s + 2 * kk), b_desc(TcW::bc_view, 2 * kk, 64), id, 1);
       }
-      tc::mma_commit(&bar);
+      tc::mma_commit_elect(&bar);
+     }
+     __syncwarp();
     }
     wait_mma();
     float cr = 0.f, cg = 0.f, cb = 0.f;

@@ -55,6 +55,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // but its inner row is only 16 bytes and the TMA unit then delivers ~1 B/clk/SM -- measured 3-5x
 // slower than the FP32 kernels; see DESIGN.md.)  Out-of-volume pixels are zero-filled (src-size 0)
 // = the convolution's zero padding.  The stage's weights arrive by one TMA bulk copy.
+template <int NTAPS, int MODE>
 __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ in, int cin, const TcConvParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], done_bar;
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
   TC_STAMP(0);
   const int npix = P.IZ * P.IY * P.IX;
   const uint32_t a_bytes = (uint32_t)npix * 32u;                   // two 4-channel planes
-  const uint32_t w_bytes = (uint32_t)P.n_taps * (uint32_t)P.N * 32u;
+  const uint32_t w_bytes = (uint32_t)NTAPS * (uint32_t)P.N * 32u;
   const uint32_t stage_bytes = (a_bytes + w_bytes + 127u) & ~127u;
   unsigned char* stage0 = smem_raw;
   int* pix_off = reinterpret_cast<int*>(smem_raw + 2 * (size_t)stage_bytes);   // [npix] global pixel index or -1
@@ -117,9 +118,7 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
   TC_STAMP(2);
   const uint32_t idesc = tc::idesc_tf32(128, P.N);
   const uint32_t lbo_a = (uint32_t)npix * 16u, lbo_b = (uint32_t)P.N * 16u;
-  int tap_r[27];                                   // tap offsets in registers (MMA issuer only uses them)
-#pragma unroll
-  for (int tp = 0; tp < 27; ++tp) tap_r[tp] = P.tap_off[tp < P.n_taps ? tp : 0];
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform copy of the TMEM base
   for (int st = 0; st < P.n_stages; ++st) {
     const int slot = st & 1;
     if (st + 1 < P.n_stages) cp_async_wait<1>(); else cp_async_wait<0>();
@@ -127,7 +126,9 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
     tc::fence_proxy_async();                      // my copies -> visible to the tensor core
     mbar_arrive(&full_bar[slot]);
     TC_STAMP(5 + 6 * st);
-    if (t == 0) {
+    // MMA issue: the whole warp 0, converged, warp-uniform operands, one elected lane issues
+    // (tc::mma_tf32_elect).  Lanes never spin next to a divergent issuer.
+    if (warp == 0) {
       tc::mbar_wait(&full_bar[slot], (uint32_t)((st >> 1) & 1));
       TC_STAMP(6 + 6 * st);                       // everyone's copies + weights visible
       tc::tc_fence_after_sync();
@@ -136,17 +137,16 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
       const uint64_t a_hi = tc::smem_desc(0, lbo_a, 128u), b_hi = tc::smem_desc(0, lbo_b, 128u);
       const uint32_t a0 = sa >> 4, b0 = (sa + a_bytes) >> 4, b_step = (2u * lbo_b) >> 4;
       for (int m = 0; m < P.n_mt; ++m) {
-        const uint32_t am = a0 + (uint32_t)(m * 128), td = tmem + (uint32_t)(m * P.N);
+        const uint32_t am = a0 + (uint32_t)(m * 128), td = tmem_u + (uint32_t)(m * P.N);
 #pragma unroll
-        for (int tp = 0; tp < 27; ++tp) {
-          if (tp < P.n_taps)
-            tc::mma_tf32_stream(td, a_hi | (uint64_t)((am + (uint32_t)tap_r[tp]) & 0x3FFFu), b_hi | (uint64_t)((b0 + (uint32_t)tp * b_step) & 0x3FFFu),
-                                idesc, (st > 0 || tp > 0) ? 1u : 0u);
-        }
+        for (int tp = 0; tp < NTAPS; ++tp)
+          tc::mma_tf32_elect(td, a_hi | (uint64_t)((am + (uint32_t)P.tap_off[tp]) & 0x3FFFu),
+                             b_hi | (uint64_t)((b0 + (uint32_t)tp * b_step) & 0x3FFFu), idesc, (st > 0 || tp > 0) ? 1u : 0u);
       }
-      tc::mma_commit(&empty_bar[slot]);           // frees the slot once these MMAs have read it
-      if (st + 1 == P.n_stages) tc::mma_commit(&done_bar);
+      tc::mma_commit_elect(&empty_bar[slot]);     // frees the slot once these MMAs have read it
+      if (st + 1 == P.n_stages) tc::mma_commit_elect(&done_bar);
       TC_STAMP(7 + 6 * st);                       // MMAs of this stage issued
+      __syncwarp();
     }
     if (st + 2 < P.n_stages) {
       tc::mbar_wait(&empty_bar[slot], (uint32_t)((st >> 1) & 1));
@@ -162,56 +162,70 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
   tc::tc_fence_after_sync();
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
   const int plane = P.IY * P.IX;
+  // linear halo position of this thread's row in M-tile 0, advanced by 128 per M-tile
+  int z = t / plane, rem = t - z * plane, y = rem / P.IX, x = rem - y * P.IX;
   for (int m = 0; m < P.n_mt; ++m) {
-    const int p = m * 128 + t;
-    const int z = p / plane, rem = p - z * plane, y = rem / P.IX, x = rem - y * P.IX;
     const int gz = z0 + z, gy = y0 + y, gx = x0 + x;
     const bool valid = (z < P.TZ) && (y < P.TY) && (x < P.TX) && (gz < P.Dn) && (gy < P.Hn) && (gx < P.Wn);
     const size_t pix = ((size_t)gz * P.Hn + gy) * P.Wn + gx;
-    for (int c0 = 0; c0 < P.N; c0 += 16) {
-      float v[16];
-      tc::tmem_ld16(trow + (uint32_t)(m * P.N + c0), v);
-      tc::tmem_ld_wait();
-      if (!valid) continue;
-      if (P.mode == TC_PLAIN) {
-        if (c0 >= P.cout) continue;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (c0 + j < P.cout) {
-            v[j] += P.bias ? __ldg(P.bias + c0 + j) : 0.f;
-            if (P.relu) v[j] = fmaxf(v[j], 0.f);
+    if constexpr (MODE == TC_PLAIN) {
+      for (int c0 = 0; c0 < P.cout; c0 += 8) {       // cout is a multiple of 8
+        float v[8];
+        tc::tmem_ld8(trow + (uint32_t)(m * P.N + c0), v);
+        tc::tmem_ld_wait();
+        if (valid) {
+          const float4 b0v = ldg4(P.bias + c0), b1v = ldg4(P.bias + c0 + 4);
+          float4 o0 = make_float4(v[0] + b0v.x, v[1] + b0v.y, v[2] + b0v.z, v[3] + b0v.w);
+          float4 o1 = make_float4(v[4] + b1v.x, v[5] + b1v.y, v[6] + b1v.z, v[7] + b1v.w);
+          if (P.relu) {
+            o0 = make_float4(fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f));
+            o1 = make_float4(fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f));
           }
+          float4* o = reinterpret_cast<float4*>(P.out + pix * P.out_cstride + P.out_coff + c0);
+          o[0] = o0;
+          o[1] = o1;
         }
-        float* o = P.out + pix * P.out_cstride + P.out_coff + c0;
-        reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[3]);
-        reinterpret_cast<float4*>(o)[1] = make_float4(v[4], v[5], v[6], v[7]);
-        if (c0 + 8 < P.cout) {
-          reinterpret_cast<float4*>(o)[2] = make_float4(v[8], v[9], v[10], v[11]);
-          reinterpret_cast<float4*>(o)[3] = make_float4(v[12], v[13], v[14], v[15]);
-        }
-      } else if (P.mode == TC_HEAD) {   // feat_conv (8) + depth_conv (1), no bias
-        float* o = P.out + pix * 8;
-        reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[3]);
-        reinterpret_cast<float4*>(o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    } else if constexpr (MODE == TC_HEAD) {          // feat_conv (8) + depth_conv (1), no bias
+      float v[16];
+      tc::tmem_ld16(trow + (uint32_t)(m * P.N), v);
+      tc::tmem_ld_wait();
+      if (valid) {
+        float4* o = reinterpret_cast<float4*>(P.out + pix * 8);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
         P.out2[pix] = v[8];
-      } else if (P.mode == TC_SINGLE) {
-        P.out[pix] = v[0];
-      } else {  // TC_DECONV: columns = parity * cout + co ; out[2b+e] = skip + (acc + bias)
-        const int Ho = 2 * P.Hn, Wo = 2 * P.Wn;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = c0 + 8 * h;
+      }
+    } else if constexpr (MODE == TC_SINGLE) {
+      float v[8];
+      tc::tmem_ld8(trow + (uint32_t)(m * P.N), v);
+      tc::tmem_ld_wait();
+      if (valid) P.out[pix] = v[0];
+    } else {  // TC_DECONV: columns = parity * cout + co ; out[2b+e] = skip + (acc + bias)
+      const int Ho = 2 * P.Hn, Wo = 2 * P.Wn;
+      for (int c = 0; c < P.N; c += 8) {
+        float v[8];
+        tc::tmem_ld8(trow + (uint32_t)(m * P.N + c), v);
+        tc::tmem_ld_wait();
+        if (valid) {
           const int e = c / P.cout, co = c - e * P.cout;
           const size_t opix = ((size_t)(2 * gz + (e >> 2)) * Ho + (2 * gy + ((e >> 1) & 1))) * Wo + (2 * gx + (e & 1));
           const float* sk = P.skip + opix * P.cout + co;
           const float4 s0 = ldg4(sk), s1 = ldg4(sk + 4);
-          const float4 b0 = ldg4(P.bias + co), b1 = ldg4(P.bias + co + 4);
-          float* o = P.out + opix * P.cout + co;
-          reinterpret_cast<float4*>(o)[0] = make_float4(s0.x + (v[8 * h + 0] + b0.x), s0.y + (v[8 * h + 1] + b0.y),
-                                                        s0.z + (v[8 * h + 2] + b0.z), s0.w + (v[8 * h + 3] + b0.w));
-          reinterpret_cast<float4*>(o)[1] = make_float4(s1.x + (v[8 * h + 4] + b1.x), s1.y + (v[8 * h + 5] + b1.y),
-                                                        s1.z + (v[8 * h + 6] + b1.z), s1.w + (v[8 * h + 7] + b1.w));
+          const float4 b0v = ldg4(P.bias + co), b1v = ldg4(P.bias + co + 4);
+          float4* o = reinterpret_cast<float4*>(P.out + opix * P.cout + co);
+          o[0] = make_float4(s0.x + (v[0] + b0v.x), s0.y + (v[1] + b0v.y), s0.z + (v[2] + b0v.z), s0.w + (v[3] + b0v.w));
+          o[1] = make_float4(s1.x + (v[4] + b1v.x), s1.y + (v[5] + b1v.y), s1.z + (v[6] + b1v.z), s1.w + (v[7] + b1v.w));
         }
+      }
+    }
+    // advance the linear position by 128 without divisions
+    x += 128;
+    while (x >= P.IX) {
+      x -= P.IX;
+      if (++y == P.IY) {
+        y = 0;
+        ++z;
       }
     }
   }
@@ -267,7 +281,11 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
     // slot (only the dropped garbage rows read them) must stay inside the allocation
     const int overflow_rows = P.n_mt * 128 + max_off - npix;
     smem = 2 * (size_t)stage_bytes + (size_t)npix * 4 + 64 + (overflow_rows > 0 ? (size_t)overflow_rows * 16 : 0);
-    if (P.n_mt * P.N <= 512 && smem <= 200 * 1024) break;
+    const long long n_cta = (long long)ceil_div(Wn, P.TX) * ceil_div(Hn, P.TY) * ceil_div(Dn, P.TZ);
+    const bool fits = P.n_mt * P.N <= 512 && smem <= 200 * 1024;
+    // small layers: keep shrinking the tile until the grid covers the 148 SMs (fewer M-tiles per
+    // CTA = shorter serial MMA phases); large layers: the biggest tile that fits
+    if (fits && (n_cta >= 148 || (P.TY <= 2 && P.TZ <= 1))) break;
     if (P.TY > 2) P.TY /= 2;
     else if (P.TZ > 1) P.TZ /= 2;
     else ENERF_REQUIRE(false, ENERF_EUNSUPPORTED, "tc_conv: no tile fits (N=%d taps=%d)", P.N, P.n_taps);
@@ -276,14 +294,26 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
   while ((int)cols < P.n_mt * P.N) cols <<= 1;
   P.tmem_cols = cols;
 
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-    smem_set = smem;
-  }
+  ENERF_REQUIRE(L.mode != TC_PLAIN || (L.cout % 8 == 0 && bias), ENERF_EINVAL, "tc_conv: plain mode needs cout %% 8 == 0 and a bias");
   dim3 grid(ceil_div(Wn, P.TX), ceil_div(Hn, P.TY), ceil_div(Dn, P.TZ));
-  tc_conv_kernel<<<grid, 128, smem, stream>>>(in, L.cin, P);
+#define TC_LAUNCH(NT, MD)                                                                                          \
+  do {                                                                                                             \
+    static size_t smem_set = 0;                                                                                    \
+    if (smem > smem_set) {                                                                                         \
+      cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<NT, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e)); \
+      smem_set = smem;                                                                                             \
+    }                                                                                                              \
+    tc_conv_kernel<NT, MD><<<grid, 128, smem, stream>>>(in, L.cin, P);                                             \
+  } while (0)
+  if (L.kind == 1) TC_LAUNCH(8, TC_DECONV);
+  else if (P.n_taps == 27 && L.mode == TC_PLAIN) TC_LAUNCH(27, TC_PLAIN);
+  else if (P.n_taps == 27 && L.mode == TC_HEAD) TC_LAUNCH(27, TC_HEAD);
+  else if (P.n_taps == 27 && L.mode == TC_SINGLE) TC_LAUNCH(27, TC_SINGLE);
+  else if (P.n_taps == 9 && L.mode == TC_PLAIN) TC_LAUNCH(9, TC_PLAIN);
+  else if (P.n_taps == 1 && L.mode == TC_PLAIN) TC_LAUNCH(1, TC_PLAIN);
+  else ENERF_REQUIRE(false, ENERF_EUNSUPPORTED, "tc_conv: no instantiation for %d taps, mode %d", P.n_taps, L.mode);
+#undef TC_LAUNCH
   ENERF_CHECK_LAUNCH("tc_conv");
   return ENERF_OK;
 }

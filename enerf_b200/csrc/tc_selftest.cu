@@ -73,3 +73,62 @@ extern "C" int enerf_tc_selftest(const float* A, const float* B, int K, int N, f
   ENERF_CHECK_LAUNCH("tc_selftest");
   return ENERF_OK;
 }
+
+// ---- microbenchmark: sustained tcgen05.mma issue rate for a given operand layout / N ------------
+// One CTA; warp 0 issues `n_mma` MMAs (M=128, K=8 tf32) back to back on the same smem operands,
+// commits, waits; reports the elapsed %globaltimer ns.  layout: 0 = no swizzle (the layout the
+// kernels use), 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B (operand CONTENT is irrelevant
+// here, only fetch speed).  accs = number of distinct accumulators cycled through.
+namespace enerf {
+__global__ void __launch_bounds__(128) tc_mma_bench_kernel(int layout, int N, int n_mma, int accs, unsigned long long* out_ns) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int t = threadIdx.x, warp = t >> 5;
+  for (int e = t; e < 48 * 1024 / 4; e += 128) reinterpret_cast<float*>(sm)[e] = 1.0f;
+  if (t == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::fence_proxy_async();
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+  if (warp == 0) {
+    const uint32_t a = tc::smem_u32(sm), b = a + 32 * 1024;
+    uint64_t ad, bd;
+    if (layout == 0) {
+      ad = tc::smem_desc(a, 2048u, 128u);
+      bd = tc::smem_desc(b, (uint32_t)N * 16u, 128u);
+    } else {
+      const uint32_t sbo = (layout == 2) ? 1024u : (layout == 4) ? 512u : 256u;
+      ad = tc::smem_desc(a, 16u, sbo) | ((uint64_t)layout << 61);
+      bd = tc::smem_desc(b, 16u, sbo) | ((uint64_t)layout << 61);
+    }
+    const uint32_t idesc = tc::idesc_tf32(128, N);
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    for (int i = 0; i < n_mma; ++i) tc::mma_tf32_elect(tmem + (uint32_t)((i % accs) * N), ad, bd, idesc, 1u);
+    tc::mma_commit_elect(&bar);
+    tc::mbar_wait(&bar, 0);
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    if (t == 0) *out_ns = t1 - t0;
+    __syncwarp();
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
+}
+}  // namespace enerf
+
+extern "C" int enerf_tc_mma_bench(int layout, int N, int n_mma, int accs, unsigned long long* out_ns, void* stream) {
+  using namespace enerf;
+  ENERF_REQUIRE(out_ns && N >= 16 && N <= 256 && N % 16 == 0 && accs >= 1 && accs * N <= 512, ENERF_EINVAL, "tc_mma_bench: bad args");
+  cudaError_t e = cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_mma_bench: %s", cudaGetErrorString(e));
+  tc_mma_bench_kernel<<<1, 128, 64 * 1024, (cudaStream_t)stream>>>(layout, N, n_mma, accs, out_ns);
+  ENERF_CHECK_LAUNCH("tc_mma_bench");
+  return ENERF_OK;
+}

@@ -31,9 +31,8 @@ def _dev(t, device):
     return t.to(device=device, dtype=torch.float32).contiguous()
 
 
-# layers enerf_feature_net runs on tcgen05 when tensor_cores != 0 (csrc/feature_net.cu keeps conv0.1 and
-# the 1x1 toplayer on the FP32 pipe, where they measured faster)
-TC_FEATURE_LAYERS = ("conv1.1", "conv2.1", "smooth1", "smooth0")
+# layers enerf_feature_net runs on tcgen05 when tensor_cores != 0 (every stride-1 layer with cin % 8 == 0)
+TC_FEATURE_LAYERS = ("conv0.1", "conv1.1", "conv2.1", "toplayer", "smooth1", "smooth0")
 
 
 def pack_feature_net(sd, device, p="feature_net", tensor_cores=False):
@@ -65,8 +64,7 @@ def pack_cost_reg(sd, p, in_ch, deep, device, with_feat, tensor_cores=False):
         if kind == "cbr":
             w, b = _fold(sd[q + ".conv.weight"], sd, q + ".bn", 0)
             wt = _taps_cin_cout(w)
-            # conv0 (full resolution, Cout 8) stays FP32; conv2/4/6 go to the tensor cores
-            use_tc = tensor_cores and stride == 1 and name != "conv0"
+            use_tc = tensor_cores and stride == 1
             out += [pack_tc_conv(wt).to(device) if use_tc else _dev(wt, device), _dev(b, device)]
         elif kind == "deconv":
             w, b = _fold(sd[q + ".0.weight"], sd, q + ".1", 1)      # (Cin,Cout,kz,ky,kx)
@@ -75,7 +73,7 @@ def pack_cost_reg(sd, p, in_ch, deep, device, with_feat, tensor_cores=False):
         else:
             head[name] = _taps_cin_cout(sd[q + ".0.weight"].double())   # [27][8][cout]
     hw = torch.cat([head["feat_conv"], head["depth_conv"]], dim=2) if with_feat else head["depth_conv"]
-    out.append(_dev(hw, device))      # the head stays on the FP32 pipe in both modes
+    out.append(pack_tc_conv(hw).to(device) if tensor_cores else _dev(hw, device))
     return out
 
 

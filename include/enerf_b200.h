@@ -75,9 +75,10 @@ ENERF_API int enerf_camera_setup(const float* src_exts /*S,4,4*/, const float* s
  * Outputs (channels-last): feat_l0 (S,H/4,W/4,32), feat_l1 (S,H/2,W/2,16), feat_l2 (S,H,W,8).
  * weights [host array, 22 device pointers], each conv as {w [tap][cin][cout] BN-folded, bias[cout]}:
  *   conv0.0, conv0.1, conv1.0, conv1.1, conv2.0, conv2.1, toplayer, lat1, lat0, smooth1, smooth0.
- * tensor_cores != 0: conv1.1, conv2.1, smooth1 and smooth0 run as tcgen05 implicit GEMMs (TF32
- * operands) and take their w in the enerf_tc_conv stage layout (packing.pack_tc_conv); the others
- * keep the [tap][cin][cout] fp32 layout (conv0.1 / toplayer measured faster on the FP32 pipe).
+ * tensor_cores != 0: the stride-1 layers with cin % 8 == 0 (conv0.1, conv1.1, conv2.1, toplayer,
+ * smooth1, smooth0) run as tcgen05 implicit GEMMs (TF32 operands) and take their w in the
+ * enerf_tc_conv stage layout (packing.pack_tc_conv); conv0.0 (cin 3), the 5x5 stride-2 layers and
+ * the laterals keep the [tap][cin][cout] fp32 layout and kernels.
  */
 ENERF_API size_t enerf_feature_net_workspace_bytes(int n_views, int H, int W);
 ENERF_API int enerf_feature_net(const float* const* weights, int n_weights, const float* src_inps, int n_views,
@@ -117,9 +118,9 @@ ENERF_API int enerf_cost_volume(const EnerfCam* cam, int level, const float* fea
  * w [tap][8][9] with output channel 8 = depth_conv and 0..7 = feat_conv when feat_vol != NULL, or
  * w [tap][8][1] (depth_conv only) when feat_vol == NULL.  Forward convs: w [tap][cin][cout];
  * transposed convs: w [tap][cin][cout] with tap = (kz*3+ky)*3+kx of the ConvTranspose3d kernel.
- * tensor_cores != 0: conv2, conv4, conv6 and the transposed layers (conv7, conv9, conv11) run on
- * tcgen05 (TF32) and take w in the enerf_tc_conv stage layout (packing.pack_tc_conv /
- * pack_tc_deconv); conv0, the head and the stride-2 layers keep the fp32 layout and kernels. */
+ * tensor_cores != 0: the stride-1 layers (conv0, conv2, conv4, conv6, head) and the transposed
+ * layers (conv7, conv9, conv11) run on tcgen05 (TF32) and take w in the enerf_tc_conv stage layout
+ * (packing.pack_tc_conv / pack_tc_deconv); the stride-2 layers keep the fp32 layout and kernels. */
 ENERF_API size_t enerf_cost_reg_workspace_bytes(int deep, int D, int h, int w);
 ENERF_API int enerf_cost_reg(const float* const* weights, int n_weights, int deep, int in_ch, const float* variance,
                    int D, int h, int w, float* feat_vol, float* depth_prob, void* workspace,
@@ -178,6 +179,10 @@ ENERF_API int enerf_tc_conv(int kind, int KD, int KH, int cin, int cout, int mod
 /* Diagnostic: when buf != NULL, CTA (0,0,0) of every later enerf_tc_conv-family launch writes 64
  * %globaltimer phase stamps (ns) into buf (device memory, 64 x u64).  NULL switches it off. */
 ENERF_API int enerf_tc_conv_debug(unsigned long long* buf);
+
+/* Diagnostic microbenchmark: ns for n_mma back-to-back tcgen05.mma (M=128, K=8 tf32) with the given
+ * operand layout (0 none, 2/4/6 = 128/64/32-byte swizzle), N, and `accs` accumulators cycled. */
+ENERF_API int enerf_tc_mma_bench(int layout, int N, int n_mma, int accs, unsigned long long* out_ns, void* stream);
 
 /* Diagnostic: D[128 x N] = A[128 x K] * B[N x K]^T on the tensor cores (tcgen05.mma kind::tf32,
  * accumulator in TMEM) through the same descriptor helpers the fused kernels use (csrc/tc.cuh).
