@@ -43,6 +43,7 @@ _SIGS = {
     "enerf_tc_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "enerf_tc_conv_debug": (_i, [_vp]),
     "enerf_tc_mma_bench": (_i, [_i, _i, _i, _i, _vp, _vp]),
+    "enerf_render_rays_debug": (_i, [_vp]),
     "enerf_tc_selftest": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
@@ -204,3 +205,7 @@ def tc_mma_bench(layout, N, n_mma, accs=1):
     _check(lib().enerf_tc_mma_bench(layout, N, n_mma, accs, out.data_ptr(), stream()), "enerf_tc_mma_bench")
     torch.cuda.synchronize()
     return int(out.item())
+
+
+def render_rays_debug(buf):
+    _check(lib().enerf_render_rays_debug(buf.data_ptr() if buf is not None else None), "enerf_render_rays_debug", launches=0)

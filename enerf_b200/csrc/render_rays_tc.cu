@@ -57,7 +57,19 @@ struct RayTcParams {
   RayParams r;
   const float* wblob;
   int n_tiles;
+  unsigned long long* dbg;   // optional phase stamps (ns) of CTA 0's first two tiles
 };
+
+__device__ unsigned long long* g_ray_dbg = nullptr;
+__device__ __forceinline__ unsigned long long ray_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define RAY_STAMP(i_)                                                          \
+  do {                                                                         \
+    if (dbg && tile_i < 2) dbg[tile_i * 16 + (i_)] = ray_gtime();              \
+  } while (0)
 
 template <int S>
 struct TcSmem {
@@ -133,7 +145,11 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
     tc::tc_fence_after_sync();
   };
 
+  unsigned long long* dbg = (g_ray_dbg && t == 0 && blockIdx.x == 0) ? g_ray_dbg : nullptr;
+  int tile_i = -1;
   for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    ++tile_i;
+    RAY_STAMP(0);
     const long long pt = (long long)tile * 128 + t;
     const bool valid = pt < (long long)p.n_rays * Ns;
     const int ray = valid ? (int)(pt / Ns) : p.n_rays - 1;
@@ -292,8 +308,10 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
       }
     }
 
+    RAY_STAMP(1);   // gathers + A rows written
     // ================= G1: global_fc =================
     sync_then_issue();
+    RAY_STAMP(2);
     if (warp == 0) {   // converged warp, uniform operands, one elected lane issues (tc::mma_tf32_elect)
      {
       const uint32_t id = tc::idesc_tf32(128, 32);
@@ -309,6 +327,7 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
      __syncwarp();
     }
     wait_mma();
+    RAY_STAMP(3);
     // ---- E1: ReLU, agg_w_fc logits, softmax over views, weighted pooling ----
     {
       float lg[S];
@@ -345,6 +364,7 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
 #pragma unroll
       for (int q = 0; q < 8; ++q) store_chunk(a_s, q, t, im[4 * q], im[4 * q + 1], im[4 * q + 2], im[4 * q + 3]);
     }
+    RAY_STAMP(4);
     // ================= G2: fc 32 -> 16 =================
     sync_then_issue();
     if (warp == 0) {   // converged warp, uniform operands, one elected lane issues (tc::mma_tf32_elect)
@@ -357,6 +377,7 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
      __syncwarp();
     }
     wait_mma();
+    RAY_STAMP(5);
     {
       float o[16];
       tc::tmem_ld16(tmem_row, o);
@@ -369,6 +390,7 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
 #pragma unroll
       for (int q = 0; q < 4; ++q) store_chunk(a_s, 18 + q, t, o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
     }
+    RAY_STAMP(6);
     // ================= G3: lr0 24 -> 64 =================
     sync_then_issue();
     if (warp == 0) {   // converged warp, uniform operands, one elected lane issues (tc::mma_tf32_elect)
@@ -381,6 +403,7 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
      __syncwarp();
     }
     wait_mma();
+    RAY_STAMP(7);
     float sigma;
     {
       float sg = sw[TcW::v_bs];
@@ -399,8 +422,10 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
       }
       sigma = (sg > 20.f) ? sg : log1pf(expf(sg));
     }
+    RAY_STAMP(8);
     // ================= G5: color.0 =================
     sync_then_issue();
+    RAY_STAMP(9);
     if (warp == 0) {   // converged warp, uniform operands, one elected lane issues (tc::mma_tf32_elect)
      {
       const uint32_t id = tc::idesc_tf32(128, 64);
@@ -416,6 +441,7 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
      __syncwarp();
     }
     wait_mma();
+    RAY_STAMP(10);
     float cr = 0.f, cg = 0.f, cb = 0.f;
     {
       float cl[S];
@@ -447,6 +473,7 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
       }
     }
 
+    RAY_STAMP(11);
     // ================= raw2outputs: prefix product / sums over the Ns lanes of a ray =================
     {
       const int gbase = lane - k;                 // first lane of this ray's group (Ns | 32)
@@ -492,9 +519,11 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
     }
     // the next tile overwrites the A rows and the accumulators: all TMEM reads above are complete
     // (tcgen05.wait::ld) and G5 has been waited for; one CTA barrier orders the reuse
+    RAY_STAMP(12);
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
+    RAY_STAMP(13);
   }
   if (warp == 0) tc::tmem_dealloc(tmem, TMEM_COLS);
 }
@@ -553,4 +582,13 @@ extern "C" int enerf_render_rays_tc(const EnerfCam* cam, int level, const float*
     case 3: return launch_rays_tc<3>(P, stream);
     default: return launch_rays_tc<4>(P, stream);
   }
+}
+
+extern "C" int enerf_render_rays_debug(unsigned long long* buf) {
+  cudaError_t e = cudaMemcpyToSymbol(enerf::g_ray_dbg, &buf, sizeof(buf));
+  if (e != cudaSuccess) {
+    enerf::set_error("render_rays_debug: %s", cudaGetErrorString(e));
+    return ENERF_ECUDA;
+  }
+  return ENERF_OK;
 }

@@ -180,6 +180,10 @@ ENERF_API int enerf_tc_conv(int kind, int KD, int KH, int cin, int cout, int mod
  * %globaltimer phase stamps (ns) into buf (device memory, 64 x u64).  NULL switches it off. */
 ENERF_API int enerf_tc_conv_debug(unsigned long long* buf);
 
+/* Diagnostic: like enerf_tc_conv_debug for enerf_render_rays_tc (32 x u64: 16 stamps for each of
+ * the first two tiles of CTA 0). */
+ENERF_API int enerf_render_rays_debug(unsigned long long* buf);
+
 /* Diagnostic microbenchmark: ns for n_mma back-to-back tcgen05.mma (M=128, K=8 tf32) with the given
  * operand layout (0 none, 2/4/6 = 128/64/32-byte swizzle), N, and `accs` accumulators cycled. */
 ENERF_API int enerf_tc_mma_bench(int layout, int N, int n_mma, int accs, unsigned long long* out_ns, void* stream);
