@@ -162,7 +162,30 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """Everything the process (NCCL banners included) writes to fd 1 goes to stderr; the single JSON
+    line is written to the original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -171,6 +194,7 @@ def main():
     ap.add_argument("--mode", default="frames", choices=["frames", "rays"], help="N>1: frame-parallel sequence (default) or intra-frame ray-band sharding")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="replay the forward as a CUDA graph (0 = eager launches)")
+    ap.add_argument("--host-rays", type=int, default=0, help="1: ship rays_1 from the host like the reference's data layer (default: generate on device)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -186,8 +210,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    local_rank = local
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
 
     from enerf_b200 import capi, config as cfg_mod, synthetic
     import torch.distributed as dist
@@ -196,19 +221,38 @@ def main():
     cfg, net, batch = build_problem(cfg_mod, synthetic, seed=2 + (rank if (world > 1 and args.mode == "frames") else 0) * 10)
     sd_cpu = {k: v.clone() for k, v in net.state_dict().items()}
     net = net.to(dev)
+    # the data layer's rays_1 (10.5 MB/frame) is not shipped: rays are generated on device from
+    # tar_ext / tar_ixt; `--host-rays 1` restores the reference's batch contract
+    batch_full = dict(batch)                       # the CPU oracle still takes the reference's full batch
+    if not args.host_rays:
+        batch.pop("rays_1", None)
     gbatch = {k: v.to(dev) for k, v in batch.items()}
     n_rays, ns = H * W, 2
 
+    from enerf_b200.pipeline import GraphedNetwork, StreamedRenderer
     if world > 1 and args.mode == "rays":
-        renderer = edist.RayShardedRenderer(edist.network_render_fn(net, 1), 1, ns, W, H, rank, world, device=dev)
+        renderer = edist.RayShardedRenderer(None, 1, ns, W, H, rank, world, device=dev)
+        local = renderer.local_batch(gbatch)
+        net.ray_rows = renderer.rows_range()
     else:
-        renderer = edist.FrameParallelRenderer(edist.network_render_fn(net, 1), n_rays, ns, rank, world, device=dev)
+        renderer = edist.FrameParallelRenderer(None, n_rays, ns, rank, world, device=dev)
+        local = gbatch
+    net.output_views = {1: renderer.local_views()}     # the ray kernel writes straight into the gather buffer
 
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # 256 MiB > 126 MB L2
+    l0 = capi.LAUNCHES
+    with torch.no_grad():
+        net(local)
+    launches_per_forward = capi.LAUNCHES - l0
+    graphed = GraphedNetwork(net, local) if args.graph else None
 
     def step():
         with torch.no_grad():
-            return renderer(gbatch)
+            if graphed is not None:
+                graphed.replay()
+            else:
+                net(local)
+            return renderer.gather()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -216,14 +260,13 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- warm-up (also builds packed weights, scratch buffers, sets smem attributes) ----
+    # ---- warm-up ----
     for _ in range(args.warmup):
         out = step()
     sync_all()
 
-    l0 = capi.LAUNCHES
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local) as clk:
+    with ClockSampler(local_rank) as clk:
         sync_all()
         for a, b in ev:
             flush_buf.zero_()            # L2 flush between timed iterations (not timed)
@@ -232,7 +275,7 @@ def main():
             b.record()
         sync_all()
     times = [a.elapsed_time(b) for a, b in ev]
-    launches = (capi.LAUNCHES - l0) / args.steps
+    launches = launches_per_forward
     t_local = sum(times)
     t = torch.tensor([t_local], device=dev, dtype=torch.float64)
     if world > 1:
@@ -242,37 +285,47 @@ def main():
     ms_per_step = total_ms / args.steps
     value = frames_per_step * 1000.0 / ms_per_step
     times.sort()
+    net.output_views, net.ray_rows = None, None
 
-    # ---- end to end through the public API with host buffers (H2D + forward + D2H every step) ----
+    # ---- end to end through the public API with HOST buffers: every frame pays its own H2D (pinned)
+    #      and D2H (pinned); StreamedRenderer overlaps copy-in / forward / copy-out of adjacent frames ----
     host_in = {k: v.clone().pin_memory() for k, v in batch.items()}
     h2d = sum(v.numel() * v.element_size() for v in host_in.values())
-    host_out = None
-    e2e_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    streamed = StreamedRenderer(net, host_in, dev, depth=2, use_graph=bool(args.graph))
+    d2h_box = {}
 
-    def e2e_step():
-        nonlocal host_out
+    def on_frame(i, host_out):
+        d2h_box["bytes"] = sum(v.numel() * v.element_size() for v in host_out.values())
+
+    streamed.render([host_in] * 4, on_frame)
+    sync_all()
+    e2e_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    e2e_ev[0].record()
+    streamed.render([host_in] * args.steps, on_frame)
+    e2e_ev[1].record()
+    sync_all()
+    e2e_ms = e2e_ev[0].elapsed_time(e2e_ev[1]) / args.steps
+    # the plain synchronous loop of run.py:57-76 (copy, forward, copy, sync) for comparison
+    sync_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    host_out = None
+    sync_ev[0].record()
+    for _ in range(args.steps):
         with torch.no_grad():
-            dbatch = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
-            o = net(dbatch)
+            o = net({k: v.to(dev, non_blocking=True) for k, v in host_in.items()})
             if host_out is None:
                 host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in o.items()}
             for k, v in o.items():
                 host_out[k].copy_(v, non_blocking=True)
-
-    for _ in range(3):
-        e2e_step()
+        torch.cuda.synchronize()
+    sync_ev[1].record()
     sync_all()
-    e2e_ev[0].record()
-    for _ in range(args.steps):
-        e2e_step()
-    e2e_ev[1].record()
-    sync_all()
-    e2e_ms = e2e_ev[0].elapsed_time(e2e_ev[1]) / args.steps
-    te = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    e2e_sync_ms = sync_ev[0].elapsed_time(sync_ev[1]) / args.steps
+    te = torch.tensor([e2e_ms, e2e_sync_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_fps = (world if world > 1 else 1) * 1000.0 / te.item()     # every rank pushes its own frame end to end
-    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+    e2e_fps = (world if world > 1 else 1) * 1000.0 / te[0].item()     # every rank pushes its own frame end to end
+    e2e_sync_fps = (world if world > 1 else 1) * 1000.0 / te[1].item()
+    d2h = d2h_box.get("bytes", 0)
 
     if rank != 0:
         if world > 1:
@@ -311,7 +364,7 @@ def main():
     cpu_baseline, parity = None, None
     if not args.no_cpu_baseline and world == 1:
         frames = 3
-        fps_cpu, ref_out, n_thr = cpu_reference_run(cfg, sd_cpu, batch, frames, warmup=1)
+        fps_cpu, ref_out, n_thr = cpu_reference_run(cfg, sd_cpu, batch_full, frames, warmup=1)
         cpu_baseline = {"value": fps_cpu, "unit": "frames/s", "cores": n_thr, "kind": "port",
                         "sample": f"{frames} full 512x640 frames after 1 warm-up; oracle/enerf_oracle.py (torch {torch.__version__} CPU ops), {n_thr} threads"}
         with torch.no_grad():
@@ -329,11 +382,14 @@ def main():
         "vs_baseline": value / PUBLISHED_FPS, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{H}x{W}, {S} src views, {PLANES[0]}+{PLANES[1]} planes, 2-level cascade, render_if [F,T] (BASELINE.json configs[1])",
                    "frames_per_step": frames_per_step, "parallelism": (f"{args.mode}x{world}" if world > 1 else "single"),
+                   "cuda_graph": bool(args.graph), "rays": "host (batch rays_1)" if args.host_rays else "generated on device from tar_ext/tar_ixt",
                    "l2": "256 MiB buffer written between timed iterations (L2 flush)", "timing": "CUDA events per step, max over ranks",
                    "p50_ms": times[len(times) // 2], "p95_ms": times[min(len(times) - 1, int(0.95 * len(times)))],
                    "vs_baseline_note": "published 21.78 FPS is RTX 3090 + trained weights (README.md:121)"},
         "clocks": clk.summary(),
-        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": te.item()},
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": te[0].item(),
+                "api": "enerf_b200.pipeline.StreamedRenderer.render (3 streams, depth 2, CUDA-graph forward)",
+                "sync_loop_value": e2e_sync_fps, "sync_loop_note": "run.py:57-76 style: copy in, Network.forward, copy out, synchronize"},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
@@ -341,7 +397,7 @@ def main():
     }
     if parity:
         line["parity"] = parity
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -28,6 +28,7 @@ _SIGS = {
     "enerf_abi_version": (_i, []),
     "enerf_last_error": (ctypes.c_char_p, []),
     "enerf_camera_setup": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, ctypes.POINTER(ctypes.c_float), _vp, _vp]),
+    "enerf_generate_rays": (_i, [_vp, _vp, ctypes.c_float, _i, _i, _i, _vp, _vp]),
     "enerf_feature_net_workspace_bytes": (_sz, [_i, _i, _i]),
     "enerf_feature_net": (_i, [ctypes.POINTER(_vp), _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "enerf_pack_img_feat": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
@@ -209,3 +210,7 @@ def tc_mma_bench(layout, N, n_mma, accs=1):
 
 def render_rays_debug(buf):
     _check(lib().enerf_render_rays_debug(buf.data_ptr() if buf is not None else None), "enerf_render_rays_debug", launches=0)
+
+
+def generate_rays(tar_ext, tar_ixt, scale, W, row0, n_rows, rays):
+    _check(lib().enerf_generate_rays(ptr(tar_ext), ptr(tar_ixt), float(scale), W, row0, n_rows, ptr(rays), stream()), "enerf_generate_rays")

@@ -58,75 +58,84 @@ __global__ void depth_hypotheses_kernel(const EnerfCam* __restrict__ cam, const 
   nf_out[(size_t)h * w + pix] = v1;
 }
 
+// thread = (voxel, half of the channels): the homography, the perspective divide and the bilinear
+// weights are computed once per view and applied to C/2 channels (C/8 float4 accumulator pairs).
+// Two lanes share a voxel and read adjacent halves of the same source pixel record.
 template <int C>
 __global__ void __launch_bounds__(256) cost_volume_kernel(const EnerfCam* __restrict__ cam, int level,
                                                           const float* __restrict__ feat, int S, int hs, int ws,
                                                           const float* __restrict__ ends, int D, int h, int w,
                                                           int depth_inv, float* __restrict__ var_out) {
-  constexpr int CG = C / 4;
+  constexpr int SPLIT = (C >= 16) ? 2 : 1;         // lanes per voxel
+  constexpr int CH = C / SPLIT;                    // channels per thread
+  constexpr int NV = CH / 4;                       // float4 per tap per thread
   __shared__ float Hm[ENERF_MAX_VIEWS * 12];
   for (int e = threadIdx.x; e < S * 12; e += blockDim.x) Hm[e] = cam->homo[level][e / 12][e % 12];
   __syncthreads();
-  const long long total = (long long)D * h * w * CG;
+  const long long total = (long long)D * h * w * SPLIT;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
-  const int g = (int)(t % CG);
-  const long long vox = t / CG;
+  const int g = (int)(t % SPLIT);
+  const long long vox = t / SPLIT;
   const int x = (int)(vox % w), y = (int)((vox / w) % h), d = (int)(vox / ((long long)w * h));
   const int pix = y * w + x;
   const float depth = plane_depth(__ldg(ends + pix), __ldg(ends + (size_t)h * w + pix), d, D, depth_inv);
+  const float inv_depth = 1.0f / depth;
   const float fx = (float)x, fy = (float)y;
-  const float wsm1 = (float)(ws - 1), hsm1 = (float)(hs - 1);
-  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 s1[NV], s2[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) s1[q] = s2[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s = 0; s < S; ++s) {
     const float* M = Hm + s * 12;
-    const float q0 = (M[0] * fx + M[1] * fy + M[2]) + M[3] / depth;
-    const float q1 = (M[4] * fx + M[5] * fy + M[6]) + M[7] / depth;
-    const float q2 = (M[8] * fx + M[9] * fy + M[10]) + M[11] / depth;
-    const float qz = fmaxf(q2, 1e-6f);
-    const float xs = q0 / qz, ys = q1 / qz;
-    // normalise to [-1,1] (utils.py:83-84) and un-normalise as grid_sample(align_corners=True) does
-    const float gx = xs / (wsm1 / 2.0f) - 1.0f, gy = ys / (hsm1 / 2.0f) - 1.0f;
-    const float ix = ((gx + 1.0f) / 2.0f) * wsm1, iy = ((gy + 1.0f) / 2.0f) * hsm1;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    // p = R (x,y,1)^T + T / depth  (utils.py:72); T/depth as T * (1/depth): <= 1 ulp from the reference
+    const float q0 = (M[0] * fx + M[1] * fy + M[2]) + M[3] * inv_depth;
+    const float q1 = (M[4] * fx + M[5] * fy + M[6]) + M[7] * inv_depth;
+    const float q2 = (M[8] * fx + M[9] * fy + M[10]) + M[11] * inv_depth;
+    const float rz = 1.0f / fmaxf(q2, 1e-6f);
+    // the reference normalises to [-1,1] (utils.py:83-84) and grid_sample(align_corners=True) maps
+    // straight back: the sample position is the source pixel coordinate itself
+    const float ix = q0 * rz, iy = q1 * rz;
+    float4 v[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ix > -1.0f && ix < (float)ws && iy > -1.0f && iy < (float)hs) {  // false for NaN
       const float fx0 = floorf(ix), fy0 = floorf(iy);
       const int x0 = (int)fx0, y0 = (int)fy0;
-      // ATen grid_sampler weights: nw = (x_se - x)(y_se - y), ne = (x - x_sw)(y_sw - y), ...
       const float txr = (fx0 + 1.f) - ix, txl = ix - fx0, tyb = (fy0 + 1.f) - iy, tyt = iy - fy0;
-      const float w_nw = txr * tyb, w_ne = txl * tyb, w_sw = txr * tyt, w_se = txl * tyt;
-      const float* base = feat + ((size_t)s * hs * ws) * C + g * 4;
-      const bool xl = x0 >= 0, xr = x0 + 1 < ws, yt = y0 >= 0, yb = y0 + 1 < hs;
-      if (yt && xl) {
-        const float4 p = ldg4(base + ((size_t)y0 * ws + x0) * C);
-        v.x = fmaf(p.x, w_nw, v.x), v.y = fmaf(p.y, w_nw, v.y), v.z = fmaf(p.z, w_nw, v.z), v.w = fmaf(p.w, w_nw, v.w);
-      }
-      if (yt && xr) {
-        const float4 p = ldg4(base + ((size_t)y0 * ws + x0 + 1) * C);
-        v.x = fmaf(p.x, w_ne, v.x), v.y = fmaf(p.y, w_ne, v.y), v.z = fmaf(p.z, w_ne, v.z), v.w = fmaf(p.w, w_ne, v.w);
-      }
-      if (yb && xl) {
-        const float4 p = ldg4(base + ((size_t)(y0 + 1) * ws + x0) * C);
-        v.x = fmaf(p.x, w_sw, v.x), v.y = fmaf(p.y, w_sw, v.y), v.z = fmaf(p.z, w_sw, v.z), v.w = fmaf(p.w, w_sw, v.w);
-      }
-      if (yb && xr) {
-        const float4 p = ldg4(base + ((size_t)(y0 + 1) * ws + x0 + 1) * C);
-        v.x = fmaf(p.x, w_se, v.x), v.y = fmaf(p.y, w_se, v.y), v.z = fmaf(p.z, w_se, v.z), v.w = fmaf(p.w, w_se, v.w);
+      const float wgt[4] = {txr * tyb, txl * tyb, txr * tyt, txl * tyt};
+      const bool okx[2] = {x0 >= 0, x0 + 1 < ws}, oky[2] = {y0 >= 0, y0 + 1 < hs};
+      const float* base = feat + ((size_t)s * hs * ws) * C + g * CH;
+#pragma unroll
+      for (int tp = 0; tp < 4; ++tp) {
+        if (oky[tp >> 1] && okx[tp & 1]) {
+          const float* p = base + ((size_t)(y0 + (tp >> 1)) * ws + (x0 + (tp & 1))) * C;
+          const float wv = wgt[tp];
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            const float4 a = ldg4(p + 4 * q);
+            v[q].x = fmaf(a.x, wv, v[q].x), v[q].y = fmaf(a.y, wv, v[q].y), v[q].z = fmaf(a.z, wv, v[q].z), v[q].w = fmaf(a.w, wv, v[q].w);
+          }
+        }
       }
     }
-    s1.x += v.x, s1.y += v.y, s1.z += v.z, s1.w += v.w;
-    s2.x += v.x * v.x, s2.y += v.y * v.y, s2.z += v.z * v.z, s2.w += v.w * v.w;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      s1[q].x += v[q].x, s1[q].y += v[q].y, s1[q].z += v[q].z, s1[q].w += v[q].w;
+      s2[q].x += v[q].x * v[q].x, s2[q].y += v[q].y * v[q].y, s2[q].z += v[q].z * v[q].z, s2[q].w += v[q].w * v[q].w;
+    }
   }
   const float fS = (float)S;
-  float4 o;
-  {
+  float4* o = reinterpret_cast<float4*>(var_out + (size_t)vox * C + g * CH);
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    float4 r;
     float m;
-    m = s1.x / fS, o.x = s2.x / fS - m * m;
-    m = s1.y / fS, o.y = s2.y / fS - m * m;
-    m = s1.z / fS, o.z = s2.z / fS - m * m;
-    m = s1.w / fS, o.w = s2.w / fS - m * m;
+    m = s1[q].x / fS, r.x = s2[q].x / fS - m * m;
+    m = s1[q].y / fS, r.y = s2[q].y / fS - m * m;
+    m = s1[q].z / fS, r.z = s2[q].z / fS - m * m;
+    m = s1[q].w / fS, r.w = s2[q].w / fS - m * m;
+    o[q] = r;
   }
-  *reinterpret_cast<float4*>(var_out + (size_t)vox * C + g * 4) = o;
 }
 
 __global__ void depth_regress_kernel(const float* __restrict__ prob, const float* __restrict__ ends, int D, int h, int w,
@@ -182,7 +191,7 @@ extern "C" int enerf_cost_volume(const EnerfCam* cam, int level, const float* fe
   ENERF_REQUIRE(cam && feat && ends && variance, ENERF_EINVAL, "cost_volume: null pointer");
   ENERF_REQUIRE(level >= 0 && level < ENERF_MAX_LEVELS, ENERF_EINVAL, "cost_volume: level %d", level);
   ENERF_REQUIRE(S >= 1 && S <= ENERF_MAX_VIEWS, ENERF_EINVAL, "cost_volume: n_views %d not in [1,%d]", S, ENERF_MAX_VIEWS);
-  const long long total = (long long)D * h * w * (C / 4);
+  const long long total = (long long)D * h * w * (C >= 16 ? 2 : 1);
   const unsigned blocks = (unsigned)((total + 255) / 256);
   switch (C) {
     case 8: cost_volume_kernel<8><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance); break;

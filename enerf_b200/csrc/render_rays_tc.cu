@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
       store_chunk(a_s, cf + 0, t, g[s][0], g[s][1], g[s][2], g[s][3]);
       store_chunk(a_s, cf + 1, t, g[s][4], g[s][5], g[s][6], g[s][7]);
       store_chunk(a_s, cf + 2, t, g[s][8], g[s][9], g[s][10], d0);
-      store_chunk(a_s, cf + 3, t, d1, d2, d3, 0.f);
+      store_chunk(a_s, cf + 3, t, d1, d2, d3, 1.f);   // column 15 = 1: color.0's bias rides in B (row 15)
       // g_s = f_s + relu(view_fc(dir_s))    (nerf.py:76-78)
       if (p.viewdir_agg) {
 #pragma unroll
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
       }
       store_chunk(a_s, 4 * s + 0, t, g[s][0], g[s][1], g[s][2], g[s][3]);
       store_chunk(a_s, 4 * s + 1, t, g[s][4], g[s][5], g[s][6], g[s][7]);
-      store_chunk(a_s, 4 * s + 2, t, g[s][8], g[s][9], g[s][10], 0.f);
+      store_chunk(a_s, 4 * s + 2, t, g[s][8], g[s][9], g[s][10], 1.f);   // column 11 = 1: global_fc's bias rides in B
       store_chunk(a_s, 4 * s + 3, t, 0.f, 0.f, 0.f, 0.f);
     }
     {
@@ -328,10 +328,13 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
     }
     wait_mma();
     RAY_STAMP(3);
-    // ---- E1: ReLU, agg_w_fc logits, softmax over views, weighted pooling ----
+    // ---- E1: ReLU, agg_w_fc logits, softmax over views, weighted pooling (one pass over TMEM:
+    //      running max + rescale, mathematically the max-subtracted softmax of nerf.py:87) ----
     {
-      float lg[S];
-      float mx = -INFINITY;
+      float im[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) im[j] = 0.f;
+      float mx = -INFINITY, den = 0.f;
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         float h[32];
@@ -339,30 +342,21 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
         tc::tmem_ld_wait();
         float a = sw[TcW::v_ba];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) a = fmaf(fmaxf(h[j] + sw[TcW::v_bg + j], 0.f), sw[TcW::v_wa + j], a);
-        lg[s] = fmaxf(a, 0.f);
-        mx = fmaxf(mx, lg[s]);
+        for (int j = 0; j < 32; ++j) {
+          h[j] = fmaxf(h[j], 0.f);                       // bias already in the accumulator
+          a = fmaf(h[j], sw[TcW::v_wa + j], a);
+        }
+        const float lg = fmaxf(a, 0.f);
+        const float mn = fmaxf(mx, lg);
+        const float sc = expf(mx - mn), e = expf(lg - mn);   // first view: sc = exp(-inf) = 0
+        den = fmaf(den, sc, e);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) im[j] = fmaf(e, h[j], im[j] * sc);
+        mx = mn;
       }
-      float den = 0.f;
+      const float inv = 1.0f / den;
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-        lg[s] = expf(lg[s] - mx);
-        den += lg[s];
-      }
-      float im[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) im[j] = 0.f;
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        float h[32];
-        tc::tmem_ld32(tmem_row + s * 32, h);
-        tc::tmem_ld_wait();
-        const float ws_ = lg[s] / den;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) im[j] = fmaf(fmaxf(h[j] + sw[TcW::v_bg + j], 0.f), ws_, im[j]);
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) store_chunk(a_s, q, t, im[4 * q], im[4 * q + 1], im[4 * q + 2], im[4 * q + 3]);
+      for (int q = 0; q < 8; ++q) store_chunk(a_s, q, t, im[4 * q] * inv, im[4 * q + 1] * inv, im[4 * q + 2] * inv, im[4 * q + 3] * inv);
     }
     RAY_STAMP(4);
     // ================= G2: fc 32 -> 16 =================
@@ -455,7 +449,7 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
           tc::tmem_ld32(tmem_row + s * 64 + half * 32, h);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a = fmaf(fmaxf(h[j] + sw[TcW::v_bc + half * 32 + j], 0.f), sw[TcW::v_w2 + half * 32 + j], a);
+          for (int j = 0; j < 32; ++j) a = fmaf(fmaxf(h[j], 0.f), sw[TcW::v_w2 + half * 32 + j], a);   // bias in the accumulator
         }
         cl[s] = fmaxf(a, 0.f);
         mx = fmaxf(mx, cl[s]);
@@ -475,7 +469,34 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
 
     RAY_STAMP(11);
     // ================= raw2outputs: prefix product / sums over the Ns lanes of a ray =================
-    {
+    if (Ns == 2) {
+      // two samples of a ray in lanes (2i, 2i+1): one xor-shuffle exchange per quantity
+      const float alpha = 1.f - expf(-sigma);
+      const float tr = 1.f - alpha + 1e-10f;
+      const float tr_o = __shfl_xor_sync(0xffffffffu, tr, 1);
+      const float wk = alpha * (k == 0 ? 1.f : tr_o);
+      const float wk_o = __shfl_xor_sync(0xffffffffu, wk, 1);
+      const float cr_o = __shfl_xor_sync(0xffffffffu, cr, 1), cg_o = __shfl_xor_sync(0xffffffffu, cg, 1),
+                  cb_o = __shfl_xor_sync(0xffffffffu, cb, 1), z_o = __shfl_xor_sync(0xffffffffu, z, 1);
+      const float mx = fmaxf(wk, wk_o);
+      const float e = expf(wk - mx), e_o = expf(wk_o - mx);
+      if (valid) {
+        if (k == 0) {
+          const float den = e + e_o;                       // same order as the sequential sum over samples
+          const float wn0 = e / den, wn1 = e_o / den;
+          float ar = fmaf(wk_o, cr_o, wk * cr), ag = fmaf(wk_o, cg_o, wk * cg), ab = fmaf(wk_o, cb_o, wk * cb);
+          if (p.white_bkgd) {
+            const float bg = 1.f - (wn0 + wn1);
+            ar += bg, ag += bg, ab += bg;
+          }
+          *reinterpret_cast<float2*>(p.out_weights + (size_t)ray * 2) = make_float2(wn0, wn1);
+          p.out_rgb[(size_t)ray * 3 + 0] = ar;
+          p.out_rgb[(size_t)ray * 3 + 1] = ag;
+          p.out_rgb[(size_t)ray * 3 + 2] = ab;
+          p.out_depth[ray] = wn0 * z + wn1 * z_o;
+        }
+      }
+    } else {
       const int gbase = lane - k;                 // first lane of this ray's group (Ns | 32)
       const float alpha = 1.f - expf(-sigma);
       const float tr = 1.f - alpha + 1e-10f;

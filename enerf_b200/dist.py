@@ -68,15 +68,27 @@ class RayShardedRenderer:
         return {"rgb": mine[o_rgb:o_depth].view(self.n_local, 3), "depth": mine[o_depth:o_w],
                 "weights": mine[o_w:seg].view(self.n_local, self.ns)}
 
-    def __call__(self, batch):
-        r0, r1 = row_band(self.H, self.rank, self.world)
+    def local_batch(self, batch):
+        """This rank's share of the frame: the row band of ``rays_<level>`` (or, when the batch carries
+        no rays, the band is generated on device -- see ``rows``)."""
+        r0, r1 = self.rows_range()
         key = f"rays_{self.level}"
         local = dict(batch)
-        local[key] = batch[key][:, r0 * self.W:r1 * self.W].contiguous()
-        self.render_fn(local, self.local_views())
+        if key in batch:
+            local[key] = batch[key][:, r0 * self.W:r1 * self.W].contiguous()
+        return local
+
+    def rows_range(self):
+        return row_band(self.H, self.rank, self.world)
+
+    def gather(self):
         if self.world > 1:
             dist.all_gather_into_tensor(self.buf, self.buf[self.rank * self.seg:(self.rank + 1) * self.seg], group=self.group)
         return self.assemble()
+
+    def __call__(self, batch):
+        self.render_fn(self.local_batch(batch), self.local_views())
+        return self.gather()
 
     def assemble(self):
         o_rgb, o_depth, o_w, seg = segment_layout(self.n_local, self.ns)
@@ -98,8 +110,7 @@ class FrameParallelRenderer:
         mine = self.buf[self.rank * seg:(self.rank + 1) * seg]
         return {"rgb": mine[o_rgb:o_depth].view(self.n, 3), "depth": mine[o_depth:o_w], "weights": mine[o_w:seg].view(self.n, self.ns)}
 
-    def __call__(self, batch):
-        self.render_fn(batch, self.local_views())
+    def gather(self):
         if self.world > 1:
             dist.all_gather_into_tensor(self.buf, self.buf[self.rank * self.seg:(self.rank + 1) * self.seg], group=self.group)
         o_rgb, o_depth, o_w, seg = segment_layout(self.n, self.ns)
@@ -107,14 +118,19 @@ class FrameParallelRenderer:
         return {"rgb": per[:, o_rgb:o_depth].reshape(self.world, self.n, 3), "depth": per[:, o_depth:o_w],
                 "weights": per[:, o_w:seg].reshape(self.world, self.n, self.ns)}
 
+    def __call__(self, batch):
+        self.render_fn(batch, self.local_views())
+        return self.gather()
 
-def network_render_fn(net, level):
-    """Adapter: run the drop-in Network with its ray-stage outputs redirected into ``out``."""
+
+def network_render_fn(net, level, rows=None):
+    """Adapter: run the drop-in Network with its ray-stage outputs redirected into ``out``
+    (``rows`` = (r0, r1): the band to generate rays for when the batch carries none)."""
 
     def fn(batch, out):
-        net.output_views = {level: out}
+        net.output_views, net.ray_rows = {level: out}, rows
         try:
             return net(batch)
         finally:
-            net.output_views = None
+            net.output_views, net.ray_rows = None, None
     return fn

@@ -42,6 +42,9 @@ class Network(nn.Module):
         # "tf32": MLP contractions on tcgen05 tensor cores (TF32 operands, fp32 accumulate) where the
         # tensor-core kernel is built for the configuration; "fp32": FP32-pipe kernels everywhere.
         self.precision = os.environ.get("ENERF_B200_PRECISION", "tf32")
+        # rows [r0, r1) of the render frame to generate rays for when the batch carries no rays_{i}
+        # (None = the full frame); set by the ray-sharding renderer (enerf_b200/dist.py)
+        self.ray_rows = None
         self.output_views = None   # {level: {"rgb","depth","weights"}} pre-allocated ray outputs (enerf_b200/dist.py)
         self.profile = False       # when True, CUDA events bracket every stage (see stage_times_ms)
         self._events = []
@@ -188,7 +191,13 @@ class Network(nn.Module):
             img = self._scratch(f"img{i}", S * Hr * Wr * (lv.feat_ch + 4), dev).view(S, Hr, Wr, lv.feat_ch + 4)
             capi.pack_img_feat(imf, src, img)
             self._mark(f"pack_img_feat_{i}")
-            rays = batch[f"rays_{i}"][b].float().contiguous()
+            if f"rays_{i}" in batch:
+                rays = batch[f"rays_{i}"][b].float().contiguous()
+            else:   # no rays from the data layer: full-frame rays generated on device
+                r0, r1 = self.ray_rows if self.ray_rows is not None else (0, Hr)
+                rays = torch.empty(((r1 - r0) * Wr, 8), **f32)
+                capi.generate_rays(batch["tar_ext"][b].float().contiguous(), batch["tar_ixt"][b].float().contiguous(),
+                                   lv.render_scale, Wr, r0, r1 - r0, rays)
             N = rays.shape[0]
             views = (self.output_views or {}).get(i)
             if views is not None:   # write straight into the caller's (gather) buffer

@@ -115,13 +115,21 @@ def pack_nerf_tc(sd, p, feat_ch, viewdir_agg, device):
     shared = torch.zeros(24, 32)
     shared[0:fc] = gw[:, fc:2 * fc].t()
     shared[12:12 + fc] = gw[:, 2 * fc:3 * fc].t()
+    # the biases of global_fc and color.0 ride in the GEMMs: the kernel stores a constant 1 in the
+    # first padding column of the per-view A operands (col 11 of [g_s|pad], col 15 of [f_s|dir_s|pad])
+    gv = torch.zeros(16, 32)
+    gv[:fc] = gw[:, :fc].t()
+    gv[fc] = cpu[f"{p}.agg.global_fc.0.bias"]
+    cv = torch.zeros(16, 64)
+    cv[:fc + 4] = cw[:, 88:88 + fc + 4].t()
+    cv[fc + 4] = cpu[f"{p}.color.0.bias"]
     parts = [
-        _b_chunks(gw[:, :fc].t(), 16, 32),
+        _b_chunks(gv, 16, 32),
         _b_chunks(shared, 24, 32),
         _b_chunks(cpu[f"{p}.agg.fc.0.weight"].t(), 32, 16),
         _b_chunks(cpu[f"{p}.lr0.0.weight"].t(), 24, 64),
         _b_chunks(cw[:, :88].t(), 88, 64),
-        _b_chunks(cw[:, 88:88 + fc + 4].t(), 16, 64),
+        _b_chunks(cv, 16, 64),
     ]
     view_w, view_b = torch.zeros(4, 12), torch.zeros(12)
     if viewdir_agg:

@@ -1,0 +1,104 @@
+"""Serving-side wrappers around the drop-in ``Network`` (no reference counterpart: the reference's
+``run.py:57-76`` loop is synchronous -- H2D, forward, sync, D2H per frame).
+
+* ``GraphedNetwork``  -- captures one ``Network.forward`` for a fixed batch signature into a CUDA
+  graph (static input/output buffers) and replays it: one ``cudaGraphLaunch`` instead of ~40 kernel
+  launches + the Python between them.
+* ``StreamedRenderer`` -- sequence rendering from HOST batches: H2D of frame i+1, the forward of
+  frame i and D2H of frame i-1 run on three streams, so the end-to-end rate is bounded by the
+  slowest of the three instead of their sum.  Every frame still pays its own copies.
+
+Both produce exactly what ``Network.forward`` produces (same kernels, same order).
+"""
+import torch
+
+
+def _signature(batch):
+    return tuple(sorted((k, tuple(v.shape)) for k, v in batch.items() if torch.is_tensor(v)))
+
+
+class GraphedNetwork:
+    def __init__(self, net, example_batch, warmup=3):
+        """example_batch: CUDA tensors; defines the static signature."""
+        self.net = net
+        self.sig = _signature(example_batch)
+        self.static_in = {k: v.clone() for k, v in example_batch.items() if torch.is_tensor(v)}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):           # builds packed weights / scratch, sets kernel attributes
+                net(self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = net(self.static_in)
+
+    def load(self, batch, non_blocking=True):
+        if _signature(batch) != self.sig:
+            raise ValueError("batch signature differs from the captured graph")
+        for k, dst in self.static_in.items():
+            dst.copy_(batch[k], non_blocking=non_blocking)
+
+    def replay(self):
+        self.graph.replay()
+        return self.static_out
+
+    def __call__(self, batch):
+        self.load(batch)
+        return self.replay()
+
+
+class StreamedRenderer:
+    """render(host_batches) -> list of dicts of pinned host tensors, one per input batch."""
+
+    def __init__(self, net, example_host_batch, device, depth=2, use_graph=True):
+        self.dev, self.depth = device, depth
+        self.copy_in, self.compute, self.copy_out = torch.cuda.Stream(device), torch.cuda.Stream(device), torch.cuda.Stream(device)
+        ex = {k: v.to(device) for k, v in example_host_batch.items() if torch.is_tensor(v)}
+        self.slots = []
+        for _ in range(depth):
+            with torch.cuda.stream(self.compute):
+                g = GraphedNetwork(net, ex) if use_graph else None
+            slot = {"g": g, "in": g.static_in if g else {k: v.clone() for k, v in ex.items()},
+                    "h2d": torch.cuda.Event(), "done": torch.cuda.Event(), "d2h": torch.cuda.Event(), "free": torch.cuda.Event(),
+                    "host_out": None, "busy": False, "out": None}
+            self.slots.append(slot)
+        self.net = net
+        torch.cuda.synchronize(device)
+
+    def _submit(self, slot, host_batch):
+        with torch.cuda.stream(self.copy_in):
+            self.copy_in.wait_event(slot["free"])          # previous forward of this slot finished reading the inputs
+            for k, dst in slot["in"].items():
+                dst.copy_(host_batch[k], non_blocking=True)
+            slot["h2d"].record(self.copy_in)
+        with torch.cuda.stream(self.compute), torch.no_grad():
+            self.compute.wait_event(slot["h2d"])
+            self.compute.wait_event(slot["d2h"])           # previous outputs of this slot have been copied out
+            out = slot["g"].replay() if slot["g"] else self.net(slot["in"])
+            slot["done"].record(self.compute)
+            slot["free"].record(self.compute)
+        if slot["host_out"] is None:
+            slot["host_out"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(slot["done"])
+            for k, v in out.items():
+                v.record_stream(self.copy_out)
+                slot["host_out"][k].copy_(v, non_blocking=True)
+            slot["d2h"].record(self.copy_out)
+        slot["out"], slot["busy"] = out, True
+
+    def render(self, host_batches, on_frame=None):
+        """Streams the batches through; ``on_frame(i, host_out)`` is called once frame i is on the host
+        (the pinned buffers are reused ``depth`` frames later)."""
+        n = len(host_batches)
+        for i in range(n + self.depth):
+            if i >= self.depth:                 # retire the frame that used this slot `depth` submissions ago
+                s = self.slots[i % self.depth]
+                s["d2h"].synchronize()
+                if on_frame is not None:
+                    on_frame(i - self.depth, s["host_out"])
+            if i < n:
+                self._submit(self.slots[i % self.depth], host_batches[i])
+        return n

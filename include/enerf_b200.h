@@ -69,6 +69,13 @@ ENERF_API int enerf_camera_setup(const float* src_exts /*S,4,4*/, const float* s
                        const float* near_far /*2*/, int n_views, int n_levels,
                        const float* scales /*[host] n_levels*3*/, EnerfCam* cam_out, void* stream);
 
+/* Full-frame target rays generated on device: replaces the numpy
+ * builder lib/datasets/enerf_utils.py:25-32,60-71 ('test' branch) and the H2D copy of rays_{i}.
+ * rays (n_rows*W, 8) for image rows [row0, row0+n_rows) of the render-resolution frame of width W;
+ * scale = render_scale of the level (K rows 0,1 are multiplied by it). */
+ENERF_API int enerf_generate_rays(const float* tar_ext /*4,4*/, const float* tar_ixt /*3,3*/, float scale, int W, int row0,
+                                  int n_rows, float* rays, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * FeatureNet.forward (feature_net.py:27-36) + Network.forward_feat (network.py:58-67).
  * src_inps (S,3,H,W) NCHW in [-1,1].  H, W multiples of 4.

@@ -211,3 +211,54 @@ def test_tc_conv_layer(kind, KD, KH, cin, cout, mode, relu, dims):
     err = (got - refc).abs().max().item()
     assert not torch.isnan(got).any()
     assert err < 2e-3 * max(1.0, refc.abs().max().item()), f"max abs err {err} (ref max {refc.abs().max().item()})"
+
+
+def test_device_ray_generation_matches_data_layer(harness):
+    """enerf_generate_rays vs the reference's numpy builder (restated in synthetic.full_frame_rays,
+    itself cross-checked against lib/datasets/enerf_utils.py in oracle/make_golden.py)."""
+    from enerf_b200 import capi, synthetic
+    from enerf_b200 import config as bcfg
+    cfg = bcfg.make_cfg(volume_planes=[8, 8], render_if=[True, True])
+    batch = synthetic.make_batch(64, 96, 3, cfg, seed=5)
+    te, ti = batch["tar_ext"][0].cuda().contiguous(), batch["tar_ixt"][0].cuda().contiguous()
+    for scale, Hs, Ws in ((1.0, 64, 96), (0.25, 16, 24)):
+        out = torch.empty((Hs * Ws, 8), device="cuda")
+        capi.generate_rays(te, ti, scale, Ws, 0, Hs, out)
+        ref = torch.from_numpy(synthetic.full_frame_rays(batch["tar_ext"][0].numpy(), batch["tar_ixt"][0].numpy(), 64, 96, scale))
+        assert (out.cpu() - ref).abs().max().item() <= 1e-6 * max(1.0, ref.abs().max().item())
+        band = torch.empty((4 * Ws, 8), device="cuda")
+        capi.generate_rays(te, ti, scale, Ws, 3, 4, band)
+        assert torch.equal(band, out[3 * Ws:7 * Ws])
+
+
+def test_forward_without_rays_graph_and_streamed(harness):
+    """(a) a batch without rays_{i} renders identically (rays generated on device); (b) CUDA-graph
+    replay and (c) the 3-stream StreamedRenderer return exactly what Network.forward returns."""
+    from enerf_b200 import config as bcfg
+    from enerf_b200.network import Network
+    from enerf_b200.pipeline import GraphedNetwork, StreamedRenderer
+    cfg = bcfg.make_cfg(volume_planes=[8, 8], render_if=[False, True])
+    sd, batch = harness.make_case(64, 96, 3, cfg, seed=3)
+    net = Network()
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    gb = {k: v.cuda() for k, v in batch.items()}
+    with torch.no_grad():
+        full = {k: v.clone() for k, v in net(gb).items()}
+        norays = {k: v for k, v in gb.items() if not k.startswith("rays_")}
+        gen = net(norays)
+    for k in full:
+        assert (gen[k] - full[k]).abs().max().item() <= 1e-5, k     # ray directions agree to ~1 ulp
+    g = GraphedNetwork(net, norays)
+    out = g(norays)
+    torch.cuda.synchronize()
+    for k in gen:
+        assert torch.equal(out[k], gen[k]), k
+    host = {k: v.cpu().pin_memory() for k, v in norays.items()}
+    got = []
+    sr = StreamedRenderer(net, host, torch.device("cuda"), depth=2)
+    sr.render([host] * 5, lambda i, o: got.append({k: v.clone() for k, v in o.items()}))
+    assert len(got) == 5
+    for o in got:
+        for k in gen:
+            assert torch.equal(o[k], gen[k].cpu()), k
