@@ -243,12 +243,16 @@ def test_forward_without_rays_graph_and_streamed(harness):
     net.load_state_dict(sd)
     net = net.cuda().eval()
     gb = {k: v.cuda() for k, v in batch.items()}
+    norays = {k: v for k, v in gb.items() if not k.startswith("rays_")}
+    net.precision = "fp32"      # exact mode: a 1-ulp change of the ray directions stays a 1e-5 change of the output
     with torch.no_grad():
         full = {k: v.clone() for k, v in net(gb).items()}
-        norays = {k: v for k, v in gb.items() if not k.startswith("rays_")}
-        gen = net(norays)
+        gen32 = net(norays)
     for k in full:
-        assert (gen[k] - full[k]).abs().max().item() <= 1e-5, k     # ray directions agree to ~1 ulp
+        assert (gen32[k] - full[k]).abs().max().item() <= 2e-5 * max(1.0, full[k].abs().max().item()), k
+    net.precision = "tf32"
+    with torch.no_grad():
+        gen = {k: v.clone() for k, v in net(norays).items()}
     g = GraphedNetwork(net, norays)
     out = g(norays)
     torch.cuda.synchronize()
