@@ -41,7 +41,7 @@ _SIGS = {
                                _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "enerf_render_rays_tc": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i,
                                   _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "enerf_tc_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "enerf_tc_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "enerf_tc_conv_debug": (_i, [_vp]),
     "enerf_tc_mma_bench": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "enerf_render_rays_debug": (_i, [_vp]),
@@ -188,10 +188,10 @@ def tc_ray_kernel_supports(feat_ch, n_views, num_samples):
     return feat_ch == 8 and 2 <= n_views <= 4 and num_samples in (1, 2, 4, 8)
 
 
-def tc_conv(kind, KD, KH, cout, mode, relu, x, wpack, bias, skip, out, out2=None, out_cstride=None, out_coff=0):
+def tc_conv(kind, KD, KH, cout, mode, relu, x, wpack, bias, skip, out, out2=None, out_cstride=None, out_coff=0, stride=1):
     """x (D,H,W,cin) channels-last.  See enerf_tc_conv in include/enerf_b200.h."""
     D, H, W, cin = x.shape
-    _check(lib().enerf_tc_conv(kind, KD, KH, cin, cout, mode, int(relu), ptr(x), D, H, W, ptr(wpack), ptr(bias, True), ptr(skip, True),
+    _check(lib().enerf_tc_conv(kind, KD, KH, stride, cin, cout, mode, int(relu), ptr(x), D, H, W, ptr(wpack), ptr(bias, True), ptr(skip, True),
                                ptr(out), ptr(out2, True), out_cstride if out_cstride is not None else cout, out_coff, stream()),
            "enerf_tc_conv")
 

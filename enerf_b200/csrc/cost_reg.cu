@@ -261,13 +261,25 @@ extern "C" int enerf_cost_reg(const float* const* wts, int n_weights, int deep, 
   } else {
     RUN(launch_conv<C0_8>("cost_reg.conv0", variance, wts[0], wts[1], ws.c0, nullptr, D, h, w, 8, 0, stream));
   }
-  RUN((launch_small<8, 16, 2>("cost_reg.conv1", ws.c0, wts[2], wts[3], ws.c1, D, h, w, stream)));
+  auto tc_s2 = [&](int cin, int cout, const float* in, int do_, int ho_, int wo_, const float* wp, const float* b, float* o) {
+    TcConvLayer L{0, 3, 3, cin, cout, TC_PLAIN, 1, 2};        // (do_,ho_,wo_) = OUTPUT grid
+    return tc_conv_launch(L, in, do_, ho_, wo_, wp, b, nullptr, o, nullptr, cout, 0, stream);
+  };
+  if (tensor_cores) {
+    RUN(tc_s2(8, 16, ws.c0, D2, h2, w2, wts[2], wts[3], ws.c1));
+  } else {
+    RUN((launch_small<8, 16, 2>("cost_reg.conv1", ws.c0, wts[2], wts[3], ws.c1, D, h, w, stream)));
+  }
   if (tensor_cores) {
     RUN(tc_cbr(16, 16, ws.c1, D2, h2, w2, wts[4], wts[5], ws.c2));
   } else {
     RUN((launch_small<16, 16, 1>("cost_reg.conv2", ws.c1, wts[4], wts[5], ws.c2, D2, h2, w2, stream)));
   }
-  RUN((launch_small<16, 32, 2>("cost_reg.conv3", ws.c2, wts[6], wts[7], ws.c3, D2, h2, w2, stream)));
+  if (tensor_cores) {
+    RUN(tc_s2(16, 32, ws.c2, D4, h4, w4, wts[6], wts[7], ws.c3));
+  } else {
+    RUN((launch_small<16, 32, 2>("cost_reg.conv3", ws.c2, wts[6], wts[7], ws.c3, D2, h2, w2, stream)));
+  }
   if (tensor_cores) {
     RUN(tc_cbr(32, 32, ws.c3, D4, h4, w4, wts[8], wts[9], ws.c4));
   } else {
@@ -276,11 +288,12 @@ extern "C" int enerf_cost_reg(const float* const* wts, int n_weights, int deep, 
   const float* x4 = ws.c4;
   int wi = 10;
   if (deep) {
-    RUN((launch_small<32, 64, 2>("cost_reg.conv5", ws.c4, wts[10], wts[11], ws.c5, D4, h4, w4, stream)));
     if (tensor_cores) {
+      RUN(tc_s2(32, 64, ws.c4, D8, h8, w8, wts[10], wts[11], ws.c5));
       RUN(tc_cbr(64, 64, ws.c5, D8, h8, w8, wts[12], wts[13], ws.c6));
       RUN(tc_dec(64, 32, ws.c6, D8, h8, w8, wts[14], wts[15], ws.c4, ws.y4));
     } else {
+      RUN((launch_small<32, 64, 2>("cost_reg.conv5", ws.c4, wts[10], wts[11], ws.c5, D4, h4, w4, stream)));
       RUN((launch_small<64, 64, 1>("cost_reg.conv6", ws.c5, wts[12], wts[13], ws.c6, D8, h8, w8, stream)));
       RUN((launch_deconv<64, 32>("cost_reg.conv7", ws.c6, wts[14], wts[15], ws.c4, ws.y4, D8, h8, w8, stream)));
     }

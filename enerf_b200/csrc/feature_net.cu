@@ -179,13 +179,23 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
   } else {
     RUN(launch_conv<Conv01>("feature_net.conv0.1", ws.c0a, wts[2], wts[3], ws.c0, nullptr, S, H, W, 8, 0, stream));
   }
-  RUN(launch_conv<Conv10>("feature_net.conv1.0", ws.c0, wts[4], wts[5], ws.c1a, nullptr, S, H, W, 16, 0, stream));
+  if (tensor_cores) {   // 5x5 stride 2: phase-tile staging (tc_conv.cuh)
+    TcConvLayer L{0, 1, 5, 8, 16, TC_PLAIN, 1, 2};
+    RUN(tc_conv_launch(L, ws.c0, S, H2, W2, wts[4], wts[5], nullptr, ws.c1a, nullptr, 16, 0, stream));
+  } else {
+    RUN(launch_conv<Conv10>("feature_net.conv1.0", ws.c0, wts[4], wts[5], ws.c1a, nullptr, S, H, W, 16, 0, stream));
+  }
   if (tensor_cores) {
     RUN(tc("feature_net.conv1.1", 3, 16, 16, 1, ws.c1a, H2, W2, wts[6], wts[7], ws.c1));
   } else {
     RUN(launch_conv<Conv11>("feature_net.conv1.1", ws.c1a, wts[6], wts[7], ws.c1, nullptr, S, H2, W2, 16, 0, stream));
   }
-  RUN(launch_conv<Conv20>("feature_net.conv2.0", ws.c1, wts[8], wts[9], ws.c2a, nullptr, S, H2, W2, 32, 0, stream));
+  if (tensor_cores) {
+    TcConvLayer L{0, 1, 5, 16, 32, TC_PLAIN, 1, 2};
+    RUN(tc_conv_launch(L, ws.c1, S, H4, W4, wts[8], wts[9], nullptr, ws.c2a, nullptr, 32, 0, stream));
+  } else {
+    RUN(launch_conv<Conv20>("feature_net.conv2.0", ws.c1, wts[8], wts[9], ws.c2a, nullptr, S, H2, W2, 32, 0, stream));
+  }
   if (tensor_cores) {
     RUN(tc("feature_net.conv2.1", 3, 32, 32, 1, ws.c2a, H4, W4, wts[10], wts[11], ws.c2));
     RUN(tc("feature_net.toplayer", 1, 32, 32, 0, ws.c2, H4, W4, wts[12], wts[13], feat_l0));

@@ -9,8 +9,11 @@ struct TcConvParams {
   int TZ, TY, TX;        // tile
   int IZ, IY, IX;        // tile + halo
   int oz, oy, ox;        // halo origin = tile origin - (oz,oy,ox)
+  int Di, Hi, Wi;        // input extent (== row grid for stride 1; 2x for stride 2)
+  int sz, sy, sx;        // stride per dimension (1|2): the halo is staged as sz*sy*sx phase tiles
+  int n_phases;          //   X_r[q] = in[s*q + r]; input coord of phase-tile pixel p: s*(o0 + p - o) + r
   int n_taps;
-  int tap_off[27];       // linear offsets (pixels) inside the halo tile
+  int tap_off[27];       // operand start offsets in 16-byte units: phase*(2*npix) + linear pixel offset
   int n_stages;          // Cin / 8
   int N;                 // MMA N (multiple of 16, <= 256)
   int n_mt;              // 128-row M-tiles per CTA
@@ -63,12 +66,13 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
   const int t = threadIdx.x, warp = t >> 5;
   unsigned long long* dbg = (g_tc_dbg && t == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_tc_dbg : nullptr;
   TC_STAMP(0);
-  const int npix = P.IZ * P.IY * P.IX;
-  const uint32_t a_bytes = (uint32_t)npix * 32u;                   // two 4-channel planes
+  const int npix = P.IZ * P.IY * P.IX;                             // pixels of ONE phase tile
+  const int npix_tot = npix * P.n_phases;
+  const uint32_t a_bytes = (uint32_t)npix_tot * 32u;               // per phase: two 4-channel planes
   const uint32_t w_bytes = (uint32_t)NTAPS * (uint32_t)P.N * 32u;
   const uint32_t stage_bytes = (a_bytes + w_bytes + 127u) & ~127u;
   unsigned char* stage0 = smem_raw;
-  int* pix_off = reinterpret_cast<int*>(smem_raw + 2 * (size_t)stage_bytes);   // [npix] global pixel index or -1
+  int* pix_off = reinterpret_cast<int*>(smem_raw + (size_t)(P.n_stages > 1 ? 2 : 1) * stage_bytes);   // [npix_tot] input pixel or -1
 
   if (t == 0) {
     tc::mbar_init(&full_bar[0], 129);   // 128 copier threads + the weight copy's expect_tx arrival
@@ -82,11 +86,13 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
   const int x0 = blockIdx.x * P.TX, y0 = blockIdx.y * P.TY, z0 = blockIdx.z * P.TZ;
   {
     const int plane = P.IY * P.IX;
-    for (int p = t; p < npix; p += 128) {
+    for (int e = t; e < npix_tot; e += 128) {
+      const int ph = e / npix, p = e - ph * npix;
+      const int rx = ph % P.sx, ry = (ph / P.sx) % P.sy, rz = ph / (P.sx * P.sy);
       const int z = p / plane, rem = p - z * plane, y = rem / P.IX, x = rem - y * P.IX;
-      const int gz = z0 - P.oz + z, gy = y0 - P.oy + y, gx = x0 - P.ox + x;
-      const bool ok = gz >= 0 && gz < P.Dn && gy >= 0 && gy < P.Hn && gx >= 0 && gx < P.Wn;
-      pix_off[p] = ok ? (gz * P.Hn + gy) * P.Wn + gx : -1;
+      const int gz = P.sz * (z0 - P.oz + z) + rz, gy = P.sy * (y0 - P.oy + y) + ry, gx = P.sx * (x0 - P.ox + x) + rx;
+      const bool ok = gz >= 0 && gz < P.Di && gy >= 0 && gy < P.Hi && gx >= 0 && gx < P.Wi;
+      pix_off[e] = ok ? (gz * P.Hi + gy) * P.Wi + gx : -1;
     }
   }
   tc::tc_fence_before_sync();
@@ -104,11 +110,12 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
     }
     const uint32_t sa_u = tc::smem_u32(sa);
     const float* src0 = in + 8 * st;
-    for (int e = t; e < 2 * npix; e += 128) {
-      const int j = e & 1, p = e >> 1;
-      const int off = pix_off[p];
+    for (int e = t; e < 2 * npix_tot; e += 128) {
+      const int j = e & 1, q = e >> 1;
+      const int ph = q / npix, p = q - ph * npix;
+      const int off = pix_off[q];
       const float* src = src0 + (off >= 0 ? (size_t)off * cin + 4 * j : 0);
-      cp_async16_zfill(sa_u + (uint32_t)j * (uint32_t)npix * 16u + (uint32_t)p * 16u, src, off >= 0 ? 16u : 0u);
+      cp_async16_zfill(sa_u + (uint32_t)((ph * 2 + j) * npix + p) * 16u, src, off >= 0 ? 16u : 0u);
     }
     cp_async_commit();
   };
@@ -245,13 +252,28 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
   P.out_cstride = out_cstride, P.out_coff = out_coff;
   P.wpack = wpack, P.bias = bias, P.skip = skip, P.out = out, P.out2 = out2;
   P.n_stages = L.cin / 8;
+  const int stride = (L.kind == 0) ? L.stride : 1;
+  ENERF_REQUIRE(stride == 1 || stride == 2, ENERF_EUNSUPPORTED, "tc_conv: stride %d", stride);
+  P.sz = (stride == 2 && L.KD > 1) ? 2 : 1, P.sy = stride, P.sx = stride;
+  P.n_phases = P.sz * P.sy * P.sx;
+  P.Di = (P.sz == 2) ? 2 * Dn : Dn, P.Hi = stride * Hn, P.Wi = stride * Wn;   // even inputs (pad K/2) halve exactly
   int n_real = (L.kind == 1) ? 8 * L.cout : L.cout;
   P.N = (n_real + 15) / 16 * 16;
   ENERF_REQUIRE(P.N <= 256, ENERF_EUNSUPPORTED, "tc_conv: N=%d > 256", P.N);
   if (L.mode == TC_DECONV) ENERF_REQUIRE(L.cout % 8 == 0 && skip && bias, ENERF_EINVAL, "tc_conv: deconv needs cout%%8==0, skip and bias");
 
-  const int hz = (L.kind == 1) ? 1 : L.KD - 1, hy = (L.kind == 1) ? 1 : L.KH - 1, hx = hy;  // halo extents
-  P.oz = (L.kind == 1) ? 0 : L.KD / 2, P.oy = (L.kind == 1) ? 0 : L.KH / 2, P.ox = P.oy;
+  // per-dimension tap decomposition  k - pad = s*d + r :  halo extent E = dmax - dmin, origin shift o = -dmin
+  auto dim_geom = [](int K, int s, int kind, int& E, int& o) {
+    if (kind == 1) { E = 1, o = 0; return; }
+    const int pad = K / 2;
+    if (s == 1) { E = K - 1, o = pad; return; }
+    const int dmin = -((pad + 1) / 2), dmax = (K - 1 - pad) / 2;    // floor(-pad/2), floor((K-1-pad)/2)
+    E = dmax - dmin, o = -dmin;
+  };
+  int hz, hy, hx;
+  dim_geom(L.KD, P.sz, L.kind, hz, P.oz);
+  dim_geom(L.KH, P.sy, L.kind, hy, P.oy);
+  dim_geom(L.KH, P.sx, L.kind, hx, P.ox);
   P.TX = 32;
   P.TY = (L.kind == 0 && L.KD == 1) ? 16 : 8;
   P.TZ = (L.kind == 0 && L.KD == 1) ? 1 : 2;
@@ -263,24 +285,36 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
     P.IZ = P.TZ + hz, P.IY = P.TY + hy, P.IX = P.TX + hx;
     const int pmax = ((P.TZ - 1) * P.IY + (P.TY - 1)) * P.IX + P.TX - 1;
     P.n_mt = pmax / 128 + 1;
-    // taps
+    const int npix = P.IZ * P.IY * P.IX;
+    // taps: operand start offset (16-byte units) = phase block + linear pixel offset inside the phase tile
     if (L.kind == 1) {
       P.n_taps = 8;
       for (int d = 0; d < 8; ++d) P.tap_off[d] = (((d >> 2) & 1) * P.IY + ((d >> 1) & 1)) * P.IX + (d & 1);
     } else {
       P.n_taps = L.KD * L.KH * L.KH;
+      auto split = [](int k, int K, int s, int o, int& d, int& r) {   // k - pad = s*d + r, returns d' = d + o
+        const int tt = k - K / 2;
+        if (s == 1) { d = tt + o, r = 0; return; }
+        const int fl = (tt >= 0) ? tt / 2 : -((-tt + 1) / 2);
+        r = tt - 2 * fl, d = fl + o;
+      };
       int i = 0;
       for (int kz = 0; kz < L.KD; ++kz)
         for (int ky = 0; ky < L.KH; ++ky)
-          for (int kx = 0; kx < L.KH; ++kx) P.tap_off[i++] = (kz * P.IY + ky) * P.IX + kx;
+          for (int kx = 0; kx < L.KH; ++kx) {
+            int dz, rz, dy, ry, dx, rx;
+            split(kz, L.KD, P.sz, P.oz, dz, rz);
+            split(ky, L.KH, P.sy, P.oy, dy, ry);
+            split(kx, L.KH, P.sx, P.ox, dx, rx);
+            const int ph = (rz * P.sy + ry) * P.sx + rx;
+            P.tap_off[i++] = ph * 2 * npix + (dz * P.IY + dy) * P.IX + dx;
+          }
     }
-    const int npix = P.IZ * P.IY * P.IX;
-    stage_bytes = ((uint32_t)npix * 32u + (uint32_t)P.n_taps * (uint32_t)P.N * 32u + 127u) & ~127u;
-    const int max_off = P.tap_off[P.n_taps - 1];
-    // [stage 0][stage 1][pixel table][tail]: rows past the end of the second plane of the last
-    // slot (only the dropped garbage rows read them) must stay inside the allocation
-    const int overflow_rows = P.n_mt * 128 + max_off - npix;
-    smem = 2 * (size_t)stage_bytes + (size_t)npix * 4 + 64 + (overflow_rows > 0 ? (size_t)overflow_rows * 16 : 0);
+    const int npix_tot = npix * P.n_phases;
+    stage_bytes = ((uint32_t)npix_tot * 32u + (uint32_t)P.n_taps * (uint32_t)P.N * 32u + 127u) & ~127u;
+    // [stage 0][stage 1][pixel table][tail]: the dropped garbage rows of the last M-tile may read past
+    // the end of a phase block; keep those reads inside the allocation
+    smem = (size_t)(P.n_stages > 1 ? 2 : 1) * stage_bytes + (size_t)npix_tot * 4 + 64 + (size_t)(P.n_mt * 128 + 64) * 16;
     const long long n_cta = (long long)ceil_div(Wn, P.TX) * ceil_div(Hn, P.TY) * ceil_div(Dn, P.TZ);
     const bool fits = P.n_mt * P.N <= 512 && smem <= 200 * 1024;
     // small layers: keep shrinking the tile until the grid covers the 148 SMs (fewer M-tiles per
@@ -288,6 +322,7 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
     if (fits && (n_cta >= 148 || (P.TY <= 2 && P.TZ <= 1))) break;
     if (P.TY > 2) P.TY /= 2;
     else if (P.TZ > 1) P.TZ /= 2;
+    else if (!fits && P.TX > 16) P.TX /= 2;
     else ENERF_REQUIRE(false, ENERF_EUNSUPPORTED, "tc_conv: no tile fits (N=%d taps=%d)", P.N, P.n_taps);
   }
   uint32_t cols = 32;
@@ -311,6 +346,7 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
   else if (P.n_taps == 27 && L.mode == TC_HEAD) TC_LAUNCH(27, TC_HEAD);
   else if (P.n_taps == 27 && L.mode == TC_SINGLE) TC_LAUNCH(27, TC_SINGLE);
   else if (P.n_taps == 9 && L.mode == TC_PLAIN) TC_LAUNCH(9, TC_PLAIN);
+  else if (P.n_taps == 25 && L.mode == TC_PLAIN) TC_LAUNCH(25, TC_PLAIN);
   else if (P.n_taps == 1 && L.mode == TC_PLAIN) TC_LAUNCH(1, TC_PLAIN);
   else ENERF_REQUIRE(false, ENERF_EUNSUPPORTED, "tc_conv: no instantiation for %d taps, mode %d", P.n_taps, L.mode);
 #undef TC_LAUNCH
@@ -320,14 +356,20 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
 
 }  // namespace enerf
 
-extern "C" int enerf_tc_conv(int kind, int KD, int KH, int cin, int cout, int mode, int relu, const float* in, int D, int H, int W,
+extern "C" int enerf_tc_conv(int kind, int KD, int KH, int stride, int cin, int cout, int mode, int relu, const float* in, int D, int H, int W,
                              const float* wpack, const float* bias, const float* skip, float* out, float* out2, int out_cstride,
                              int out_coff, void* stream) {
   using namespace enerf;
   ENERF_REQUIRE(in && wpack && out, ENERF_EINVAL, "tc_conv: null pointer");
   ENERF_REQUIRE(kind == 0 || kind == 1, ENERF_EINVAL, "tc_conv: kind %d", kind);
-  ENERF_REQUIRE((KD == 1 || KD == 3) && (KH == 1 || KH == 3), ENERF_EUNSUPPORTED, "tc_conv: kernel %dx%dx%d", KD, KH, KH);
-  TcConvLayer L{kind, KD, KH, cin, cout, mode, relu};
+  ENERF_REQUIRE((KD == 1 || KD == 3) && (KH == 1 || KH == 3 || (KH == 5 && KD == 1)), ENERF_EUNSUPPORTED, "tc_conv: kernel %dx%dx%d", KD, KH, KH);
+  ENERF_REQUIRE(stride == 1 || (stride == 2 && kind == 0 && D % (KD > 1 ? 2 : 1) == 0 && H % 2 == 0 && W % 2 == 0), ENERF_EINVAL,
+                "tc_conv: stride %d needs an even input extent", stride);
+  if (stride == 2) {   // (D,H,W) is the INPUT extent; rows are enumerated over the output grid
+    if (KD > 1) D /= 2;
+    H /= 2, W /= 2;
+  }
+  TcConvLayer L{kind, KD, KH, cin, cout, mode, relu, stride};
   return tc_conv_launch(L, in, D, H, W, wpack, bias, skip, out, out2, out_cstride, out_coff, (cudaStream_t)stream);
 }
 

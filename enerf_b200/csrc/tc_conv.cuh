@@ -15,6 +15,8 @@
 //            TMA bulk copy (cp.async.bulk) next to the activations.
 //   MMA    : one thread issues n_stages * n_mtiles * n_taps tcgen05.mma (M=128, N=Cout padded to
 //            16, K=8); accumulators of all M-tiles of the CTA live in TMEM (n_mtiles*N columns).
+//   Stride 2 : the halo is staged as 2^d phase tiles X_r[q] = in[2q + r]; a tap k - pad = 2d + r reads
+//            phase r at offset d, i.e. once more just a different operand start address.
 //   Epilogue: 128 threads = 128 TMEM lanes; tcgen05.ld, bias / ReLU / skip add, coalesced
 //            channels-last stores; for the transposed convolutions the 8 output parities are the
 //            N dimension (N = 8*Cout) and the epilogue does the pixel shuffle.
@@ -32,6 +34,7 @@ struct TcConvLayer {
   int KD, KH;        // conv kernel extents (KD = 1 for 2-D layers)
   int cin, cout;
   int mode, relu;
+  int stride = 1;    // 1 | 2 (kind 0 only).  Dn,Hn,Wn passed to tc_conv_launch are ALWAYS the output grid.
 };
 
 int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias,

@@ -31,8 +31,8 @@ def _dev(t, device):
     return t.to(device=device, dtype=torch.float32).contiguous()
 
 
-# layers enerf_feature_net runs on tcgen05 when tensor_cores != 0 (every stride-1 layer with cin % 8 == 0)
-TC_FEATURE_LAYERS = ("conv0.1", "conv1.1", "conv2.1", "toplayer", "smooth1", "smooth0")
+# layers enerf_feature_net runs on tcgen05 when tensor_cores != 0 (every layer with cin % 8 == 0; all but conv0.0)
+TC_FEATURE_LAYERS = ("conv0.1", "conv1.0", "conv1.1", "conv2.0", "conv2.1", "toplayer", "smooth1", "smooth0")
 
 
 def pack_feature_net(sd, device, p="feature_net", tensor_cores=False):
@@ -64,7 +64,7 @@ def pack_cost_reg(sd, p, in_ch, deep, device, with_feat, tensor_cores=False):
         if kind == "cbr":
             w, b = _fold(sd[q + ".conv.weight"], sd, q + ".bn", 0)
             wt = _taps_cin_cout(w)
-            use_tc = tensor_cores and stride == 1
+            use_tc = tensor_cores
             out += [pack_tc_conv(wt).to(device) if use_tc else _dev(wt, device), _dev(b, device)]
         elif kind == "deconv":
             w, b = _fold(sd[q + ".0.weight"], sd, q + ".1", 1)      # (Cin,Cout,kz,ky,kx)

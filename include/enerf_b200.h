@@ -82,10 +82,10 @@ ENERF_API int enerf_generate_rays(const float* tar_ext /*4,4*/, const float* tar
  * Outputs (channels-last): feat_l0 (S,H/4,W/4,32), feat_l1 (S,H/2,W/2,16), feat_l2 (S,H,W,8).
  * weights [host array, 22 device pointers], each conv as {w [tap][cin][cout] BN-folded, bias[cout]}:
  *   conv0.0, conv0.1, conv1.0, conv1.1, conv2.0, conv2.1, toplayer, lat1, lat0, smooth1, smooth0.
- * tensor_cores != 0: the stride-1 layers with cin % 8 == 0 (conv0.1, conv1.1, conv2.1, toplayer,
- * smooth1, smooth0) run as tcgen05 implicit GEMMs (TF32 operands) and take their w in the
- * enerf_tc_conv stage layout (packing.pack_tc_conv); conv0.0 (cin 3), the 5x5 stride-2 layers and
- * the laterals keep the [tap][cin][cout] fp32 layout and kernels.
+ * tensor_cores != 0: every layer with cin % 8 == 0 (conv0.1, conv1.0, conv1.1, conv2.0, conv2.1,
+ * toplayer, smooth1, smooth0) runs as a tcgen05 implicit GEMM (TF32 operands) and takes its w in
+ * the enerf_tc_conv stage layout (packing.pack_tc_conv); conv0.0 (cin 3) and the fused laterals
+ * keep the [tap][cin][cout] fp32 layout and kernels.
  */
 ENERF_API size_t enerf_feature_net_workspace_bytes(int n_views, int H, int W);
 ENERF_API int enerf_feature_net(const float* const* weights, int n_weights, const float* src_inps, int n_views,
@@ -125,9 +125,8 @@ ENERF_API int enerf_cost_volume(const EnerfCam* cam, int level, const float* fea
  * w [tap][8][9] with output channel 8 = depth_conv and 0..7 = feat_conv when feat_vol != NULL, or
  * w [tap][8][1] (depth_conv only) when feat_vol == NULL.  Forward convs: w [tap][cin][cout];
  * transposed convs: w [tap][cin][cout] with tap = (kz*3+ky)*3+kx of the ConvTranspose3d kernel.
- * tensor_cores != 0: the stride-1 layers (conv0, conv2, conv4, conv6, head) and the transposed
- * layers (conv7, conv9, conv11) run on tcgen05 (TF32) and take w in the enerf_tc_conv stage layout
- * (packing.pack_tc_conv / pack_tc_deconv); the stride-2 layers keep the fp32 layout and kernels. */
+ * tensor_cores != 0: every layer runs on tcgen05 (TF32) and takes w in the enerf_tc_conv stage
+ * layout (packing.pack_tc_conv; transposed layers packing.pack_tc_deconv). */
 ENERF_API size_t enerf_cost_reg_workspace_bytes(int deep, int D, int h, int w);
 ENERF_API int enerf_cost_reg(const float* const* weights, int n_weights, int deep, int in_ch, const float* variance,
                    int D, int h, int w, float* feat_vol, float* depth_prob, void* workspace,
@@ -173,13 +172,14 @@ ENERF_API int enerf_render_rays_tc(const EnerfCam* cam, int level, const float* 
 
 /* One convolution layer on the tensor cores (tcgen05 implicit GEMM, csrc/tc_conv.cuh): the building
  * block enerf_feature_net / enerf_cost_reg use in TF32 mode, exported for layer-level parity tests.
- *   kind 0: stride-1 convolution KD x KH x KH (KD in {1,3}, KH in {1,3}), zero padding K/2.
+ *   kind 0: convolution KD x KH x KH (KD in {1,3}, KH in {1,3}; KH = 5 with KD = 1), zero padding K/2,
+ *           stride 1 or 2 (stride 2 strides H and W, and D when KD = 3; (D,H,W) = INPUT extent, even).
  *   kind 1: ConvTranspose3d(k3, s2, p1, output_padding 1) in sub-pixel form; (D,H,W) is the INPUT grid.
  *   mode 0: out[pix][out_coff..+cout) = act(acc + bias);  1: head (8 feat -> out, 1 prob -> out2);
  *        2: transposed conv, out = skip + acc + bias;     3: single channel -> out.
  * in (D,H,W,cin) channels-last, cin % 8 == 0.  wpack: enerf_b200/packing.py::pack_tc_conv /
  * pack_tc_deconv ([cin/8][tap][2][N][4], TF32-rounded, N = cout (x8 for kind 1) padded to 16). */
-ENERF_API int enerf_tc_conv(int kind, int KD, int KH, int cin, int cout, int mode, int relu, const float* in, int D, int H,
+ENERF_API int enerf_tc_conv(int kind, int KD, int KH, int stride, int cin, int cout, int mode, int relu, const float* in, int D, int H,
                             int W, const float* wpack, const float* bias, const float* skip, float* out, float* out2,
                             int out_cstride, int out_coff, void* stream);
 

@@ -159,11 +159,18 @@ TC_CONV_CASES = [
     (1, 3, 3, 16, 8, 2, 0, (4, 16, 24)),     # conv11 (transposed)
     (1, 3, 3, 32, 16, 2, 0, (2, 8, 12)),     # conv9
     (1, 3, 3, 64, 32, 2, 0, (1, 4, 6)),      # conv7
+    (0, 3, 3, 8, 16, 0, 1, (8, 32, 48), 2),  # conv1 (stride 2: phase-tile staging)
+    (0, 3, 3, 16, 32, 0, 1, (4, 16, 24), 2),  # conv3
+    (0, 3, 3, 32, 64, 0, 1, (2, 8, 12), 2),  # conv5
+    (0, 1, 5, 8, 16, 0, 1, (3, 64, 96), 2),  # FeatureNet conv1.0 (5x5 stride 2)
+    (0, 1, 5, 16, 32, 0, 1, (2, 32, 48), 2),  # conv2.0
 ]
 
 
-@pytest.mark.parametrize("kind,KD,KH,cin,cout,mode,relu,dims", TC_CONV_CASES)
-def test_tc_conv_layer(kind, KD, KH, cin, cout, mode, relu, dims):
+@pytest.mark.parametrize("case", TC_CONV_CASES)
+def test_tc_conv_layer(case):
+    kind, KD, KH, cin, cout, mode, relu, dims = case[:8]
+    stride = case[8] if len(case) > 8 else 1
     """tcgen05 implicit-GEMM convolution vs torch's fp32 conv on the same (TF32-rounded) operands.
     Bound: 2e-3 * max|ref| (TF32 operand rounding of activations; weights are pre-rounded)."""
     if not torch.cuda.is_available():
@@ -176,7 +183,7 @@ def test_tc_conv_layer(kind, KD, KH, cin, cout, mode, relu, dims):
     if kind == 0:
         w = torch.randn(cout, cin, KD, KH, KH, generator=g) / (cin * KD * KH * KH) ** 0.5
         b = torch.randn(cout, generator=g) * 0.1 if mode == 0 else None
-        ref = F.conv3d(x, w, b, 1, (KD // 2, KH // 2, KH // 2))
+        ref = F.conv3d(x, w, b, (stride if KD > 1 else 1, stride, stride), (KD // 2, KH // 2, KH // 2))
         if relu:
             ref = F.relu(ref)
         wp = packing.pack_tc_conv(packing._taps_cin_cout(w)).cuda()
@@ -199,7 +206,7 @@ def test_tc_conv_layer(kind, KD, KH, cin, cout, mode, relu, dims):
     else:
         out = torch.full((Do, Ho, Wo, cout), float("nan"), device="cuda")
     capi.tc_conv(kind, KD, KH, cout, mode, relu, xin, wp, b.cuda() if b is not None else None, skip, out, out2,
-                 out_cstride=(8 if mode == 1 else cout))
+                 out_cstride=(8 if mode == 1 else cout), stride=stride)
     torch.cuda.synchronize()
     refc = ref[0].permute(1, 2, 3, 0)
     if mode == 1:
