@@ -30,7 +30,7 @@ _SIGS = {
     "enerf_camera_setup": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, ctypes.POINTER(ctypes.c_float), _vp, _vp]),
     "enerf_generate_rays": (_i, [_vp, _vp, ctypes.c_float, _i, _i, _i, _vp, _vp]),
     "enerf_feature_net_workspace_bytes": (_sz, [_i, _i, _i]),
-    "enerf_feature_net": (_i, [ctypes.POINTER(_vp), _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "enerf_feature_net": (_i, [ctypes.POINTER(_vp), _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     "enerf_pack_img_feat": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "enerf_depth_hypotheses": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "enerf_cost_volume": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
@@ -111,12 +111,12 @@ def feature_net_workspace_bytes(S, H, W):
     return lib().enerf_feature_net_workspace_bytes(S, H, W)
 
 
-def feature_net(weights, src_inps, feat_l0, feat_l1, feat_l2, workspace, tensor_cores=False):
+def feature_net(weights, src_inps, feat_l0, feat_l1, feat_l2, workspace, tensor_cores=False, part=0):
     S, _, H, W = src_inps.shape
     _check(lib().enerf_feature_net(ptr_array(weights), len(weights), ptr(src_inps), S, H, W, ptr(feat_l0), ptr(feat_l1),
                                    ptr(feat_l2), workspace.data_ptr(), workspace.numel() * workspace.element_size(),
-                                   int(tensor_cores), stream()),
-           "enerf_feature_net", launches=11)
+                                   int(tensor_cores), part, stream()),
+           "enerf_feature_net", launches={0: 11, 1: 7, 2: 4}[part])
 
 
 def pack_img_feat(feat, src_inps, out):

@@ -153,7 +153,7 @@ extern "C" size_t enerf_feature_net_workspace_bytes(int n_views, int H, int W) {
 
 extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const float* src_inps, int S, int H, int W,
                                  float* feat_l0, float* feat_l1, float* feat_l2, void* workspace, size_t workspace_bytes,
-                                 int tensor_cores, void* stream_) {
+                                 int tensor_cores, int part, void* stream_) {
   using namespace enerf;
   cudaStream_t stream = (cudaStream_t)stream_;
   ENERF_REQUIRE(wts && n_weights == 22, ENERF_EINVAL, "feature_net: expected 22 weight pointers, got %d", n_weights);
@@ -173,6 +173,11 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
     TcConvLayer L{0, 1, KH, cin, cout, TC_PLAIN, relu};
     return tc_conv_launch(L, in, S, h, w, wp, b, nullptr, o, nullptr, cout, 0, stream);
   };
+  // part 0: everything; 1: trunk (conv0.0 .. toplayer -> feat_l0); 2: pyramid tail (laterals + smooth
+  // convs -> feat_l1, feat_l2; reads the trunk's c0 / c1 / feat_l0 from the same workspace).  The split
+  // lets the host run the tail on a second stream next to the level-0 cost-volume chain.
+  ENERF_REQUIRE(part >= 0 && part <= 2, ENERF_EINVAL, "feature_net: part %d", part);
+  if (part != 2) {
   RUN(launch_conv<Conv00>("feature_net.conv0.0", src_inps, wts[0], wts[1], ws.c0a, nullptr, S, H, W, 8, 0, stream));
   if (tensor_cores) {
     RUN(tc("feature_net.conv0.1", 3, 8, 8, 1, ws.c0a, H, W, wts[2], wts[3], ws.c0));
@@ -203,6 +208,8 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
     RUN(launch_conv<Conv21>("feature_net.conv2.1", ws.c2a, wts[10], wts[11], ws.c2, nullptr, S, H4, W4, 32, 0, stream));
     RUN(launch_conv<Top>("feature_net.toplayer", ws.c2, wts[12], wts[13], feat_l0, nullptr, S, H4, W4, 32, 0, stream));
   }
+  }  // trunk
+  if (part == 1) return ENERF_OK;
   {
     const long long total = (long long)S * H2 * W2 * 4;
     const int blocks = (int)((total + 255) / 256);

@@ -42,6 +42,11 @@ class Network(nn.Module):
         # "tf32": MLP contractions on tcgen05 tensor cores (TF32 operands, fp32 accumulate) where the
         # tensor-core kernel is built for the configuration; "fp32": FP32-pipe kernels everywhere.
         self.precision = os.environ.get("ENERF_B200_PRECISION", "tf32")
+        # two-stream schedule: the FeatureNet pyramid tail (laterals + smooth convs -> level_1/level_2
+        # features, only needed from the level-1 cost volume on) runs on a side stream concurrently
+        # with the level-0 chain (cost volume -> MinCostRegNet -> depth regression)
+        self.overlap = os.environ.get("ENERF_B200_OVERLAP", "1") != "0"
+        self._side = None
         # rows [r0, r1) of the render frame to generate rays for when the batch carries no rays_{i}
         # (None = the full frame); set by the ray-sharding renderer (enerf_b200/dist.py)
         self.ray_rows = None
@@ -147,7 +152,24 @@ class Network(nn.Module):
         ws = self._scratch("feat_ws", capi.feature_net_workspace_bytes(S, H, W) // 4, dev)
         self._mark("camera_setup")
         tcs = self.precision == "tf32"
-        capi.feature_net(pk["feature"], src, feats[0], feats[1], feats[2], ws, tensor_cores=tcs)
+        fork = self.overlap and not self.profile and len(levels) > 1
+        tail_done = None
+        if fork:
+            main = torch.cuda.current_stream()
+            if self._side is None or self._side.device != dev:
+                self._side = torch.cuda.Stream(device=dev)
+            capi.feature_net(pk["feature"], src, feats[0], feats[1], feats[2], ws, tensor_cores=tcs, part=1)
+            trunk_done = torch.cuda.Event()
+            trunk_done.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(trunk_done)
+                capi.feature_net(pk["feature"], src, feats[0], feats[1], feats[2], ws, tensor_cores=tcs, part=2)
+                tail_done = torch.cuda.Event()
+                tail_done.record(self._side)
+            for tns in (feats[1], feats[2], ws, src):
+                tns.record_stream(self._side)
+        else:
+            capi.feature_net(pk["feature"], src, feats[0], feats[1], feats[2], ws, tensor_cores=tcs)
         self._mark("feature_net")
 
         ret = {}
@@ -160,6 +182,9 @@ class Network(nn.Module):
                 raise ValueError(f"level {i}: volume {D}x{h}x{w} must be divisible by {div} (U-Net skip connections)")
             if i > 0 and not lv.prev_depth_inv:
                 raise NotImplementedError("cascade needs depth_inv on the previous level (reference: utils.py:129-130)")
+            if i > 0 and tail_done is not None:     # join: level >= 1 reads the pyramid features
+                torch.cuda.current_stream().wait_event(tail_done)
+                tail_done = None
             feat = feats[i]
             ends = torch.empty((2, h, w), **f32)
             nf_new = torch.empty((2, h, w), **f32)
@@ -185,6 +210,9 @@ class Network(nn.Module):
                 raise NotImplementedError("render_scale != im_ibr_scale (feature up-sampling in render_rays, network.py:30-32) "
                                           "is not used by any shipped config and is not implemented")
             Hr, Wr = int(H * lv.render_scale), int(W * lv.render_scale)
+            if tail_done is not None and lv.im_feat_level > 0:
+                torch.cuda.current_stream().wait_event(tail_done)
+                tail_done = None
             imf = feats[lv.im_feat_level]
             if imf.shape[1] != Hr or imf.shape[2] != Wr or imf.shape[3] != lv.feat_ch:
                 raise ValueError(f"level {i}: image features {tuple(imf.shape)} do not match render size {Hr}x{Wr}x{lv.feat_ch}")
@@ -217,4 +245,6 @@ class Network(nn.Module):
             self._mark(f"render_rays_{i}")
             ret.update({f"rgb_level{i}": rgb[None], f"depth_level{i}": dmap[None], f"weights_level{i}": wts[None],
                         f"depth_mvs_level{i}": mvs[None], f"std_level{i}": std[None]})
+        if tail_done is not None:                   # always join the side stream before returning
+            torch.cuda.current_stream().wait_event(tail_done)
         return ret

@@ -86,11 +86,14 @@ ENERF_API int enerf_generate_rays(const float* tar_ext /*4,4*/, const float* tar
  * toplayer, smooth1, smooth0) runs as a tcgen05 implicit GEMM (TF32 operands) and takes its w in
  * the enerf_tc_conv stage layout (packing.pack_tc_conv); conv0.0 (cin 3) and the fused laterals
  * keep the [tap][cin][cout] fp32 layout and kernels.
+ * part: 0 = whole net; 1 = trunk only (conv0.0..toplayer, writes feat_l0); 2 = pyramid tail only
+ * (laterals + smooth convs, writes feat_l1 / feat_l2 from the trunk's workspace tensors) -- the
+ * host runs part 2 on a second stream concurrently with the level-0 cost-volume chain.
  */
 ENERF_API size_t enerf_feature_net_workspace_bytes(int n_views, int H, int W);
 ENERF_API int enerf_feature_net(const float* const* weights, int n_weights, const float* src_inps, int n_views,
                       int H, int W, float* feat_l0, float* feat_l1, float* feat_l2, void* workspace,
-                      size_t workspace_bytes, int tensor_cores, void* stream);
+                      size_t workspace_bytes, int tensor_cores, int part, void* stream);
 
 /* cat(im_feat, unpreprocess(src_inps)) of render_rays (network.py:28-34, utils.py:605-612):
  * out (S,Hr,Wr,Cpad) with channels [0,C) = feat (must already be at Hr x Wr), [C,C+3) = rgb*0.5+0.5
