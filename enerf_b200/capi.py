@@ -39,6 +39,9 @@ _SIGS = {
     "enerf_depth_regress": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "enerf_render_rays": (_i, [_vp, _i, ctypes.POINTER(_vp), _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i,
                                _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "enerf_mask_compact_workspace_bytes": (_sz, [_i]),
+    "enerf_mask_compact": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "enerf_scatter_rows": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "enerf_render_rays_tc": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i,
                                   _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "enerf_tc_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
@@ -214,3 +217,22 @@ def render_rays_debug(buf):
 
 def generate_rays(tar_ext, tar_ixt, scale, W, row0, n_rows, rays):
     _check(lib().enerf_generate_rays(ptr(tar_ext), ptr(tar_ixt), float(scale), W, row0, n_rows, ptr(rays), stream()), "enerf_generate_rays")
+
+
+def mask_compact(mask, rays, idx_out, rays_out, count_out, workspace):
+    """mask: contiguous CUDA tensor with one element per ray (any integer/bool dtype)."""
+    if not mask.is_cuda or not mask.is_contiguous():
+        raise ValueError("mask must be a contiguous CUDA tensor")
+    n = rays.shape[0]
+    _check(lib().enerf_mask_compact(mask.data_ptr(), mask.element_size(), ptr(rays), n, idx_out.data_ptr(), ptr(rays_out),
+                                    count_out.data_ptr(), workspace.data_ptr(), workspace.numel() * workspace.element_size(), stream()),
+           "enerf_mask_compact", launches=3)
+
+
+def mask_compact_workspace_bytes(n):
+    return lib().enerf_mask_compact_workspace_bytes(n)
+
+
+def scatter_rows(src, idx, m, dst):
+    C = dst.shape[-1]
+    _check(lib().enerf_scatter_rows(ptr(src) if m else None, idx.data_ptr() if m else None, m, C, ptr(dst), stream()), "enerf_scatter_rows")

@@ -46,6 +46,9 @@ class Network(nn.Module):
         # features, only needed from the level-1 cost volume on) runs on a side stream concurrently
         # with the level-0 chain (cost volume -> MinCostRegNet -> depth regression)
         self.overlap = os.environ.get("ENERF_B200_OVERLAP", "1") != "0"
+        # network_human.py behaviour (render only rays inside batch['mask_at_box'] at the last level);
+        # enerf_b200/network_human.py switches it on
+        self.masked = False
         self._side = None
         # rows [r0, r1) of the render frame to generate rays for when the batch carries no rays_{i}
         # (None = the full frame); set by the ray-sharding renderer (enerf_b200/dist.py)
@@ -226,6 +229,20 @@ class Network(nn.Module):
                 rays = torch.empty(((r1 - r0) * Wr, 8), **f32)
                 capi.generate_rays(batch["tar_ext"][b].float().contiguous(), batch["tar_ixt"][b].float().contiguous(),
                                    lv.render_scale, Wr, r0, r1 - r0, rays)
+            n_full = rays.shape[0]
+            use_mask = self.masked and "mask_at_box" in batch and i == len(levels) - 1
+            if use_mask:   # rays = rays[mask_at_box]  (network_human.py:90-92), order-preserving, on device
+                mask = batch["mask_at_box"][b].reshape(-1).contiguous()
+                if mask.numel() != n_full:
+                    raise ValueError(f"mask_at_box has {mask.numel()} elements, the level renders {n_full} rays")
+                midx = torch.empty(n_full, device=dev, dtype=torch.int32)
+                rays_c = torch.empty((n_full, 8), **f32)
+                cnt = torch.empty(1, device=dev, dtype=torch.int32)
+                mws = self._scratch("mask_ws", capi.mask_compact_workspace_bytes(n_full) // 4 + 1, dev)
+                capi.mask_compact(mask, rays, midx, rays_c, cnt, mws)
+                # the output shapes depend on the count: one D2H read, as the reference's boolean indexing implies
+                n_sel = int(cnt.item())
+                rays = rays_c[:n_sel]
             N = rays.shape[0]
             views = (self.output_views or {}).get(i)
             if views is not None:   # write straight into the caller's (gather) buffer
@@ -236,13 +253,20 @@ class Network(nn.Module):
                 rgb = torch.empty((N, 3), **f32)
                 dmap = torch.empty((N,), **f32)
                 wts = torch.empty((N, lv.num_samples), **f32)
-            if self.precision == "tf32" and capi.tc_ray_kernel_supports(lv.feat_ch, S, lv.num_samples):
+            if N == 0:
+                pass
+            elif self.precision == "tf32" and capi.tc_ray_kernel_supports(lv.feat_ch, S, lv.num_samples):
                 capi.render_rays_tc(cam, i, pk[f"nerf_tc{i}"], rays, depth, std, nf, vol, img, lv.feat_ch, lv.num_samples,
                                     lv.depth_inv, bool(cfg.enerf.white_bkgd), bool(cfg.enerf.viewdir_agg), rgb, dmap, wts)
             else:
                 capi.render_rays(cam, i, pk[f"nerf{i}"], rays, depth, std, nf, vol, img, lv.feat_ch, lv.num_samples, lv.depth_inv,
                                  bool(cfg.enerf.white_bkgd), bool(cfg.enerf.viewdir_agg), rgb, dmap, wts)
             self._mark(f"render_rays_{i}")
+            if use_mask:   # rgb scattered into a zero image, depth / weights stay compact (network_human.py:102-106)
+                rgb_full = torch.zeros((n_full, 3), **f32)
+                if N > 1:
+                    capi.scatter_rows(rgb, midx, N, rgb_full)
+                rgb = rgb_full
             ret.update({f"rgb_level{i}": rgb[None], f"depth_level{i}": dmap[None], f"weights_level{i}": wts[None],
                         f"depth_mvs_level{i}": mvs[None], f"std_level{i}": std[None]})
         if tail_done is not None:                   # always join the side stream before returning

@@ -99,3 +99,14 @@ def psnr(a, b):
     """10*log10(1/MSE), data_range 1 (lib/evaluators/enerf.py:71 uses skimage psnr, data_range=1)."""
     mse = torch.mean((a.double() - b.double()) ** 2).item()
     return float("inf") if mse == 0 else 10.0 * math.log10(1.0 / mse)
+
+
+def make_mask_at_box(H, W, seed=9):
+    """Synthetic `mask_at_box` (1,H,W) int32 like zjumocap/enerf_interactive.py:192: a centred box with
+    seeded holes, so that compaction sees both long runs and isolated pixels."""
+    g = torch.Generator().manual_seed(seed)
+    m = torch.zeros(H, W, dtype=torch.int32)
+    m[H // 5: H - H // 6, W // 4: W - W // 5] = 1
+    m[torch.rand(H, W, generator=g) < 0.07] = 0
+    m[0, :3] = 1
+    return m[None]

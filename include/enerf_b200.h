@@ -161,6 +161,18 @@ ENERF_API int enerf_render_rays(const EnerfCam* cam, int level, const float* con
                       int num_samples, int depth_inv, int white_bkgd, int viewdir_agg, float* out_rgb,
                       float* out_depth, float* out_weights, void* stream);
 
+/* Masked-ray path (network_human.py:90-107).
+ * enerf_mask_compact: order-preserving compaction of the rays whose mask element is non-zero
+ *   (mask: n elements of elem_size bytes -- uint8/bool, int32, int64 ...): idx_out[i] = original ray
+ *   index of the i-th kept ray, rays_out[i] = rays[idx_out[i]], *count_out = number kept (device int).
+ *   == `rays[mask_at_box]` (network_human.py:92).  n <= 4096*1024.
+ * enerf_scatter_rows: dst[idx[i]][0..C) = src[i][0..C) for i < m  == `rgb[mask_at_box] = ...` (:105);
+ *   the caller zero-fills dst. */
+ENERF_API size_t enerf_mask_compact_workspace_bytes(int n);
+ENERF_API int enerf_mask_compact(const void* mask, int elem_size, const float* rays, int n, int* idx_out, float* rays_out,
+                                 int* count_out, void* workspace, size_t workspace_bytes, void* stream);
+ENERF_API int enerf_scatter_rows(const float* src, const int* idx, int m, int C, float* dst, void* stream);
+
 /* Tensor-core variant of enerf_render_rays (same stage, same arguments, same outputs): the MLP
  * contractions run as tcgen05.mma kind::tf32 with accumulators in TMEM, 128 sample points per CTA.
  * feat_ch == 8, n_views in [2,4], num_samples in {1,2,4,8}.  wblob = one packed device buffer of

@@ -338,8 +338,11 @@ def render_rays(sd, cfg, level, rays, batch, im_feat, vol, stash=None):
     return raw2outputs(raw, z, cfg.enerf.white_bkgd)
 
 
-def forward(sd, cfg, batch, intermediates=False):
+def forward(sd, cfg, batch, intermediates=False, human=False):
     """Network.forward, network.py:76-113 (chunking by cfg.enerf.chunk_size as :45-55).
+    ``human=True`` follows network_human.py:60-119 instead: identical except that, at the last level,
+    only the rays inside ``batch['mask_at_box']`` are rendered (:90-92) and rgb is scattered back
+    into a zero image (:102-106); depth / weights stay compact.
     Returns the reference's output dict; with ``intermediates`` also a dict of per-stage tensors."""
     c = cfg.enerf.cas_config
     B, S, _, H, W = batch["src_inps"].shape
@@ -358,6 +361,10 @@ def forward(sd, cfg, batch, intermediates=False):
             continue
         rays = build_rays(depth, std, batch, cfg, near_far, i)
         mid[f"rays12_{i}"] = rays
+        masked = human and "mask_at_box" in batch and i == c.num - 1
+        if masked:
+            mask = batch["mask_at_box"].bool().reshape(1, -1)
+            rays = rays[mask][None]
         chunk = int(cfg.enerf.chunk_size)
         parts, stash = [], ({} if intermediates else None)
         for j in range(0, rays.shape[1], chunk):
@@ -366,6 +373,11 @@ def forward(sd, cfg, batch, intermediates=False):
         out = {k: torch.cat([p[k] for p in parts], dim=1) for k in parts[0]}
         if stash:
             mid.update({f"{k}_{i}": v for k, v in stash.items()})
+        if masked:
+            rgb = torch.zeros(1, mask.shape[1], 3)
+            if mask.sum() > 1:
+                rgb[mask] = out["rgb"][0]
+            out["rgb"] = rgb
         out["depth_mvs"] = 1.0 / depth if c.depth_inv[i] else depth   # network.py:105-108
         out["std"] = std
         ret.update({f"{k}_level{i}": v for k, v in out.items()})

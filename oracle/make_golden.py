@@ -31,6 +31,10 @@ CASES = {
     "c2_headline_small": dict(yaml="configs/enerf/dtu_pretrain.yaml",
                               opts=["enerf.cas_config.volume_planes", "16,8", "enerf.cas_config.render_if", "False,True"],
                               kind="cascade", over=dict(volume_planes=[16, 8], render_if=[False, True]), H=96, W=64, S=4),
+    # network_human (ZJU-MoCap / interactive variant): rays masked by mask_at_box at the last level
+    "c4_human_small": dict(yaml="configs/enerf/dtu_pretrain.yaml",
+                           opts=["enerf.cas_config.volume_planes", "8,8", "enerf.cas_config.render_if", "False,True"],
+                           kind="cascade", over=dict(volume_planes=[8, 8], render_if=[False, True]), H=64, W=96, S=2, human=True),
 }
 
 
@@ -44,10 +48,16 @@ def run_case(name):
     cfg, mods = load_reference(case["yaml"], case["opts"])
     utils = mods["utils"]
     torch.manual_seed(0)
-    net = mods["network"].Network().eval()
+    if case.get("human"):
+        import lib.networks.enerf.network_human as network_human
+        net = network_human.Network().eval()
+    else:
+        net = mods["network"].Network().eval()
     synthetic.randomize_bn_(net, seed=1)
     my_cfg = (bcfg.nocascade_cfg if case["kind"] == "nocascade" else bcfg.make_cfg)(**case["over"])
     batch = synthetic.make_batch(case["H"], case["W"], case["S"], my_cfg, seed=2)
+    if case.get("human"):
+        batch["mask_at_box"] = synthetic.make_mask_at_box(case["H"], case["W"])
     # cross-check the ray generator against the reference's own (lib/datasets/enerf_utils.py:25-71)
     import numpy as np
     for i in range(cfg.enerf.cas_config.num):
@@ -74,7 +84,7 @@ def run_case(name):
             if i == cfg.enerf.cas_config.num - 1:
                 mid[f"feat_volume_{i}"] = vol
     fixture = {
-        "case": name, "cfg_kind": case["kind"], "cfg_over": case["over"], "H": case["H"], "W": case["W"], "S": case["S"],
+        "case": name, "human": bool(case.get("human")), "cfg_kind": case["kind"], "cfg_over": case["over"], "H": case["H"], "W": case["W"], "S": case["S"],
         "state_dict": {k: v.clone() for k, v in net.state_dict().items()},
         "batch": batch,
         "out": {k: v.clone() for k, v in out.items()},

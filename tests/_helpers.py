@@ -7,7 +7,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["c1_nocascade", "c2_small_cascade", "c2_headline_small"]
+GOLDEN_CASES = ["c1_nocascade", "c2_small_cascade", "c2_headline_small", "c4_human_small"]
 
 
 def load_golden(name):

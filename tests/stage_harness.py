@@ -43,13 +43,13 @@ def make_case(H, W, S, cfg, seed=2):
     return sd, batch
 
 
-def stage_report(sd, cfg, batch, oracle_out=None, oracle_mid=None, precision="fp32"):
+def stage_report(sd, cfg, batch, oracle_out=None, oracle_mid=None, precision="fp32", human=False):
     """Returns {stage: err-dict}.  Needs a CUDA device."""
     from enerf_b200.network import Network
     bcfg.set_cfg(cfg)
     if oracle_out is None:
         with torch.no_grad():
-            oracle_out, oracle_mid = O.forward(sd, cfg, batch, intermediates=True)
+            oracle_out, oracle_mid = O.forward(sd, cfg, batch, intermediates=True, human=human)
     mid = oracle_mid
     levels = snapshot(cfg)
     dev = torch.device("cuda")
@@ -134,8 +134,8 @@ def stage_report(sd, cfg, batch, oracle_out=None, oracle_mid=None, precision="fp
         o_depth, o_std, o_nf = (mid[f"depth_{i}"][0].contiguous().cuda(), mid[f"std_{i}"][0].contiguous().cuda(),
                                 mid[f"near_far_{i}"][0].contiguous().cuda())
         prev = (o_depth, o_std, o_nf)
-        if not lv.render_if:
-            continue
+        if not lv.render_if or (human and i == len(levels) - 1):
+            continue          # (the masked level is covered end to end below)
         # fused ray stage fed with oracle depth/std/near_far/volume/features
         Hr, Wr = int(H * lv.render_scale), int(W * lv.render_scale)
         imf = nhwc(mid[f"feat_level_{lv.im_feat_level}"][0])
@@ -162,7 +162,11 @@ def stage_report(sd, cfg, batch, oracle_out=None, oracle_mid=None, precision="fp
             rep[f"render_rays_tc.weights_{i}"] = err(w2, oracle_out[f"weights_level{i}"][0])
 
     # end to end through the drop-in Network
-    net = Network()
+    if human:
+        from enerf_b200.network_human import Network as HumanNetwork
+        net = HumanNetwork()
+    else:
+        net = Network()
     net.load_state_dict(sd, strict=True)
     net = net.cuda().eval()
     net.precision = precision
@@ -195,7 +199,7 @@ if __name__ == "__main__":
         rep, _ = stage_report(sd, cfg, batch)
     else:
         fx = load_golden(arg)
-        rep, _ = stage_report(fx["state_dict"], fx["cfg"], fx["batch"])
+        rep, _ = stage_report(fx["state_dict"], fx["cfg"], fx["batch"], human=fx.get("human", False))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"stage_report_{arg}.json"), "w") as f:
         json.dump(rep, f, indent=1)

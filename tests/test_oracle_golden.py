@@ -13,7 +13,7 @@ TOL = dict(rgb=2e-5, depth=2e-5, weights=2e-5, depth_mvs=2e-5, std=2e-5)
 def test_oracle_matches_reference_outputs(golden):
     torch.set_num_threads(8)
     with torch.no_grad():
-        out, mid = O.forward(golden["state_dict"], golden["cfg"], golden["batch"], intermediates=True)
+        out, mid = O.forward(golden["state_dict"], golden["cfg"], golden["batch"], intermediates=True, human=golden.get("human", False))
     assert set(out) == set(golden["out"])
     for k, ref in golden["out"].items():
         err = (out[k] - ref).abs().max().item()

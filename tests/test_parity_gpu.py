@@ -50,7 +50,7 @@ def harness():
 
 
 def test_stages_and_e2e_vs_oracle_on_golden_inputs(harness, golden):
-    rep, out = harness.stage_report(golden["state_dict"], golden["cfg"], golden["batch"])
+    rep, out = harness.stage_report(golden["state_dict"], golden["cfg"], golden["batch"], human=golden.get("human", False))
     _check_report(rep)
     # (b) directly against what the unmodified reference produced
     for k, ref in golden["out"].items():
@@ -140,7 +140,7 @@ def test_tcgen05_selftest_gemm(K, N):
 def test_e2e_tf32_tensor_core_path(harness, golden):
     """Default precision: the ray-stage MLP runs on tcgen05 (TF32 operands).  Same oracle, wider
     element-wise bound, same |dPSNR| < 0.01 dB criterion."""
-    rep, out = harness.stage_report(golden["state_dict"], golden["cfg"], golden["batch"], precision="tf32")
+    rep, out = harness.stage_report(golden["state_dict"], golden["cfg"], golden["batch"], precision="tf32", human=golden.get("human", False))
     _check_report({k: v for k, v in rep.items() if k.startswith("e2e.")}, E2E_TOL_TF32)
 
 
@@ -273,3 +273,37 @@ def test_forward_without_rays_graph_and_streamed(harness):
     for o in got:
         for k in gen:
             assert torch.equal(o[k], gen[k].cpu()), k
+
+
+def test_mask_compaction_edge_cases():
+    """Order-preserving compaction == rays[mask] for empty / full / single / ragged masks and every
+    mask dtype the data layer produces (bool, uint8, int32, int64)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from enerf_b200 import capi
+    g = torch.Generator().manual_seed(0)
+    for n in (1, 31, 1024, 1025, 70001):
+        rays = torch.randn(n, 8, generator=g).cuda()
+        for kind in ("empty", "full", "single", "random"):
+            m = {"empty": torch.zeros(n), "full": torch.ones(n), "single": torch.zeros(n), "random": (torch.rand(n, generator=g) < 0.3).float()}[kind]
+            if kind == "single":
+                m[n // 2] = 1
+            for dt in (torch.bool, torch.uint8, torch.int32, torch.int64):
+                mask = m.to(dt).cuda()
+                idx = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+                out = torch.zeros(n, 8, device="cuda")
+                cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+                ws = torch.zeros(capi.mask_compact_workspace_bytes(n) // 4 + 1, device="cuda")
+                capi.mask_compact(mask, rays, idx, out, cnt, ws)
+                k = int(cnt.item())
+                ref = torch.nonzero(m.bool()).reshape(-1)
+                assert k == ref.numel(), (n, kind, dt)
+                assert torch.equal(idx[:k].cpu().long(), ref)
+                assert torch.equal(out[:k].cpu(), rays.cpu()[m.bool()])
+                if k:
+                    dst = torch.zeros(n, 3, device="cuda")
+                    src = torch.randn(k, 3, generator=g).cuda()
+                    capi.scatter_rows(src, idx, k, dst)
+                    exp = torch.zeros(n, 3)
+                    exp[m.bool()] = src.cpu()
+                    assert torch.equal(dst.cpu(), exp)
