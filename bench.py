@@ -355,9 +355,17 @@ def main():
     roofline = ({"bound": "tensor", "achieved": ach_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach_tf / peaks["bf16_tflops"]}
                 if compute_bound else
                 {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"]})
-    roofline.update({"kernel": dom, "ms": dom_ms, "traffic": None, "peak_src": peaks["src"],
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")    # dram__bytes_{read,write}.sum per launch, ncu --set full
+    if os.path.exists(tpath) and dom.startswith("render_rays"):
+        tj = json.load(open(tpath)).get("render_rays_tc")
+        if tj:
+            traffic = {"dram_bytes_per_launch": (tj["dram_read_MB"] + tj["dram_write_MB"]) * 1e6, "algorithmic_bytes": work[dom]["bytes"],
+                       "src": "profiles/r1_ncu_full_final.md"}
+    roofline.update({"kernel": dom, "ms": dom_ms, "traffic": traffic, "peak_src": peaks["src"],
                      "note": "algorithmic FLOPs (reference formulation, BASELINE.md section 2) / CUDA-event time of the stage; "
-                             "this stage runs on the FP32 pipe, the tensor peak is the contract's denominator",
+                             "tensor peak = measured bf16 burst (the contract's denominator); the kernels use TF32 (half that rate) "
+                             "and M=128,K=8 MMAs whose shared-memory operand stream floors at ~89 cycles (profiles/r1_mma_microbench.md)",
                      "fp32_pipe_frac": ach_tf / 72.0 if compute_bound else None})
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
