@@ -194,6 +194,8 @@ def main():
     ap.add_argument("--mode", default="frames", choices=["frames", "rays"], help="N>1: frame-parallel sequence (default) or intra-frame ray-band sharding")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="replay the forward as a CUDA graph (0 = eager launches)")
+    ap.add_argument("--inflight", type=int, default=3, help="frames rendered concurrently per GPU (one CUDA graph + stream each); "
+                    "1 = strictly one frame at a time (latency mode)")
     ap.add_argument("--host-rays", type=int, default=0, help="1: ship rays_1 from the host like the reference's data layer (default: generate on device)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -244,15 +246,43 @@ def main():
     with torch.no_grad():
         net(local)
     launches_per_forward = capi.LAUNCHES - l0
-    graphed = GraphedNetwork(net, local) if args.graph else None
+    # `inflight` frames are rendered concurrently (sequence rendering): replica j has its own captured
+    # graph, stream, static inputs and gather buffer; a step = one frame on every replica
+    nfl = max(1, args.inflight) if args.graph else 1
+    main_stream = torch.cuda.current_stream()
+    replicas = []
+    for j in range(nfl):
+        rj = renderer if j == 0 else (edist.RayShardedRenderer(None, 1, ns, W, H, rank, world, device=dev) if (world > 1 and args.mode == "rays")
+                                      else edist.FrameParallelRenderer(None, n_rays, ns, rank, world, device=dev))
+        net.output_views = {1: rj.local_views()}
+        st = torch.cuda.Stream(device=dev) if j > 0 else main_stream
+        with torch.cuda.stream(st):
+            g = GraphedNetwork(net, local) if args.graph else None
+        replicas.append((rj, st, g, torch.cuda.Event(), torch.cuda.Event()))
+    torch.cuda.synchronize()
 
     def step():
+        """one frame per replica, concurrently; all joined back on the main stream"""
         with torch.no_grad():
-            if graphed is not None:
-                graphed.replay()
-            else:
-                net(local)
-            return renderer.gather()
+            if nfl == 1:
+                if replicas[0][2] is not None:
+                    replicas[0][2].replay()
+                else:
+                    net(local)
+                return replicas[0][0].gather()
+            fork = replicas[0][3]
+            fork.record(main_stream)
+            for rj, st, g, _, done in replicas:
+                if st is not main_stream:
+                    st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    g.replay()
+                    out_j = rj.gather()
+                    if st is not main_stream:
+                        done.record(st)
+            for rj, st, g, _, done in replicas[1:]:
+                main_stream.wait_event(done)
+            return out_j
 
     def sync_all():
         torch.cuda.synchronize()
@@ -275,23 +305,35 @@ def main():
             b.record()
         sync_all()
     times = [a.elapsed_time(b) for a, b in ev]
-    launches = launches_per_forward
+    launches = launches_per_forward * nfl
     t_local = sum(times)
     t = torch.tensor([t_local], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = t.item()
-    frames_per_step = world if (world > 1 and args.mode == "frames") else 1
+    frames_per_step = nfl * (world if (world > 1 and args.mode == "frames") else 1)
     ms_per_step = total_ms / args.steps
     value = frames_per_step * 1000.0 / ms_per_step
     times.sort()
+    # single-frame latency (one replica, nothing else in flight) for reference
+    lat_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    lat_ev[0].record()
+    for _ in range(10):
+        with torch.no_grad():
+            if replicas[0][2] is not None:
+                replicas[0][2].replay()
+            else:
+                net(local)
+    lat_ev[1].record()
+    sync_all()
+    latency_ms = lat_ev[0].elapsed_time(lat_ev[1]) / 10
     net.output_views, net.ray_rows = None, None
 
     # ---- end to end through the public API with HOST buffers: every frame pays its own H2D (pinned)
     #      and D2H (pinned); StreamedRenderer overlaps copy-in / forward / copy-out of adjacent frames ----
     host_in = {k: v.clone().pin_memory() for k, v in batch.items()}
     h2d = sum(v.numel() * v.element_size() for v in host_in.values())
-    streamed = StreamedRenderer(net, host_in, dev, depth=2, use_graph=bool(args.graph))
+    streamed = StreamedRenderer(net, host_in, dev, depth=max(2, args.inflight), use_graph=bool(args.graph))
     d2h_box = {}
 
     def on_frame(i, host_out):
@@ -390,13 +432,13 @@ def main():
         "vs_baseline": value / PUBLISHED_FPS, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{H}x{W}, {S} src views, {PLANES[0]}+{PLANES[1]} planes, 2-level cascade, render_if [F,T] (BASELINE.json configs[1])",
                    "frames_per_step": frames_per_step, "parallelism": (f"{args.mode}x{world}" if world > 1 else "single"),
-                   "cuda_graph": bool(args.graph), "rays": "host (batch rays_1)" if args.host_rays else "generated on device from tar_ext/tar_ixt",
+                   "cuda_graph": bool(args.graph), "frames_in_flight_per_gpu": nfl, "single_frame_latency_ms": latency_ms, "rays": "host (batch rays_1)" if args.host_rays else "generated on device from tar_ext/tar_ixt",
                    "l2": "256 MiB buffer written between timed iterations (L2 flush)", "timing": "CUDA events per step, max over ranks",
                    "p50_ms": times[len(times) // 2], "p95_ms": times[min(len(times) - 1, int(0.95 * len(times)))],
                    "vs_baseline_note": "published 21.78 FPS is RTX 3090 + trained weights (README.md:121)"},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": te[0].item(),
-                "api": "enerf_b200.pipeline.StreamedRenderer.render (3 streams, depth 2, CUDA-graph forward)",
+                "api": f"enerf_b200.pipeline.StreamedRenderer.render (copy-in / compute / copy-out streams, {max(2, args.inflight)} frames in flight, CUDA-graph forward)",
                 "sync_loop_value": e2e_sync_fps, "sync_loop_note": "run.py:57-76 style: copy in, Network.forward, copy out, synchronize"},
         "gpu_launches": launches,
         "roofline": roofline,

@@ -4,9 +4,10 @@
 * ``GraphedNetwork``  -- captures one ``Network.forward`` for a fixed batch signature into a CUDA
   graph (static input/output buffers) and replays it: one ``cudaGraphLaunch`` instead of ~40 kernel
   launches + the Python between them.
-* ``StreamedRenderer`` -- sequence rendering from HOST batches: H2D of frame i+1, the forward of
-  frame i and D2H of frame i-1 run on three streams, so the end-to-end rate is bounded by the
-  slowest of the three instead of their sum.  Every frame still pays its own copies.
+* ``StreamedRenderer`` -- sequence rendering from HOST batches: the H2D copy, the forward and the D2H
+  copy of adjacent frames run on separate streams (and, with graphs, the forwards of ``depth`` frames
+  overlap each other), so the end-to-end rate is bounded by the slowest resource instead of the sum.
+  Every frame still pays its own copies.
 
 Both produce exactly what ``Network.forward`` produces (same kernels, same order).
 """
@@ -52,15 +53,21 @@ class GraphedNetwork:
 class StreamedRenderer:
     """render(host_batches) -> list of dicts of pinned host tensors, one per input batch."""
 
-    def __init__(self, net, example_host_batch, device, depth=2, use_graph=True):
+    def __init__(self, net, example_host_batch, device, depth=3, use_graph=True):
+        """depth = frames in flight.  With CUDA graphs every slot replays on its OWN compute stream, so
+        the forwards of adjacent frames overlap as well (the coarse layers of one frame launch fewer CTAs
+        than the GPU has SMs); without graphs the slots share one compute stream (Network keeps per-call
+        scratch buffers)."""
         self.dev, self.depth = device, depth
-        self.copy_in, self.compute, self.copy_out = torch.cuda.Stream(device), torch.cuda.Stream(device), torch.cuda.Stream(device)
+        self.copy_in, self.copy_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        shared = torch.cuda.Stream(device)
         ex = {k: v.to(device) for k, v in example_host_batch.items() if torch.is_tensor(v)}
         self.slots = []
         for _ in range(depth):
-            with torch.cuda.stream(self.compute):
+            cs = torch.cuda.Stream(device) if use_graph else shared
+            with torch.cuda.stream(cs):
                 g = GraphedNetwork(net, ex) if use_graph else None
-            slot = {"g": g, "in": g.static_in if g else {k: v.clone() for k, v in ex.items()},
+            slot = {"g": g, "cs": cs, "in": g.static_in if g else {k: v.clone() for k, v in ex.items()},
                     "h2d": torch.cuda.Event(), "done": torch.cuda.Event(), "d2h": torch.cuda.Event(), "free": torch.cuda.Event(),
                     "host_out": None, "busy": False, "out": None}
             self.slots.append(slot)
@@ -73,12 +80,13 @@ class StreamedRenderer:
             for k, dst in slot["in"].items():
                 dst.copy_(host_batch[k], non_blocking=True)
             slot["h2d"].record(self.copy_in)
-        with torch.cuda.stream(self.compute), torch.no_grad():
-            self.compute.wait_event(slot["h2d"])
-            self.compute.wait_event(slot["d2h"])           # previous outputs of this slot have been copied out
+        cs = slot["cs"]
+        with torch.cuda.stream(cs), torch.no_grad():
+            cs.wait_event(slot["h2d"])
+            cs.wait_event(slot["d2h"])                     # previous outputs of this slot have been copied out
             out = slot["g"].replay() if slot["g"] else self.net(slot["in"])
-            slot["done"].record(self.compute)
-            slot["free"].record(self.compute)
+            slot["done"].record(cs)
+            slot["free"].record(cs)
         if slot["host_out"] is None:
             slot["host_out"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
         with torch.cuda.stream(self.copy_out):

@@ -267,7 +267,7 @@ def test_forward_without_rays_graph_and_streamed(harness):
         assert torch.equal(out[k], gen[k]), k
     host = {k: v.cpu().pin_memory() for k, v in norays.items()}
     got = []
-    sr = StreamedRenderer(net, host, torch.device("cuda"), depth=2)
+    sr = StreamedRenderer(net, host, torch.device("cuda"), depth=3)
     sr.render([host] * 5, lambda i, o: got.append({k: v.clone() for k, v in o.items()}))
     assert len(got) == 5
     for o in got:
