@@ -42,6 +42,8 @@ _SIGS = {
     "enerf_mask_compact_workspace_bytes": (_sz, [_i]),
     "enerf_mask_compact": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "enerf_scatter_rows": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "enerf_psnr_accumulate": (_i, [_vp, _vp, _vp, _i, ctypes.c_longlong, _vp, _vp]),
+    "enerf_pack_rgb8": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "enerf_render_rays_tc": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i,
                                   _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "enerf_tc_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
@@ -236,3 +238,14 @@ def mask_compact_workspace_bytes(n):
 def scatter_rows(src, idx, m, dst):
     C = dst.shape[-1]
     _check(lib().enerf_scatter_rows(ptr(src) if m else None, idx.data_ptr() if m else None, m, C, ptr(dst), stream()), "enerf_scatter_rows")
+
+
+def psnr_accumulate(pred, gt, mask, acc):
+    """pred, gt (N,3) float CUDA; mask (N,) any integer/bool dtype or None; acc: 2 float64 (zeroed by the caller)."""
+    n = pred.numel() // 3
+    _check(lib().enerf_psnr_accumulate(ptr(pred), ptr(gt), mask.data_ptr() if mask is not None else None,
+                                       mask.element_size() if mask is not None else 0, n, acc.data_ptr(), stream()), "enerf_psnr_accumulate")
+
+
+def pack_rgb8(rgb, H, W, out, flip_vertical=False):
+    _check(lib().enerf_pack_rgb8(ptr(rgb), H, W, int(flip_vertical), out.data_ptr(), stream()), "enerf_pack_rgb8")

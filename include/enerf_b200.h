@@ -173,6 +173,16 @@ ENERF_API int enerf_mask_compact(const void* mask, int elem_size, const float* r
                                  int* count_out, void* workspace, size_t workspace_bytes, void* stream);
 ENERF_API int enerf_scatter_rows(const float* src, const int* idx, int m, int C, float* dst, void* stream);
 
+/* Device-side consumers of the rendered frame.
+ * enerf_psnr_accumulate: acc[0] += sum (pred-gt)^2 over the pixels whose mask element is non-zero
+ *   (mask == NULL: all pixels) x 3 channels, acc[1] += number of values; PSNR = 10 log10(acc[1]/acc[0])
+ *   (lib/evaluators/enerf.py:45-71, skimage psnr with data_range 1).  acc: 2 doubles, caller-zeroed.
+ * enerf_pack_rgb8: (H*W,3) float rgb -> (H,W,3) uint8 = trunc(clamp(x,0,1)*255), optional vertical
+ *   flip (gui_human.py:88-91). */
+ENERF_API int enerf_psnr_accumulate(const float* pred, const float* gt, const void* mask, int mask_elem_size,
+                                    long long n_pixels, double* acc, void* stream);
+ENERF_API int enerf_pack_rgb8(const float* rgb, int H, int W, int flip_vertical, unsigned char* out, void* stream);
+
 /* Tensor-core variant of enerf_render_rays (same stage, same arguments, same outputs): the MLP
  * contractions run as tcgen05.mma kind::tf32 with accumulators in TMEM, 128 sample points per CTA.
  * feat_ch == 8, n_views in [2,4], num_samples in {1,2,4,8}.  wblob = one packed device buffer of

@@ -307,3 +307,31 @@ def test_mask_compaction_edge_cases():
                     exp = torch.zeros(n, 3)
                     exp[m.bool()] = src.cpu()
                     assert torch.equal(dst.cpu(), exp)
+
+
+def test_device_psnr_and_rgb8_pack():
+    """enerf_psnr_accumulate == the evaluator's masked PSNR; enerf_pack_rgb8 == (img*255).to(uint8) (+flip)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import math
+    from enerf_b200 import capi
+    g = torch.Generator().manual_seed(4)
+    H, W = 48, 80
+    pred, gt = torch.rand(H * W, 3, generator=g), torch.rand(H * W, 3, generator=g)
+    msk = (torch.rand(H * W, generator=g) < 0.6)
+    for mask in (None, msk.to(torch.uint8), msk.to(torch.int32)):
+        acc = torch.zeros(2, dtype=torch.float64, device="cuda")
+        capi.psnr_accumulate(pred.cuda(), gt.cuda(), mask.cuda() if mask is not None else None, acc)
+        sse, cnt = acc.cpu().tolist()
+        sel = msk if mask is not None else torch.ones_like(msk)
+        ref_mse = ((pred[sel] - gt[sel]).double() ** 2).mean().item()
+        assert cnt == sel.sum().item() * 3
+        assert abs(10 * math.log10(cnt / sse) - 10 * math.log10(1.0 / ref_mse)) < 1e-6
+    rgb = (torch.rand(H * W, 3, generator=g) * 1.2 - 0.1)
+    for flip in (False, True):
+        out = torch.zeros(H, W, 3, dtype=torch.uint8, device="cuda")
+        capi.pack_rgb8(rgb.cuda(), H, W, out, flip_vertical=flip)
+        ref = (rgb.clamp(0, 1) * 255).to(torch.uint8).view(H, W, 3)
+        if flip:
+            ref = torch.flip(ref, (0,))
+        assert torch.equal(out.cpu(), ref)
