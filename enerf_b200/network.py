@@ -202,9 +202,12 @@ class Network(nn.Module):
             rws = self._scratch(f"reg_ws{i}", capi.cost_reg_workspace_bytes(deep, D, h, w) // 4, dev)
             capi.cost_reg(pk[f"reg{i}"], deep, var, vol, prob, rws, tensor_cores=tcs)
             self._mark(f"cost_reg_{i}")
+            lvl_views = (self.output_views or {}).get(i) or {}
             depth = torch.empty((h, w), **f32)
-            std = torch.empty((h, w), **f32)
-            mvs = torch.empty((h, w), **f32)
+            std = lvl_views["std"] if "std" in lvl_views else torch.empty((h, w), **f32)
+            mvs = lvl_views["depth_mvs"] if "depth_mvs" in lvl_views else torch.empty((h, w), **f32)
+            if std.shape != (h, w) or mvs.shape != (h, w):
+                raise ValueError("output_views std / depth_mvs shapes do not match the level's volume resolution")
             capi.depth_regress(prob, ends, lv.depth_inv, depth, std, mvs)
             self._mark(f"depth_regress_{i}")
             if not lv.render_if:
@@ -245,7 +248,7 @@ class Network(nn.Module):
                 rays = rays_c[:n_sel]
             N = rays.shape[0]
             views = (self.output_views or {}).get(i)
-            if views is not None:   # write straight into the caller's (gather) buffer
+            if views is not None and "rgb" in views:   # write straight into the caller's (gather) buffer
                 rgb, dmap, wts = views["rgb"], views["depth"], views["weights"]
                 if rgb.shape != (N, 3) or dmap.shape != (N,) or wts.shape != (N, lv.num_samples):
                     raise ValueError("output_views shapes do not match the ray batch")

@@ -19,8 +19,10 @@ def _signature(batch):
 
 
 class GraphedNetwork:
-    def __init__(self, net, example_batch, warmup=3):
-        """example_batch: CUDA tensors; defines the static signature."""
+    def __init__(self, net, example_batch, warmup=3, flat_outputs=False):
+        """example_batch: CUDA tensors; defines the static signature.
+        flat_outputs: every output tensor of the captured forward lives in ONE device buffer
+        (``self.flat_out``), so a consumer can fetch the whole result with a single copy."""
         self.net = net
         self.sig = _signature(example_batch)
         self.static_in = {k: v.clone() for k, v in example_batch.items() if torch.is_tensor(v)}
@@ -28,12 +30,27 @@ class GraphedNetwork:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(warmup):           # builds packed weights / scratch, sets kernel attributes
-                net(self.static_in)
+                probe = net(self.static_in)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self.flat_out, self.out_layout, saved_views = None, None, net.output_views
+        if flat_outputs and net.output_views is None and not getattr(net, "masked", False):
+            self.out_layout, off = {}, 0
+            for k, v in probe.items():
+                self.out_layout[k] = (off, tuple(v.shape))
+                off += (v.numel() + 63) // 64 * 64
+            self.flat_out = torch.empty(off, device=next(iter(probe.values())).device, dtype=torch.float32)
+            views = {}
+            for k, (o, shp) in self.out_layout.items():
+                name, lvl = k.rsplit("_level", 1)
+                views.setdefault(int(lvl), {})[name] = self.flat_out[o:o + int(torch.tensor(shp).prod())].view(shp[1:])
+            net.output_views = views
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph), torch.no_grad():
-            self.static_out = net(self.static_in)
+        try:
+            with torch.cuda.graph(self.graph), torch.no_grad():
+                self.static_out = net(self.static_in)
+        finally:
+            net.output_views = saved_views
 
     def load(self, batch, non_blocking=True):
         if _signature(batch) != self.sig:
@@ -66,10 +83,13 @@ class StreamedRenderer:
         for _ in range(depth):
             cs = torch.cuda.Stream(device) if use_graph else shared
             with torch.cuda.stream(cs):
-                g = GraphedNetwork(net, ex) if use_graph else None
+                g = GraphedNetwork(net, ex, flat_outputs=True) if use_graph else None
             slot = {"g": g, "cs": cs, "in": g.static_in if g else {k: v.clone() for k, v in ex.items()},
                     "h2d": torch.cuda.Event(), "done": torch.cuda.Event(), "d2h": torch.cuda.Event(), "free": torch.cuda.Event(),
-                    "host_out": None, "busy": False, "out": None}
+                    "host_out": None, "host_flat": None}
+            if g is not None and g.flat_out is not None:   # one pinned buffer mirrors the flat device buffer
+                slot["host_flat"] = torch.empty(g.flat_out.numel(), dtype=torch.float32).pin_memory()
+                slot["host_out"] = {k: slot["host_flat"][o:o + int(torch.tensor(shp).prod())].view(shp) for k, (o, shp) in g.out_layout.items()}
             self.slots.append(slot)
         self.net = net
         torch.cuda.synchronize(device)
@@ -87,15 +107,17 @@ class StreamedRenderer:
             out = slot["g"].replay() if slot["g"] else self.net(slot["in"])
             slot["done"].record(cs)
             slot["free"].record(cs)
-        if slot["host_out"] is None:
-            slot["host_out"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
         with torch.cuda.stream(self.copy_out):
             self.copy_out.wait_event(slot["done"])
-            for k, v in out.items():
-                v.record_stream(self.copy_out)
-                slot["host_out"][k].copy_(v, non_blocking=True)
+            if slot["host_flat"] is not None:              # the whole result in one D2H copy
+                slot["host_flat"].copy_(slot["g"].flat_out, non_blocking=True)
+            else:
+                if slot["host_out"] is None:
+                    slot["host_out"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+                for k, v in out.items():
+                    v.record_stream(self.copy_out)
+                    slot["host_out"][k].copy_(v, non_blocking=True)
             slot["d2h"].record(self.copy_out)
-        slot["out"], slot["busy"] = out, True
 
     def render(self, host_batches, on_frame=None):
         """Streams the batches through; ``on_frame(i, host_out)`` is called once frame i is on the host
