@@ -81,6 +81,15 @@ def nocascade_cfg(**cas_overrides):
     return make_cfg(**base)
 
 
+def composite_cfg(num_fg_layers=1, **cas_overrides):
+    """configs/enerf/enerf_outdoor/actor1.yaml:13-22 (network_composite: layered foreground + background)."""
+    base = dict(viewdir_agg=False, volume_planes=[32, 8], num_samples=[2, 1])
+    base.update(cas_overrides)
+    cfg = make_cfg(**base)
+    cfg.num_fg_layers = int(num_fg_layers)
+    return cfg
+
+
 def set_cfg(cfg):
     """Install a stand-alone cfg (ignored when the reference's lib.config is importable AND
     ``prefer_reference`` resolution finds it first; see get_cfg)."""

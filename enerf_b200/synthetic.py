@@ -95,6 +95,28 @@ def make_batch(H, W, S, cfg, seed=2, near_far=(2.0, 6.0), B=1):
     return batch
 
 
+def make_composite_batch(H, W, S, cfg, seed=2):
+    """``make_batch`` + the extra keys of lib/datasets/enerf_outdoor/enerf.py:183-190: one bbox (x,y,w,h;
+    w,h multiples of 32 as read_tar :161-162 pads them) and one [near, far] per foreground layer, the
+    background [near, far] last, and the background plates ``bg_src_inps``."""
+    L = int(cfg.num_fg_layers)
+    batch = make_batch(H, W, S, cfg, seed=seed)
+    g = torch.Generator().manual_seed(seed + 7)
+    batch["bg_src_inps"] = 2.0 * torch.rand((1, S, 3, H, W), generator=g) - 1.0
+    boxes, nfs = [], []
+    for l in range(L):
+        w = max(32, (W * 2 // 3) // 32 * 32) if l == 0 else 32
+        h = max(32, (H // 2) // 32 * 32)
+        x = min(W - w, 20 if l == 0 else 4)
+        y = min(H - h, 8 if l == 0 else 24)
+        boxes.append([x, y, w, h])
+        nfs.append([2.5 + 0.5 * l, 4.5 + 1.0 * l])
+    nfs.append([2.0, 6.0])
+    batch["bbox"] = torch.tensor([boxes], dtype=torch.float32)
+    batch["near_far"] = torch.tensor([nfs], dtype=torch.float32)
+    return batch
+
+
 def psnr(a, b):
     """10*log10(1/MSE), data_range 1 (lib/evaluators/enerf.py:71 uses skimage psnr, data_range=1)."""
     mse = torch.mean((a.double() - b.double()) ** 2).item()

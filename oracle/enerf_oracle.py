@@ -186,11 +186,12 @@ def depth_values_for_level(batch, cfg, level, D, depth, std, near_far):
     return dv.contiguous(), out_nf
 
 
-def feature_volume(feat, batch, cfg, level, depth, std, near_far):
-    """build_feature_volume, utils.py:322-349.  feat (B,S,C,hs,ws) -> variance (B,C,D,h,w)."""
+def feature_volume(feat, batch, cfg, level, depth, std, near_far, planes=None):
+    """build_feature_volume, utils.py:322-349.  feat (B,S,C,hs,ws) -> variance (B,C,D,h,w).
+    ``planes`` overrides cfg volume_planes[level] (the D argument of the reference function)."""
     c = cfg.enerf.cas_config
     S = feat.shape[1]
-    dv, nf = depth_values_for_level(batch, cfg, level, c.volume_planes[level], depth, std, near_far)
+    dv, nf = depth_values_for_level(batch, cfg, level, planes or c.volume_planes[level], depth, std, near_far)
     pm = proj_mats(batch, c.im_feat_scale[level], c.volume_scale[level])
     s1, s2 = 0, 0
     for s in range(S):

@@ -35,10 +35,56 @@ CASES = {
     "c4_human_small": dict(yaml="configs/enerf/dtu_pretrain.yaml",
                            opts=["enerf.cas_config.volume_planes", "8,8", "enerf.cas_config.render_if", "False,True"],
                            kind="cascade", over=dict(volume_planes=[8, 8], render_if=[False, True]), H=64, W=96, S=2, human=True),
+    # network_composite (configs/enerf/enerf_outdoor/actor1.yaml): one bbox-cropped foreground layer + background
+    "c5_composite_1fg": dict(yaml="configs/enerf/enerf_outdoor/actor1.yaml",
+                             opts=["enerf.cas_config.volume_planes", "8,8"],
+                             kind="composite", over=dict(volume_planes=[8, 8]), H=64, W=96, S=3, composite=1),
+    # two overlapping foreground layers (exercises the per-pixel z-sort), level 0 not rendered, 2 samples
+    "c5_composite_2fg": dict(yaml="configs/enerf/enerf_outdoor/actor1.yaml",
+                             opts=["num_fg_layers", "2", "enerf.cas_config.volume_planes", "8,8", "enerf.cas_config.num_samples", "2,2",
+                                   "enerf.cas_config.render_if", "False,True"],
+                             kind="composite", over=dict(volume_planes=[8, 8], num_samples=[2, 2], render_if=[False, True]),
+                             H=64, W=96, S=2, composite=2),
 }
 
 
+def run_composite_case(name):
+    """network_composite has no per-stage hooks worth stashing: outputs + a few layer intermediates
+    recomputed with the reference's own functions."""
+    import torch
+    from oracle.ref_loader import load_reference
+    from enerf_b200 import config as bcfg
+    from enerf_b200 import synthetic
+
+    case = CASES[name]
+    cfg, mods = load_reference(case["yaml"], case["opts"])
+    assert cfg.num_fg_layers == case["composite"]
+    import lib.networks.enerf.network_composite as network_composite
+    torch.manual_seed(0)
+    net = network_composite.Network().eval()
+    synthetic.randomize_bn_(net, seed=1)
+    my_cfg = bcfg.composite_cfg(num_fg_layers=case["composite"], **case["over"])
+    batch = synthetic.make_composite_batch(case["H"], case["W"], case["S"], my_cfg, seed=2)
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        out = net({k: v.clone() for k, v in batch.items()})
+    fixture = {
+        "case": name, "composite": case["composite"], "cfg_kind": case["kind"], "cfg_over": case["over"],
+        "H": case["H"], "W": case["W"], "S": case["S"],
+        "state_dict": {k: v.clone() for k, v in net.state_dict().items()},
+        "batch": batch,
+        "out": {k: (v.clone() if torch.is_tensor(v) else v) for k, v in out.items()},
+        "mid": {},
+        "reference_commit": "5a084e9", "torch": torch.__version__,
+    }
+    path = os.path.join(_ROOT, "tests", "golden", name + ".pt")
+    torch.save(fixture, path)
+    print(name, "->", path, os.path.getsize(path) // 1024, "KiB;", {k: (tuple(v.shape) if torch.is_tensor(v) else v) for k, v in out.items()})
+
+
 def run_case(name):
+    if CASES[name].get("composite"):
+        return run_composite_case(name)
     import torch
     from oracle.ref_loader import load_reference
     from enerf_b200 import config as bcfg

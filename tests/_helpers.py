@@ -8,6 +8,7 @@ if ROOT not in sys.path:
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["c1_nocascade", "c2_small_cascade", "c2_headline_small", "c4_human_small"]
+COMPOSITE_CASES = ["c5_composite_1fg", "c5_composite_2fg"]
 
 
 def load_golden(name):
@@ -15,6 +16,9 @@ def load_golden(name):
     from enerf_b200 import config as bcfg
 
     fx = torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
-    mk = bcfg.nocascade_cfg if fx["cfg_kind"] == "nocascade" else bcfg.make_cfg
-    fx["cfg"] = mk(**fx["cfg_over"])
+    if fx["cfg_kind"] == "composite":
+        fx["cfg"] = bcfg.composite_cfg(num_fg_layers=fx["composite"], **fx["cfg_over"])
+    else:
+        mk = bcfg.nocascade_cfg if fx["cfg_kind"] == "nocascade" else bcfg.make_cfg
+        fx["cfg"] = mk(**fx["cfg_over"])
     return fx

@@ -1,9 +1,12 @@
 """Pins the CPU oracle (oracle/enerf_oracle.py) against outputs of the unmodified reference
 (tests/golden/*.pt, minted by oracle/make_golden.py from /root/reference @5a084e9).
 The reference's own tests hold no vectors for this path."""
+import pytest
 import torch
 
 from oracle import enerf_oracle as O
+from oracle import enerf_oracle_composite as OC
+from _helpers import COMPOSITE_CASES, load_golden
 
 # fp32 noise floor of the reference against itself is ~5e-6 on rgb; the
 # oracle uses the same torch ops in the same order, so it should sit at or below that.
@@ -24,3 +27,33 @@ def test_oracle_matches_reference_outputs(golden):
         err = (mid[k] - ref).abs().max().item()
         scale = max(1.0, ref.abs().max().item())
         assert err <= 2e-5 * scale, f"intermediate {k}: {err}"
+
+
+def check_composite_outputs(out, ref_out, tol=2e-5, ztol=2e-5):
+    """Compares a composite forward with the reference's.  ``idx`` (the per-pixel sort permutation) is
+    implementation-defined where z values tie (all the zero samples outside a layer's window), so it
+    is checked through what it must do: z_vals gathered by idx is sorted and matches the reference's."""
+    assert set(out) == set(ref_out)
+    for k, ref in ref_out.items():
+        if ref is None:
+            assert out[k] is None, k
+            continue
+        assert tuple(out[k].shape) == tuple(ref.shape), k
+        if k.startswith("idx_"):
+            lvl = k.rsplit("_level", 1)[1]
+            z = ref_out[f"z_vals_level{lvl}"]
+            mine, theirs = z.gather(-1, out[k].long().cpu()), z.gather(-1, ref)
+            assert torch.equal(mine, theirs), f"{k}: permutation does not sort like the reference"
+            continue
+        scale = max(1.0, ref.abs().max().item())
+        err = (out[k].float().cpu() - ref).abs().max().item()
+        assert err <= (ztol if "z_vals" in k or "depth" in k else tol) * scale, f"{k}: max abs err {err}"
+
+
+@pytest.mark.parametrize("name", COMPOSITE_CASES)
+def test_composite_oracle_matches_reference_outputs(name):
+    fx = load_golden(name)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        out = OC.forward(fx["state_dict"], fx["cfg"], fx["batch"])
+    check_composite_outputs(out, fx["out"])
