@@ -39,6 +39,12 @@ _SIGS = {
     "enerf_depth_regress": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "enerf_render_rays": (_i, [_vp, _i, ctypes.POINTER(_vp), _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i,
                                _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "enerf_depth_hypotheses_layer": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "enerf_cost_volume_window": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, ctypes.POINTER(_i), _i, _vp, _vp]),
+    "enerf_depth_regress_window": (_i, [_vp, ctypes.POINTER(_i), _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "enerf_render_rays_raw": (_i, [_vp, _i, ctypes.POINTER(_vp), _i, _vp, ctypes.POINTER(_i), _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i,
+                                   _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "enerf_composite_layers": (_i, [_vp, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(_i), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "enerf_mask_compact_workspace_bytes": (_sz, [_i]),
     "enerf_mask_compact": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "enerf_scatter_rows": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
@@ -170,6 +176,51 @@ def render_rays(cam, level, weights, rays, depth, std, near_far, feat_vol, img_f
                                    ptr(near_far), hv, wv, ptr(feat_vol), D, ptr(img_feat_rgb), S, Hr, Wr, feat_ch, num_samples,
                                    int(depth_inv), int(white_bkgd), int(viewdir_agg), ptr(out_rgb), ptr(out_depth),
                                    ptr(out_weights), stream()), "enerf_render_rays")
+
+
+def _ints(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def depth_hypotheses_layer(layer_near_far, prev_depth, prev_std, prev_nf, h, w, D, depth_inv, ends, nf_out):
+    hp, wp = (prev_depth.shape[-2:] if prev_depth is not None else (0, 0))
+    _check(lib().enerf_depth_hypotheses_layer(ptr(layer_near_far, True), ptr(prev_depth, True), ptr(prev_std, True), ptr(prev_nf, True),
+                                              hp, wp, h, w, D, int(depth_inv), ptr(ends), ptr(nf_out), stream()),
+           "enerf_depth_hypotheses_layer")
+
+
+def cost_volume_window(cam, level, feat, ends, D, h, w, window, depth_inv, variance):
+    S, hs, ws, C = feat.shape
+    _check(lib().enerf_cost_volume_window(ptr(cam), level, ptr(feat), S, C, hs, ws, ptr(ends), D, h, w, _ints(window), int(depth_inv),
+                                          ptr(variance), stream()), "enerf_cost_volume_window")
+
+
+def depth_regress_window(depth_prob, window, ends, depth_inv, depth, std, depth_mvs=None):
+    D = depth_prob.shape[0]
+    h, w = ends.shape[-2:]
+    _check(lib().enerf_depth_regress_window(ptr(depth_prob), _ints(window), ptr(ends), D, h, w, int(depth_inv), ptr(depth), ptr(std),
+                                            ptr(depth_mvs, True), stream()), "enerf_depth_regress_window")
+
+
+def render_rays_raw(cam, level, weights, rays, window, depth, std, near_far, img_feat_rgb, feat_ch, num_samples, depth_inv,
+                    viewdir_agg, out_raw, out_z, out_off):
+    hv, wv = depth.shape[-2:]
+    S, Hr, Wr, _ = img_feat_rgb.shape
+    if rays.shape[0] != Hr * Wr:
+        raise ValueError(f"render_rays_raw wants the full {Hr}x{Wr} frame of rays, got {rays.shape[0]}")
+    _check(lib().enerf_render_rays_raw(ptr(cam), level, ptr_array(weights), len(weights), ptr(rays), _ints(window), ptr(depth), ptr(std),
+                                       ptr(near_far), hv, wv, ptr(img_feat_rgb), S, Hr, Wr, feat_ch, num_samples, int(depth_inv),
+                                       int(viewdir_agg), ptr(out_raw), ptr(out_z), out_z.shape[-1], out_off, stream()),
+           "enerf_render_rays_raw", launches=(1 if window[2] * window[3] > 0 else 0))
+
+
+def composite_layers(raw, z, Hr, Wr, n_fg_layers, ns_fg, ns_bg, boxes, rgb, depth, weights, net_output, idx, z_vals):
+    flat = [v for b in boxes for v in b]
+    if idx is not None and (idx.dtype != torch.int64 or not idx.is_cuda or not idx.is_contiguous()):
+        raise ValueError("idx must be a contiguous CUDA int64 tensor")
+    _check(lib().enerf_composite_layers(ptr(raw), ptr(z), Hr, Wr, n_fg_layers, ns_fg, ns_bg, _ints(flat), ptr(rgb), ptr(depth),
+                                        ptr(weights), ptr(net_output), idx.data_ptr() if idx is not None else None, ptr(z_vals), stream()),
+           "enerf_composite_layers")
 
 
 def tc_selftest(A, B, D):

@@ -29,14 +29,14 @@ __device__ __forceinline__ float plane_depth(float a, float b, int i, int D, boo
 __global__ void depth_hypotheses_kernel(const EnerfCam* __restrict__ cam, const float* __restrict__ prev_depth,
                                         const float* __restrict__ prev_std, const float* __restrict__ prev_nf, int hp,
                                         int wp, int h, int w, int D, int depth_inv, float* __restrict__ ends,
-                                        float* __restrict__ nf_out) {
+                                        float* __restrict__ nf_out, const float* __restrict__ first_nf) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= h * w) return;
   const int x = pix % w, y = pix / w;
   float a, b;
   if (prev_depth == nullptr) {
-    a = cam->near_far[0];
-    b = cam->near_far[1];
+    a = first_nf ? first_nf[0] : cam->near_far[0];
+    b = first_nf ? first_nf[1] : cam->near_far[1];
   } else {
     const float d = bilinear_ac(prev_depth, hp, wp, h, w, y, x);
     const float s = bilinear_ac(prev_std, hp, wp, h, w, y, x);
@@ -65,19 +65,22 @@ template <int C>
 __global__ void __launch_bounds__(256) cost_volume_kernel(const EnerfCam* __restrict__ cam, int level,
                                                           const float* __restrict__ feat, int S, int hs, int ws,
                                                           const float* __restrict__ ends, int D, int h, int w,
-                                                          int depth_inv, float* __restrict__ var_out) {
+                                                          int depth_inv, float* __restrict__ var_out, int x0, int y0, int wc,
+                                                          int hc) {
   constexpr int SPLIT = (C >= 16) ? 2 : 1;         // lanes per voxel
   constexpr int CH = C / SPLIT;                    // channels per thread
   constexpr int NV = CH / 4;                       // float4 per tap per thread
   __shared__ float Hm[ENERF_MAX_VIEWS * 12];
   for (int e = threadIdx.x; e < S * 12; e += blockDim.x) Hm[e] = cam->homo[level][e / 12][e % 12];
   __syncthreads();
-  const long long total = (long long)D * h * w * SPLIT;
+  // the volume covers the window [x0,x0+wc) x [y0,y0+hc) of the h x w target grid (the whole grid
+  // for enerf_cost_volume; a layer's bbox for enerf_cost_volume_window, utils.py:284-289)
+  const long long total = (long long)D * hc * wc * SPLIT;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int g = (int)(t % SPLIT);
   const long long vox = t / SPLIT;
-  const int x = (int)(vox % w), y = (int)((vox / w) % h), d = (int)(vox / ((long long)w * h));
+  const int x = x0 + (int)(vox % wc), y = y0 + (int)((vox / wc) % hc), d = (int)(vox / ((long long)wc * hc));
   const int pix = y * w + x;
   const float depth = plane_depth(__ldg(ends + pix), __ldg(ends + (size_t)h * w + pix), d, D, depth_inv);
   const float inv_depth = 1.0f / depth;
@@ -140,25 +143,31 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const EnerfCam* __rest
 
 __global__ void depth_regress_kernel(const float* __restrict__ prob, const float* __restrict__ ends, int D, int h, int w,
                                      int depth_inv, float* __restrict__ depth_out, float* __restrict__ std_out,
-                                     float* __restrict__ mvs_out) {
+                                     float* __restrict__ mvs_out, int x0, int y0, int wc, int hc) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  const int hw = h * w;
-  if (pix >= hw) return;
-  const float a = ends[pix], b = ends[(size_t)hw + pix];
+  if (pix >= h * w) return;
+  const float a = ends[pix], b = ends[(size_t)h * w + pix];
+  // prob covers the window [x0,x0+wc) x [y0,y0+hc) and is zero-padded to the h x w grid
+  // (network_composite.py:102: F.pad(depth_prob)); outside, softmax of zeros = uniform
+  const int lx = pix % w - x0, ly = pix / w - y0;
+  const bool inside = lx >= 0 && lx < wc && ly >= 0 && ly < hc;
+  const int hw = wc * hc;
+  prob += inside ? ly * wc + lx : 0;
+#define PROB_AT(d_) (inside ? __ldg(prob + (size_t)(d_) * hw) : 0.f)
   float mx = -INFINITY;
-  for (int d = 0; d < D; ++d) mx = fmaxf(mx, __ldg(prob + (size_t)d * hw + pix));
+  for (int d = 0; d < D; ++d) mx = fmaxf(mx, PROB_AT(d));
   float den = 0.f;
-  for (int d = 0; d < D; ++d) den += expf(__ldg(prob + (size_t)d * hw + pix) - mx);
+  for (int d = 0; d < D; ++d) den += expf(PROB_AT(d) - mx);
   float mean = 0.f;
   for (int d = 0; d < D; ++d) {
-    const float p = expf(__ldg(prob + (size_t)d * hw + pix) - mx) / den;
+    const float p = expf(PROB_AT(d) - mx) / den;
     float v = plane_depth(a, b, d, D, depth_inv);
     if (depth_inv) v = 1.0f / fmaxf(v, 1e-6f);
     mean += p * v;
   }
   float var = 0.f;
   for (int d = 0; d < D; ++d) {
-    const float p = expf(__ldg(prob + (size_t)d * hw + pix) - mx) / den;
+    const float p = expf(PROB_AT(d) - mx) / den;
     float v = plane_depth(a, b, d, D, depth_inv);
     if (depth_inv) v = 1.0f / fmaxf(v, 1e-6f);
     const float e = v - mean;
@@ -167,6 +176,7 @@ __global__ void depth_regress_kernel(const float* __restrict__ prob, const float
   depth_out[pix] = mean;
   std_out[pix] = sqrtf(fmaxf(var, 1e-10f));
   if (mvs_out) mvs_out[pix] = depth_inv ? 1.0f / mean : mean;
+#undef PROB_AT
 }
 
 }  // namespace enerf
@@ -179,24 +189,57 @@ extern "C" int enerf_depth_hypotheses(const EnerfCam* cam, const float* prev_dep
   ENERF_REQUIRE(h > 0 && w > 0 && D >= 1, ENERF_EINVAL, "depth_hypotheses: bad dims h=%d w=%d D=%d", h, w, D);
   if (prev_depth) ENERF_REQUIRE(prev_std && prev_near_far && hp > 0 && wp > 0, ENERF_EINVAL, "depth_hypotheses: prev level incomplete");
   depth_hypotheses_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(cam, prev_depth, prev_std, prev_near_far,
-                                                                                 hp, wp, h, w, D, depth_inv, ends, near_far_out);
+                                                                                 hp, wp, h, w, D, depth_inv, ends, near_far_out, nullptr);
   ENERF_CHECK_LAUNCH("depth_hypotheses");
   return ENERF_OK;
 }
 
+extern "C" int enerf_depth_hypotheses_layer(const float* layer_near_far, const float* prev_depth, const float* prev_std,
+                                            const float* prev_near_far, int hp, int wp, int h, int w, int D, int depth_inv,
+                                            float* ends, float* near_far_out, void* stream) {
+  using namespace enerf;
+  ENERF_REQUIRE(ends && near_far_out, ENERF_EINVAL, "depth_hypotheses_layer: null pointer");
+  ENERF_REQUIRE(prev_depth || layer_near_far, ENERF_EINVAL, "depth_hypotheses_layer: need the layer's near/far or a previous level");
+  ENERF_REQUIRE(h > 0 && w > 0 && D >= 1, ENERF_EINVAL, "depth_hypotheses_layer: bad dims h=%d w=%d D=%d", h, w, D);
+  if (prev_depth) ENERF_REQUIRE(prev_std && prev_near_far && hp > 0 && wp > 0, ENERF_EINVAL, "depth_hypotheses_layer: prev level incomplete");
+  depth_hypotheses_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(nullptr, prev_depth, prev_std, prev_near_far, hp, wp,
+                                                                                 h, w, D, depth_inv, ends, near_far_out, layer_near_far);
+  ENERF_CHECK_LAUNCH("depth_hypotheses_layer");
+  return ENERF_OK;
+}
+
+static int cost_volume_launch(const EnerfCam* cam, int level, const float* feat, int S, int C, int hs, int ws, const float* ends, int D,
+                              int h, int w, int depth_inv, float* variance, int x0, int y0, int wc, int hc, void* stream_);
+
 extern "C" int enerf_cost_volume(const EnerfCam* cam, int level, const float* feat, int S, int C, int hs, int ws,
                                  const float* ends, int D, int h, int w, int depth_inv, float* variance, void* stream_) {
+  return cost_volume_launch(cam, level, feat, S, C, hs, ws, ends, D, h, w, depth_inv, variance, 0, 0, w, h, stream_);
+}
+
+extern "C" int enerf_cost_volume_window(const EnerfCam* cam, int level, const float* feat, int S, int C, int hs, int ws,
+                                        const float* ends, int D, int h, int w, const int* window, int depth_inv, float* variance,
+                                        void* stream_) {
+  using namespace enerf;
+  ENERF_REQUIRE(window, ENERF_EINVAL, "cost_volume_window: null window");
+  const int x0 = window[0], y0 = window[1], wc = window[2], hc = window[3];
+  ENERF_REQUIRE(x0 >= 0 && y0 >= 0 && wc > 0 && hc > 0 && x0 + wc <= w && y0 + hc <= h, ENERF_EINVAL,
+                "cost_volume_window: window (%d,%d,%d,%d) outside the %dx%d grid", x0, y0, wc, hc, w, h);
+  return cost_volume_launch(cam, level, feat, S, C, hs, ws, ends, D, h, w, depth_inv, variance, x0, y0, wc, hc, stream_);
+}
+
+static int cost_volume_launch(const EnerfCam* cam, int level, const float* feat, int S, int C, int hs, int ws, const float* ends, int D,
+                              int h, int w, int depth_inv, float* variance, int x0, int y0, int wc, int hc, void* stream_) {
   using namespace enerf;
   cudaStream_t stream = (cudaStream_t)stream_;
   ENERF_REQUIRE(cam && feat && ends && variance, ENERF_EINVAL, "cost_volume: null pointer");
   ENERF_REQUIRE(level >= 0 && level < ENERF_MAX_LEVELS, ENERF_EINVAL, "cost_volume: level %d", level);
   ENERF_REQUIRE(S >= 1 && S <= ENERF_MAX_VIEWS, ENERF_EINVAL, "cost_volume: n_views %d not in [1,%d]", S, ENERF_MAX_VIEWS);
-  const long long total = (long long)D * h * w * (C >= 16 ? 2 : 1);
+  const long long total = (long long)D * hc * wc * (C >= 16 ? 2 : 1);
   const unsigned blocks = (unsigned)((total + 255) / 256);
   switch (C) {
-    case 8: cost_volume_kernel<8><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance); break;
-    case 16: cost_volume_kernel<16><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance); break;
-    case 32: cost_volume_kernel<32><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance); break;
+    case 8: cost_volume_kernel<8><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance, x0, y0, wc, hc); break;
+    case 16: cost_volume_kernel<16><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance, x0, y0, wc, hc); break;
+    case 32: cost_volume_kernel<32><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance, x0, y0, wc, hc); break;
     default: ENERF_REQUIRE(false, ENERF_EUNSUPPORTED, "cost_volume: C=%d not in {8,16,32}", C);
   }
   ENERF_CHECK_LAUNCH("cost_volume");
@@ -208,7 +251,20 @@ extern "C" int enerf_depth_regress(const float* depth_prob, const float* ends, i
   using namespace enerf;
   ENERF_REQUIRE(depth_prob && ends && depth && std, ENERF_EINVAL, "depth_regress: null pointer");
   depth_regress_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
-                                                                              depth_mvs);
+                                                                              depth_mvs, 0, 0, w, h);
   ENERF_CHECK_LAUNCH("depth_regress");
+  return ENERF_OK;
+}
+
+extern "C" int enerf_depth_regress_window(const float* depth_prob, const int* window, const float* ends, int D, int h, int w,
+                                          int depth_inv, float* depth, float* std, float* depth_mvs, void* stream) {
+  using namespace enerf;
+  ENERF_REQUIRE(depth_prob && window && ends && depth && std, ENERF_EINVAL, "depth_regress_window: null pointer");
+  const int x0 = window[0], y0 = window[1], wc = window[2], hc = window[3];
+  ENERF_REQUIRE(x0 >= 0 && y0 >= 0 && wc > 0 && hc > 0 && x0 + wc <= w && y0 + hc <= h, ENERF_EINVAL,
+                "depth_regress_window: window (%d,%d,%d,%d) outside the %dx%d grid", x0, y0, wc, hc, w, h);
+  depth_regress_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
+                                                                              depth_mvs, x0, y0, wc, hc);
+  ENERF_CHECK_LAUNCH("depth_regress_window");
   return ENERF_OK;
 }

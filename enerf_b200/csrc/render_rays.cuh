@@ -106,8 +106,9 @@ __global__ void __launch_bounds__(128) render_rays_kernel(const RayParams p) {
   }
   __syncthreads();
 
-  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  int ray = blockIdx.x * blockDim.x + threadIdx.x;
   if (ray >= p.n_rays) return;
+  if (p.out_raw) ray = (p.win_y + ray / p.win_w) * p.Wr + p.win_x + ray % p.win_w;   // window -> frame pixel
   const int S = STATIC_S ? SMAX : p.S;
   const int Ns = p.num_samples;
 
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(128) render_rays_kernel(const RayParams p) {
                   iz = ((gz + 1.f) / 2.f) * (float)(p.D - 1);
 #pragma unroll
       for (int c = 0; c < 8; ++c) vif[c] = 0.f;
-      if (ix > -1.f && ix < (float)p.wv && iy > -1.f && iy < (float)p.hv && iz > -1.f && iz < (float)p.D) {
+      if (p.feat_vol != nullptr && ix > -1.f && ix < (float)p.wv && iy > -1.f && iy < (float)p.hv && iz > -1.f && iz < (float)p.D) {
         const float fx0 = floorf(ix), fy0 = floorf(iy), fz0 = floorf(iz);
         const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0;
         const float wx[2] = {(fx0 + 1.f) - ix, ix - fx0}, wy[2] = {(fy0 + 1.f) - iy, iy - fy0}, wz[2] = {(fz0 + 1.f) - iz, iz - fz0};
@@ -427,6 +428,12 @@ __global__ void __launch_bounds__(128) render_rays_kernel(const RayParams p) {
         cr = fmaf(f[s][FC - 3], ws_, cr), cg = fmaf(f[s][FC - 2], ws_, cg), cbl = fmaf(f[s][FC - 1], ws_, cbl);
       }
 
+    if (p.out_raw) {   // layered mode: the samples are merged across layers later (enerf_composite_layers)
+      const size_t o = (size_t)ray * p.out_stride + p.out_off + k;
+      *reinterpret_cast<float4*>(p.out_raw + o * 4) = make_float4(cr, cg, cbl, sigma);
+      p.out_z[o] = p.depth_inv ? 1.0f / z : z;   // network_composite.py:48-51
+      continue;
+    }
     // ---- raw2outputs (running transmittance) ----
     const float alpha = 1.f - expf(-sigma);
     const float wk = alpha * T;
@@ -436,6 +443,7 @@ __global__ void __launch_bounds__(128) render_rays_kernel(const RayParams p) {
     wgt_all[k] = wk;
   }
 
+  if (p.out_raw) return;
   // depth uses softmax(weights) (utils.py:594-595)
   float mx = -INFINITY;
   for (int k = 0; k < Ns; ++k) mx = fmaxf(mx, wgt_all[k]);

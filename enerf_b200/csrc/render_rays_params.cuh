@@ -18,6 +18,12 @@ struct RayParams {
   int S, Hr, Wr;
   int num_samples, depth_inv, white_bkgd, viewdir_agg;
   float *out_rgb, *out_depth, *out_weights;
+  // layered ("composite") mode, out_raw != nullptr: rays is the full (Hr*Wr, 8) frame, ray r of the
+  // launch is pixel (win_x + r % win_w, win_y + r / win_w), and instead of compositing, the per-sample
+  // (r,g,b,sigma) and metric z go to out_raw[(pixel*out_stride + out_off + k)*4] / out_z[pixel*out_stride + out_off + k]
+  int win_x, win_y, win_w;
+  float *out_raw, *out_z;
+  int out_stride, out_off;
 };
 
 }  // namespace enerf

@@ -596,6 +596,7 @@ extern "C" int enerf_render_rays_tc(const EnerfCam* cam, int level, const float*
   p.feat_vol = feat_vol, p.D = D, p.img = img_feat_rgb, p.S = n_views, p.Hr = Hr, p.Wr = Wr;
   p.num_samples = num_samples, p.depth_inv = depth_inv, p.white_bkgd = white_bkgd, p.viewdir_agg = viewdir_agg;
   p.out_rgb = out_rgb, p.out_depth = out_depth, p.out_weights = out_weights;
+  p.win_x = p.win_y = p.win_w = 0, p.out_raw = p.out_z = nullptr, p.out_stride = p.out_off = 0;
   P.wblob = wblob;
   P.n_tiles = (int)(((long long)n_rays * num_samples + 127) / 128);
   switch (n_views) {

@@ -92,6 +92,18 @@ def pack_nerf(sd, p, feat_ch, viewdir_agg, device):
     return out
 
 
+def pack_nerf_novox(sd, p, feat_ch, viewdir_agg, device):
+    """nerf_.NeRF (no voxel feature, nerf_.py:29-43) in the 16-tensor layout of ``pack_nerf``: the 8
+    voxel input rows of lr0 ([24][64]) and of color.0 ([88+fc+4][64], rows 64..71) are zero, so the
+    ray kernels compute exactly the nerf_ network (adding 0 * x is exact)."""
+    out = pack_nerf(sd, p, feat_ch, viewdir_agg, device)
+    lr0, c0 = out[8], out[12]                       # [16][64], [64+16+fc+4][64]
+    z8 = torch.zeros((8, 64), device=lr0.device, dtype=lr0.dtype)
+    out[8] = torch.cat([z8, lr0], dim=0).contiguous()
+    out[12] = torch.cat([c0[:64], z8, c0[64:]], dim=0).contiguous()
+    return out
+
+
 def tf32_round(x):
     """cvt.rna.tf32.f32 on the host: round to nearest (ties away from zero) to a 10-bit mantissa."""
     b = x.to(torch.float32).contiguous().view(torch.int32)

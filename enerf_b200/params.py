@@ -94,13 +94,15 @@ class AggParams(nn.Module):
 
 
 class NerfParams(nn.Module):
-    def __init__(self, feat_ch, viewdir_agg, hid=64):
+    def __init__(self, feat_ch, viewdir_agg, hid=64, vox_ch=8):
+        """vox_ch=8: nerf.NeRF (nerf.py:7-27); vox_ch=0: nerf_.NeRF, which drops the voxel feature
+        (nerf_.py:13,20: lr0 Linear(16,hid), color.0 Linear(hid+16+feat_ch+4,hid))."""
         super().__init__()
-        self.feat_ch = feat_ch
+        self.feat_ch, self.vox_ch = feat_ch, vox_ch
         self.agg = AggParams(feat_ch, viewdir_agg)
-        self.lr0 = _fc(8 + 16, hid)
+        self.lr0 = _fc(vox_ch + 16, hid)
         self.sigma = _fc(hid, 1)
         # indices 0 and 2 carry the Linear layers (nerf.py:21-25: Linear, ReLU, Linear, ReLU)
-        self.color = nn.Sequential(nn.Linear(hid + 24 + feat_ch + 4, hid), nn.Identity(), nn.Linear(hid, 1))
+        self.color = nn.Sequential(nn.Linear(hid + vox_ch + 16 + feat_ch + 4, hid), nn.Identity(), nn.Linear(hid, 1))
         for m in (self.lr0, self.sigma, self.color):
             m.apply(_kaiming)

@@ -173,6 +173,47 @@ ENERF_API int enerf_mask_compact(const void* mask, int elem_size, const float* r
                                  int* count_out, void* workspace, size_t workspace_bytes, void* stream);
 ENERF_API int enerf_scatter_rows(const float* src, const int* idx, int m, int C, float* dst, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Layered ("composite") rendering, lib/networks/enerf/network_composite.py (SURVEY.md section 8f
+ * row f2): every foreground layer owns a bbox window of the frame, its own near/far, cost-volume
+ * regulariser and NeRF; a full-frame background layer is merged in behind them.
+ * `window` / `boxes` are HOST int arrays {x, y, w, h}.
+ *
+ * enerf_depth_hypotheses_layer: enerf_depth_hypotheses with the layer's own [near, far] (device, 2
+ *   floats) at the first level (get_depth_values_composite, utils.py:153-214).
+ * enerf_cost_volume_window: the variance volume over the window only; `ends` stays (2,h,w) over the
+ *   full grid, variance is (D,hc,wc,C)  (build_feature_volume_composite / homo_warp_composite,
+ *   utils.py:249-320).
+ * enerf_depth_regress_window: depth_regression of a (D,hc,wc) probability volume zero-padded to the
+ *   (h,w) grid (network_composite.py:102-103) -> full-grid depth / std.
+ * enerf_render_rays_raw: the fused ray stage of enerf_render_rays WITHOUT compositing and without the
+ *   voxel feature (nerf_.NeRF, nerf_.py:29-43; pass its weights through packing.pack_nerf_novox):
+ *   `rays` is the full (Hr*Wr,8) frame, the launch covers the window (build_rays_composite,
+ *   utils.py:216-247), and sample k of pixel q goes to out_raw[(q*out_stride + out_off + k)*4 .. +4)
+ *   = (r,g,b,sigma), out_z[q*out_stride + out_off + k] = metric z (network_composite.py:48-51).
+ * enerf_composite_layers: parse_layer + raw2outputs_composite (utils.py:875-942).  raw/z as written by
+ *   enerf_render_rays_raw with out_stride = n_fg_layers*ns_fg + ns_bg (layer l at offset l*ns_fg, the
+ *   background last); samples outside their layer's box count as zeros.  Outputs: rgb (HW,3),
+ *   depth (HW), weights (HW,n_total), net_output (HW,n_total,4) in composited order, z_vals
+ *   (HW,n_fg) before sorting, idx (HW,n_fg) int64 sort permutation (written when n_fg_layers > 1,
+ *   else may be NULL).  n_fg_layers in [1,8], n_fg_layers*ns_fg <= 32. */
+ENERF_API int enerf_depth_hypotheses_layer(const float* layer_near_far, const float* prev_depth, const float* prev_std,
+                                           const float* prev_near_far, int hp, int wp, int h, int w, int D, int depth_inv,
+                                           float* ends, float* near_far_out, void* stream);
+ENERF_API int enerf_cost_volume_window(const EnerfCam* cam, int level, const float* feat, int n_views, int C, int hs, int ws,
+                                       const float* ends, int D, int h, int w, const int* window, int depth_inv, float* variance,
+                                       void* stream);
+ENERF_API int enerf_depth_regress_window(const float* depth_prob, const int* window, const float* ends, int D, int h, int w,
+                                         int depth_inv, float* depth, float* std, float* depth_mvs, void* stream);
+ENERF_API int enerf_render_rays_raw(const EnerfCam* cam, int level, const float* const* weights, int n_weights, const float* rays,
+                                    const int* window, const float* depth, const float* std, const float* near_far, int hv, int wv,
+                                    const float* img_feat_rgb, int n_views, int Hr, int Wr, int feat_ch, int num_samples,
+                                    int depth_inv, int viewdir_agg, float* out_raw, float* out_z, int out_stride, int out_off,
+                                    void* stream);
+ENERF_API int enerf_composite_layers(const float* raw, const float* z, int Hr, int Wr, int n_fg_layers, int ns_fg, int ns_bg,
+                                     const int* boxes, float* rgb, float* depth, float* weights, float* net_output,
+                                     long long* idx, float* z_vals, void* stream);
+
 /* Device-side consumers of the rendered frame.
  * enerf_psnr_accumulate: acc[0] += sum (pred-gt)^2 over the pixels whose mask element is non-zero
  *   (mask == NULL: all pixels) x 3 channels, acc[1] += number of values; PSNR = 10 log10(acc[1]/acc[0])

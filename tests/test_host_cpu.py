@@ -107,3 +107,29 @@ def test_cfg_snapshot_and_ray_layout():
     assert b["rays_1"].shape == (1, 64 * 96, 8) and b["rays_0"].shape == (1, 16 * 24, 8)
     r = b["rays_1"][0].view(64, 96, 8)
     assert r[5, 7, 6] == 7 and r[5, 7, 7] == 5  # u, v are pixel coordinates, row-major
+
+
+def test_composite_state_dict_and_packing_match_reference_golden():
+    """network_composite: the reference's own state_dict (seed 0 + randomised BN) is reproduced key by
+    key and value by value; nerf_.NeRF weights embed into the 16-tensor ray-kernel layout with zero
+    rows where nerf.NeRF reads the voxel feature."""
+    from enerf_b200.network_composite import Network as CompositeNetwork
+    for name in ("c5_composite_1fg", "c5_composite_2fg"):
+        fx = load_golden(name)
+        bcfg.set_cfg(fx["cfg"])
+        torch.manual_seed(0)
+        net = CompositeNetwork()
+        synthetic.randomize_bn_(net, seed=1)
+        sd = net.state_dict()
+        assert list(sd.keys()) == list(fx["state_dict"].keys())
+        for k, v in fx["state_dict"].items():
+            assert sd[k].shape == v.shape and torch.equal(sd[k], v), k
+        net.load_state_dict(fx["state_dict"], strict=True)
+        with pytest.raises(ValueError, match="CUDA"):
+            net.eval()(fx["batch"])
+    sd = load_golden("c5_composite_1fg")["state_dict"]
+    pn = packing.pack_nerf_novox(sd, "nerf_1_bg", 11, False, "cpu")
+    assert pn[0] is None and pn[1] is None
+    assert tuple(pn[8].shape) == (24, 64) and tuple(pn[12].shape) == (103, 64)
+    assert pn[8][:8].abs().max() == 0 and pn[12][64:72].abs().max() == 0
+    assert torch.equal(pn[8][8:], sd["nerf_1_bg.lr0.0.weight"].t()) and torch.equal(pn[12][72:], sd["nerf_1_bg.color.0.weight"].t()[64:])
