@@ -44,6 +44,8 @@ _SIGS = {
     "enerf_depth_regress_window": (_i, [_vp, ctypes.POINTER(_i), _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "enerf_render_rays_raw": (_i, [_vp, _i, ctypes.POINTER(_vp), _i, _vp, ctypes.POINTER(_i), _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i,
                                    _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "enerf_render_rays_raw_tc": (_i, [_vp, _i, _vp, _vp, ctypes.POINTER(_i), _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i,
+                                      _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "enerf_composite_layers": (_i, [_vp, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(_i), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "enerf_mask_compact_workspace_bytes": (_sz, [_i]),
     "enerf_mask_compact": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -212,6 +214,18 @@ def render_rays_raw(cam, level, weights, rays, window, depth, std, near_far, img
                                        ptr(near_far), hv, wv, ptr(img_feat_rgb), S, Hr, Wr, feat_ch, num_samples, int(depth_inv),
                                        int(viewdir_agg), ptr(out_raw), ptr(out_z), out_z.shape[-1], out_off, stream()),
            "enerf_render_rays_raw", launches=(1 if window[2] * window[3] > 0 else 0))
+
+
+def render_rays_raw_tc(cam, level, wblob, rays, window, depth, std, near_far, img_feat_rgb, feat_ch, num_samples, depth_inv,
+                       viewdir_agg, out_raw, out_z, out_off):
+    hv, wv = depth.shape[-2:]
+    S, Hr, Wr, _ = img_feat_rgb.shape
+    if rays.shape[0] != Hr * Wr:
+        raise ValueError(f"render_rays_raw_tc wants the full {Hr}x{Wr} frame of rays, got {rays.shape[0]}")
+    _check(lib().enerf_render_rays_raw_tc(ptr(cam), level, ptr(wblob), ptr(rays), _ints(window), ptr(depth), ptr(std), ptr(near_far), hv, wv,
+                                          ptr(img_feat_rgb), S, Hr, Wr, feat_ch, num_samples, int(depth_inv), int(viewdir_agg),
+                                          ptr(out_raw), ptr(out_z), out_z.shape[-1], out_off, stream()),
+           "enerf_render_rays_raw_tc", launches=(1 if window[2] * window[3] > 0 else 0))
 
 
 def composite_layers(raw, z, Hr, Wr, n_fg_layers, ns_fg, ns_bg, boxes, rgb, depth, weights, net_output, idx, z_vals):

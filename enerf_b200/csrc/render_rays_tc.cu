@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
     RAY_STAMP(0);
     const long long pt = (long long)tile * 128 + t;
     const bool valid = pt < (long long)p.n_rays * Ns;
-    const int ray = valid ? (int)(pt / Ns) : p.n_rays - 1;
+    int ray = valid ? (int)(pt / Ns) : p.n_rays - 1;
+    if (p.out_raw) ray = (p.win_y + ray / p.win_w) * p.Wr + p.win_x + ray % p.win_w;   // layered mode: window -> frame pixel
     const int k = (int)(pt % Ns);
 
     // ================= stage A: build_rays + sample + gathers (FP32 pipe) =================
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
                   iz = ((gz + 1.f) / 2.f) * (float)(p.D - 1);
 #pragma unroll
       for (int c = 0; c < 8; ++c) vox[c] = 0.f;
-      if (ix > -1.f && ix < (float)p.wv && iy > -1.f && iy < (float)p.hv && iz > -1.f && iz < (float)p.D) {
+      if (p.feat_vol != nullptr && ix > -1.f && ix < (float)p.wv && iy > -1.f && iy < (float)p.hv && iz > -1.f && iz < (float)p.D) {
         const float fx0 = floorf(ix), fy0 = floorf(iy), fz0 = floorf(iz);
         const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0;
         const float wx[2] = {(fx0 + 1.f) - ix, ix - fx0}, wy[2] = {(fy0 + 1.f) - iy, iy - fy0}, wz[2] = {(fz0 + 1.f) - iz, iz - fz0};
@@ -469,7 +470,13 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
 
     RAY_STAMP(11);
     // ================= raw2outputs: prefix product / sums over the Ns lanes of a ray =================
-    if (Ns == 2) {
+    if (p.out_raw) {   // layered mode: samples are merged across layers by enerf_composite_layers
+      if (valid) {
+        const size_t o = (size_t)ray * p.out_stride + p.out_off + k;
+        *reinterpret_cast<float4*>(p.out_raw + o * 4) = make_float4(cr, cg, cb, sigma);
+        p.out_z[o] = p.depth_inv ? 1.0f / z : z;
+      }
+    } else if (Ns == 2) {
       // two samples of a ray in lanes (2i, 2i+1): one xor-shuffle exchange per quantity
       const float alpha = 1.f - expf(-sigma);
       const float tr = 1.f - alpha + 1e-10f;
@@ -599,6 +606,44 @@ extern "C" int enerf_render_rays_tc(const EnerfCam* cam, int level, const float*
   p.win_x = p.win_y = p.win_w = 0, p.out_raw = p.out_z = nullptr, p.out_stride = p.out_off = 0;
   P.wblob = wblob;
   P.n_tiles = (int)(((long long)n_rays * num_samples + 127) / 128);
+  switch (n_views) {
+    case 2: return launch_rays_tc<2>(P, stream);
+    case 3: return launch_rays_tc<3>(P, stream);
+    default: return launch_rays_tc<4>(P, stream);
+  }
+}
+
+extern "C" int enerf_render_rays_raw_tc(const EnerfCam* cam, int level, const float* wblob, const float* rays, const int* window,
+                                        const float* depth, const float* std, const float* near_far, int hv, int wv,
+                                        const float* img_feat_rgb, int n_views, int Hr, int Wr, int feat_ch, int num_samples,
+                                        int depth_inv, int viewdir_agg, float* out_raw, float* out_z, int out_stride, int out_off,
+                                        void* stream_) {
+  using namespace enerf;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ENERF_REQUIRE(cam && wblob && rays && window && depth && std && near_far && img_feat_rgb && out_raw && out_z, ENERF_EINVAL,
+                "render_rays_raw_tc: null pointer");
+  ENERF_REQUIRE(feat_ch == 8, ENERF_EUNSUPPORTED, "render_rays_raw_tc: feat_ch %d (tensor-core kernel is built for 8)", feat_ch);
+  ENERF_REQUIRE(n_views >= 2 && n_views <= 4, ENERF_EUNSUPPORTED, "render_rays_raw_tc: n_views %d not in [2,4]", n_views);
+  ENERF_REQUIRE(num_samples == 1 || num_samples == 2 || num_samples == 4 || num_samples == 8, ENERF_EUNSUPPORTED,
+                "render_rays_raw_tc: num_samples %d not in {1,2,4,8}", num_samples);
+  ENERF_REQUIRE(level >= 0 && level < ENERF_MAX_LEVELS, ENERF_EINVAL, "render_rays_raw_tc: level %d", level);
+  const int x = window[0], y = window[1], w = window[2], h = window[3];
+  ENERF_REQUIRE(x >= 0 && y >= 0 && w >= 0 && h >= 0 && x + w <= Wr && y + h <= Hr, ENERF_EINVAL,
+                "render_rays_raw_tc: window (%d,%d,%d,%d) outside the %dx%d frame", x, y, w, h, Wr, Hr);
+  ENERF_REQUIRE(out_off >= 0 && out_off + num_samples <= out_stride, ENERF_EINVAL, "render_rays_raw_tc: slot [%d,%d) outside stride %d",
+                out_off, out_off + num_samples, out_stride);
+  if (w == 0 || h == 0) return ENERF_OK;
+  RayTcParams P;
+  RayParams& p = P.r;
+  p.cam = cam, p.level = level;
+  for (int i = 0; i < 18; ++i) p.w[i] = nullptr;
+  p.rays = rays, p.n_rays = w * h, p.depth = depth, p.std = std, p.near_far = near_far, p.hv = hv, p.wv = wv;
+  p.feat_vol = nullptr, p.D = 1, p.img = img_feat_rgb, p.S = n_views, p.Hr = Hr, p.Wr = Wr;
+  p.num_samples = num_samples, p.depth_inv = depth_inv, p.white_bkgd = 0, p.viewdir_agg = viewdir_agg;
+  p.out_rgb = p.out_depth = p.out_weights = nullptr;
+  p.win_x = x, p.win_y = y, p.win_w = w, p.out_raw = out_raw, p.out_z = out_z, p.out_stride = out_stride, p.out_off = out_off;
+  P.wblob = wblob;
+  P.n_tiles = (int)(((long long)p.n_rays * num_samples + 127) / 128);
   switch (n_views) {
     case 2: return launch_rays_tc<2>(P, stream);
     case 3: return launch_rays_tc<3>(P, stream);

@@ -88,6 +88,8 @@ class Network(nn.Module):
                     pk[f"reg{i}_{tag}"] = packing.pack_cost_reg(sd, f"cost_reg_{i}_{tag}", int(32 * (2 ** (-i))), False, dev, False,
                                                                 tensor_cores=tcs)
                     pk[f"nerf{i}_{tag}"] = packing.pack_nerf_novox(sd, f"nerf_{i}_{tag}", lv.feat_ch + 3, vd, dev)
+                    if lv.feat_ch == 8:
+                        pk[f"nerf_tc{i}_{tag}"] = packing.pack_nerf_tc_novox(sd, f"nerf_{i}_{tag}", lv.feat_ch + 3, vd, dev)
             self._packed, self._packed_key = pk, key
         return self._packed
 
@@ -152,6 +154,16 @@ class Network(nn.Module):
         else:
             capi.depth_regress_window(prob, window, ends, lv.depth_inv, depth, std)
         return depth, std, nf
+
+    def _raw_rays(self, pk, tag, S, cam, i, rays, window, depth, std, nf, img, lv, vd, raw, zbuf, off):
+        """Per-sample (rgb, sigma, z) of the rays in `window`: tcgen05 MLP where the tensor-core kernel is
+        built for the configuration and precision allows, else the FP32-pipe kernel."""
+        if self.precision == "tf32" and capi.tc_ray_kernel_supports(lv.feat_ch, S, lv.num_samples):
+            capi.render_rays_raw_tc(cam, i, pk[f"nerf_tc{tag}"], rays, window, depth, std, nf, img, lv.feat_ch, lv.num_samples,
+                                    lv.depth_inv, vd, raw, zbuf, off)
+        else:
+            capi.render_rays_raw(cam, i, pk[f"nerf{tag}"], rays, window, depth, std, nf, img, lv.feat_ch, lv.num_samples, lv.depth_inv,
+                                 vd, raw, zbuf, off)
 
     def _forward_one(self, batch, b):
         cfg = get_cfg()
@@ -226,8 +238,7 @@ class Network(nn.Module):
                 if lv.render_if:
                     win_r = _int_box(boxes[l], lv.render_scale)
                     r_boxes.append(win_r)
-                    capi.render_rays_raw(cam, i, pk[f"nerf{i}_layer{l}"], rays, win_r, depth, std, nf, img, lv.feat_ch, ns, lv.depth_inv,
-                                         vd, raw, zbuf, l * ns)
+                    self._raw_rays(pk, f"{i}_layer{l}", S, cam, i, rays, win_r, depth, std, nf, img, lv, vd, raw, zbuf, l * ns)
             with torch.cuda.stream(side):
                 depth_, std_, nf_ = self._volume_stage(pk[f"reg{i}_bg"], "bg", i, lv, BG_PLANES[i], hw, cam, feats_bg[i], None, prev_bg,
                                                        None, tcs)
@@ -237,8 +248,7 @@ class Network(nn.Module):
                         side.wait_stream(main)      # rays / raw / zbuf were produced on the main stream
                     img_bg = self._scratch(f"img_bg{i}", S * Hr * Wr * (lv.feat_ch + 4), dev).view(S, Hr, Wr, lv.feat_ch + 4)
                     capi.pack_img_feat(feats_bg[lv.im_feat_level], bg_src, img_bg)
-                    capi.render_rays_raw(cam, i, pk[f"nerf{i}_bg"], rays, [0, 0, Wr, Hr], depth_, std_, nf_, img_bg, lv.feat_ch, ns,
-                                         lv.depth_inv, vd, raw, zbuf, n_fg)
+                    self._raw_rays(pk, f"{i}_bg", S, cam, i, rays, [0, 0, Wr, Hr], depth_, std_, nf_, img_bg, lv, vd, raw, zbuf, n_fg)
             if not lv.render_if:
                 continue
             if side is not main:

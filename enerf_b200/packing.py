@@ -92,16 +92,26 @@ def pack_nerf(sd, p, feat_ch, viewdir_agg, device):
     return out
 
 
+def _novox_as_vox(sd, p):
+    """nerf_.NeRF (no voxel feature, nerf_.py:29-43) embedded in nerf.NeRF's shapes: zero columns
+    where nerf.NeRF reads the 8 voxel channels (lr0 inputs 0..7, color.0 inputs 64..71), so the ray
+    kernels compute exactly the nerf_ network (adding 0 * x is exact)."""
+    sub = {k: v for k, v in sd.items() if k.startswith(p + ".")}
+    lr0, c0 = sub[f"{p}.lr0.0.weight"], sub[f"{p}.color.0.weight"]      # (64,16), (64, 64+16+fc+4)
+    z8 = torch.zeros((64, 8), device=lr0.device, dtype=lr0.dtype)
+    sub[f"{p}.lr0.0.weight"] = torch.cat([z8, lr0], dim=1)
+    sub[f"{p}.color.0.weight"] = torch.cat([c0[:, :64], z8, c0[:, 64:]], dim=1)
+    return sub
+
+
 def pack_nerf_novox(sd, p, feat_ch, viewdir_agg, device):
-    """nerf_.NeRF (no voxel feature, nerf_.py:29-43) in the 16-tensor layout of ``pack_nerf``: the 8
-    voxel input rows of lr0 ([24][64]) and of color.0 ([88+fc+4][64], rows 64..71) are zero, so the
-    ray kernels compute exactly the nerf_ network (adding 0 * x is exact)."""
-    out = pack_nerf(sd, p, feat_ch, viewdir_agg, device)
-    lr0, c0 = out[8], out[12]                       # [16][64], [64+16+fc+4][64]
-    z8 = torch.zeros((8, 64), device=lr0.device, dtype=lr0.dtype)
-    out[8] = torch.cat([z8, lr0], dim=0).contiguous()
-    out[12] = torch.cat([c0[:64], z8, c0[64:]], dim=0).contiguous()
-    return out
+    """nerf_.NeRF in the 16-tensor layout of ``pack_nerf`` (for enerf_render_rays_raw)."""
+    return pack_nerf(_novox_as_vox(sd, p), p, feat_ch, viewdir_agg, device)
+
+
+def pack_nerf_tc_novox(sd, p, feat_ch, viewdir_agg, device):
+    """nerf_.NeRF in the blob layout of ``pack_nerf_tc`` (for enerf_render_rays_raw_tc)."""
+    return pack_nerf_tc(_novox_as_vox(sd, p), p, feat_ch, viewdir_agg, device)
 
 
 def tf32_round(x):

@@ -33,8 +33,8 @@ class GraphedNetwork:
                 probe = net(self.static_in)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.flat_out, self.out_layout, saved_views = None, None, net.output_views
-        if flat_outputs and net.output_views is None and not getattr(net, "masked", False):
+        self.flat_out, self.out_layout, saved_views = None, None, getattr(net, "output_views", None)
+        if flat_outputs and hasattr(net, "output_views") and net.output_views is None and not getattr(net, "masked", False):
             self.out_layout, off = {}, 0
             for k, v in probe.items():
                 self.out_layout[k] = (off, tuple(v.shape))
@@ -50,7 +50,8 @@ class GraphedNetwork:
             with torch.cuda.graph(self.graph), torch.no_grad():
                 self.static_out = net(self.static_in)
         finally:
-            net.output_views = saved_views
+            if hasattr(net, "output_views"):
+                net.output_views = saved_views
 
     def load(self, batch, non_blocking=True):
         if _signature(batch) != self.sig:

@@ -210,6 +210,13 @@ ENERF_API int enerf_render_rays_raw(const EnerfCam* cam, int level, const float*
                                     const float* img_feat_rgb, int n_views, int Hr, int Wr, int feat_ch, int num_samples,
                                     int depth_inv, int viewdir_agg, float* out_raw, float* out_z, int out_stride, int out_off,
                                     void* stream);
+/* enerf_render_rays_raw with the MLP on the tensor cores (wblob: packing.pack_nerf_tc_novox); same
+ * support matrix as enerf_render_rays_tc (feat_ch 8, n_views 2..4, num_samples in {1,2,4,8}). */
+ENERF_API int enerf_render_rays_raw_tc(const EnerfCam* cam, int level, const float* wblob, const float* rays, const int* window,
+                                       const float* depth, const float* std, const float* near_far, int hv, int wv,
+                                       const float* img_feat_rgb, int n_views, int Hr, int Wr, int feat_ch, int num_samples,
+                                       int depth_inv, int viewdir_agg, float* out_raw, float* out_z, int out_stride, int out_off,
+                                       void* stream);
 ENERF_API int enerf_composite_layers(const float* raw, const float* z, int Hr, int Wr, int n_fg_layers, int ns_fg, int ns_bg,
                                      const int* boxes, float* rgb, float* depth, float* weights, float* net_output,
                                      long long* idx, float* z_vals, void* stream);
