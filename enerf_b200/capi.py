@@ -56,6 +56,7 @@ _SIGS = {
                                   _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "enerf_tc_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "enerf_tc_conv_debug": (_i, [_vp]),
+    "enerf_tc_conv_tune": (_i, [_i, _i, _i]),
     "enerf_tc_mma_bench": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "enerf_render_rays_debug": (_i, [_vp]),
     "enerf_tc_selftest": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
@@ -235,6 +236,10 @@ def composite_layers(raw, z, Hr, Wr, n_fg_layers, ns_fg, ns_bg, boxes, rgb, dept
     _check(lib().enerf_composite_layers(ptr(raw), ptr(z), Hr, Wr, n_fg_layers, ns_fg, ns_bg, _ints(flat), ptr(rgb), ptr(depth),
                                         ptr(weights), ptr(net_output), idx.data_ptr() if idx is not None else None, ptr(z_vals), stream()),
            "enerf_composite_layers")
+
+
+def tc_conv_tune(tz=0, ty=0, fold=-1):
+    _check(lib().enerf_tc_conv_tune(int(tz), int(ty), int(fold)), "enerf_tc_conv_tune", launches=0)
 
 
 def tc_selftest(A, B, D):

@@ -2,6 +2,8 @@
 // launch, and the C-ABI test/diagnostic entry.
 #include "tc_conv.cuh"
 
+#include <algorithm>
+
 namespace enerf {
 
 struct TcConvParams {
@@ -58,7 +60,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // but its inner row is only 16 bytes and the TMA unit then delivers ~1 B/clk/SM -- measured 3-5x
 // slower than the FP32 kernels; see DESIGN.md.)  Out-of-volume pixels are zero-filled (src-size 0)
 // = the convolution's zero padding.  The stage's weights arrive by one TMA bulk copy.
-template <int NTAPS, int MODE>
+//
+// FOLD = 1 (stride-1 3x3 / 3x3x3 layers): the three kx taps ride in the N dimension.  One MMA per
+// (kz,ky) tap computes P[m][kx*C + co] = sum_cin in[m + (kz*IY+ky)*IX][cin] * W[kz][ky][kx][cin][co] for the
+// 128 linear halo positions m, i.e. NTAPS = KD*KH MMAs of N = 3C instead of 3*KD*KH MMAs of N = C --
+// an M=128,K=8 TF32 MMA costs the same ~89 cycles for any N <= 64 (profiles/r1_mma_microbench.md), so
+// the tensor-pipe time drops 3x.  The epilogue undoes the shift: out[m] = P[m][0] + P[m+1][1] + P[m+2][2]
+// (rows = TMEM lanes: two warp shuffles; the two rows a warp needs from the next warp go through a
+// small shared-memory exchange).
+template <int NTAPS, int MODE, int FOLD>
 __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ in, int cin, const TcConvParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], done_bar;
@@ -171,11 +181,87 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
   const int plane = P.IY * P.IX;
   // linear halo position of this thread's row in M-tile 0, advanced by 128 per M-tile
   int z = t / plane, rem = t - z * plane, y = rem / P.IX, x = rem - y * P.IX;
+  const int lane = t & 31;
+  float* xch = reinterpret_cast<float*>(smem_raw);   // FOLD: [n_mt*4 + 1][2 lanes][N]; the stage buffers are free now
+  if constexpr (FOLD) {
+    // rows 0 and 1 of every 32-row group, for the two last lanes of the group before it
+    for (int m = 0; m < P.n_mt; ++m)
+      for (int c = 0; c < P.N; c += 8) {
+        float v[8];
+        tc::tmem_ld8(trow + (uint32_t)(m * P.N + c), v);
+        tc::tmem_ld_wait();
+        if (lane < 2) {
+          float4* d = reinterpret_cast<float4*>(xch + ((size_t)((m * 4 + warp) * 2 + lane)) * P.N + c);
+          d[0] = make_float4(v[0], v[1], v[2], v[3]);
+          d[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+    __syncthreads();
+  }
   for (int m = 0; m < P.n_mt; ++m) {
     const int gz = z0 + z, gy = y0 + y, gx = x0 + x;
     const bool valid = (z < P.TZ) && (y < P.TY) && (x < P.TX) && (gz < P.Dn) && (gy < P.Hn) && (gx < P.Wn);
     const size_t pix = ((size_t)gz * P.Hn + gy) * P.Wn + gx;
-    if constexpr (MODE == TC_PLAIN) {
+    const float* nx = xch + (size_t)((m * 4 + warp + 1) * 2) * P.N;   // rows 0,1 of the next 32-row group
+    // P[m+1][C + j] and P[m+2][2C + j] for this thread's row, given its own row's column values
+    auto shifted = [&](float b, float c, int colb, int colc, float& b1, float& c2) {
+      b1 = __shfl_down_sync(0xffffffffu, b, 1);
+      c2 = __shfl_down_sync(0xffffffffu, c, 2);
+      if (lane == 31) b1 = nx[colb];
+      if (lane >= 30) c2 = nx[(lane - 30) * P.N + colc];
+    };
+    if constexpr (FOLD && MODE == TC_PLAIN) {
+      const int C = P.cout;
+      for (int c0 = 0; c0 < C; c0 += 8) {
+        float a[8], b[8], c[8];
+        tc::tmem_ld8(trow + (uint32_t)(m * P.N + c0), a);
+        tc::tmem_ld8(trow + (uint32_t)(m * P.N + C + c0), b);
+        tc::tmem_ld8(trow + (uint32_t)(m * P.N + 2 * C + c0), c);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float b1, c2;
+          shifted(b[j], c[j], C + c0 + j, 2 * C + c0 + j, b1, c2);
+          a[j] = (a[j] + b1) + c2;
+        }
+        if (valid) {
+          const float4 b0v = ldg4(P.bias + c0), b1v = ldg4(P.bias + c0 + 4);
+          float4 o0 = make_float4(a[0] + b0v.x, a[1] + b0v.y, a[2] + b0v.z, a[3] + b0v.w);
+          float4 o1 = make_float4(a[4] + b1v.x, a[5] + b1v.y, a[6] + b1v.z, a[7] + b1v.w);
+          if (P.relu) {
+            o0 = make_float4(fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f));
+            o1 = make_float4(fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f));
+          }
+          float4* o = reinterpret_cast<float4*>(P.out + pix * P.out_cstride + P.out_coff + c0);
+          o[0] = o0;
+          o[1] = o1;
+        }
+      }
+    } else if constexpr (FOLD && MODE == TC_HEAD) {   // columns kx*9 + co: 8 feat + 1 prob per kx
+      float v[32];
+      tc::tmem_ld32(trow + (uint32_t)(m * P.N), v);
+      tc::tmem_ld_wait();
+      float r[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        float b1, c2;
+        shifted(v[9 + j], v[18 + j], 9 + j, 18 + j, b1, c2);
+        r[j] = (v[j] + b1) + c2;
+      }
+      if (valid) {
+        float4* o = reinterpret_cast<float4*>(P.out + pix * 8);
+        o[0] = make_float4(r[0], r[1], r[2], r[3]);
+        o[1] = make_float4(r[4], r[5], r[6], r[7]);
+        P.out2[pix] = r[8];
+      }
+    } else if constexpr (FOLD && MODE == TC_SINGLE) {
+      float v[8];
+      tc::tmem_ld8(trow + (uint32_t)(m * P.N), v);
+      tc::tmem_ld_wait();
+      float b1, c2;
+      shifted(v[1], v[2], 1, 2, b1, c2);
+      if (valid) P.out[pix] = (v[0] + b1) + c2;
+    } else if constexpr (MODE == TC_PLAIN) {
       for (int c0 = 0; c0 < P.cout; c0 += 8) {       // cout is a multiple of 8
         float v[8];
         tc::tmem_ld8(trow + (uint32_t)(m * P.N + c0), v);
@@ -243,6 +329,9 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
   TC_STAMP(62);
 }
 
+// Tuning override (enerf_tc_conv_tune): tile TZ x TY and kx folding forced for every later launch.
+static int g_tune_tz = 0, g_tune_ty = 0, g_tune_fold = -1;
+
 int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias,
                    const float* skip, float* out, float* out2, int out_cstride, int out_coff, cudaStream_t stream) {
   ENERF_REQUIRE(L.cin % 8 == 0 && L.cin >= 8, ENERF_EUNSUPPORTED, "tc_conv: cin %d must be a multiple of 8", L.cin);
@@ -257,7 +346,14 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
   P.sz = (stride == 2 && L.KD > 1) ? 2 : 1, P.sy = stride, P.sx = stride;
   P.n_phases = P.sz * P.sy * P.sx;
   P.Di = (P.sz == 2) ? 2 * Dn : Dn, P.Hi = stride * Hn, P.Wi = stride * Wn;   // even inputs (pad K/2) halve exactly
-  int n_real = (L.kind == 1) ? 8 * L.cout : L.cout;
+  // kx taps folded into N (see the kernel comment).  Measured (tools_tc_tile_sweep.py): it pays where the
+  // unfolded layer is tensor-issue bound -- 3-D layers with 8 (or 1) output channels: CostRegNet conv0
+  // 101 -> 64 us / 134 -> 97 us, depth head 27 -> 21 us -- and costs 10-40 % elsewhere (3x the TMEM
+  // read-out per row).  packing.tc_fold_kx() applies the same rule to the weights.
+  bool fold = (L.kind == 0 && stride == 1 && L.KH == 3 && L.KD == 3 && ((L.mode == TC_PLAIN && L.cout == 8) || L.mode == TC_SINGLE));
+  if (g_tune_fold == 0) fold = false;
+  if (g_tune_fold == 1) fold = (L.kind == 0 && stride == 1 && L.KH == 3);
+  int n_real = (L.kind == 1) ? 8 * L.cout : fold ? 3 * L.cout : L.cout;
   P.N = (n_real + 15) / 16 * 16;
   ENERF_REQUIRE(P.N <= 256, ENERF_EUNSUPPORTED, "tc_conv: N=%d > 256", P.N);
   if (L.mode == TC_DECONV) ENERF_REQUIRE(L.cout % 8 == 0 && skip && bias, ENERF_EINVAL, "tc_conv: deconv needs cout%%8==0, skip and bias");
@@ -277,6 +373,16 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
   P.TX = 32;
   P.TY = (L.kind == 0 && L.KD == 1) ? 16 : 8;
   P.TZ = (L.kind == 0 && L.KD == 1) ? 1 : 2;
+  // measured tile rules for the stride-1 3x3 layers (tools_tc_tile_sweep.py): what matters is the share of
+  // real outputs among the 128-row M-tiles (rows are linear halo positions, IX = 34 per row of 32):
+  // 2-D: 7 rows -> 2 M-tiles (87 %), 15 rows -> 4 (94 %; best for the one-stage Cin = 8 layer);
+  // folded 3-D: 4 x 4 rows (least halo re-read: 2.25x)
+  if (L.kind == 0 && stride == 1 && L.KH == 3) {
+    if (L.KD == 1) P.TY = (L.cin == 8) ? 15 : 7;
+    else if (fold) P.TZ = 4, P.TY = 4;
+  }
+  if (g_tune_tz > 0) P.TZ = g_tune_tz;
+  if (g_tune_ty > 0) P.TY = g_tune_ty;
   if (P.TZ > Dn) P.TZ = Dn;
   if (P.TY > Hn) P.TY = Hn;
   size_t smem = 0;
@@ -284,12 +390,16 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
   for (;;) {
     P.IZ = P.TZ + hz, P.IY = P.TY + hy, P.IX = P.TX + hx;
     const int pmax = ((P.TZ - 1) * P.IY + (P.TY - 1)) * P.IX + P.TX - 1;
-    P.n_mt = pmax / 128 + 1;
+    P.n_mt = (pmax + (fold ? 2 : 0)) / 128 + 1;   // folded: output row m also reads rows m+1, m+2
     const int npix = P.IZ * P.IY * P.IX;
     // taps: operand start offset (16-byte units) = phase block + linear pixel offset inside the phase tile
     if (L.kind == 1) {
       P.n_taps = 8;
       for (int d = 0; d < 8; ++d) P.tap_off[d] = (((d >> 2) & 1) * P.IY + ((d >> 1) & 1)) * P.IX + (d & 1);
+    } else if (fold) {
+      P.n_taps = L.KD * L.KH;
+      for (int kz = 0, i = 0; kz < L.KD; ++kz)
+        for (int ky = 0; ky < L.KH; ++ky) P.tap_off[i++] = (kz * P.IY + ky) * P.IX;
     } else {
       P.n_taps = L.KD * L.KH * L.KH;
       auto split = [](int k, int K, int s, int o, int& d, int& r) {   // k - pad = s*d + r, returns d' = d + o
@@ -316,10 +426,12 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
     // the end of a phase block; keep those reads inside the allocation
     smem = (size_t)(P.n_stages > 1 ? 2 : 1) * stage_bytes + (size_t)npix_tot * 4 + 64 + (size_t)(P.n_mt * 128 + 64) * 16;
     const long long n_cta = (long long)ceil_div(Wn, P.TX) * ceil_div(Hn, P.TY) * ceil_div(Dn, P.TZ);
+    if (fold) smem = std::max(smem, (size_t)(P.n_mt * 4 + 1) * 2 * P.N * 4 + 128);   // epilogue row exchange reuses the stage buffers
     const bool fits = P.n_mt * P.N <= 512 && smem <= 200 * 1024;
     // small layers: keep shrinking the tile until the grid covers the 148 SMs (fewer M-tiles per
     // CTA = shorter serial MMA phases); large layers: the biggest tile that fits
-    if (fits && (n_cta >= 148 || (P.TY <= 2 && P.TZ <= 1))) break;
+    if (fits && (n_cta >= 148 || (P.TY <= 2 && P.TZ <= 1) || g_tune_ty > 0)) break;
+    ENERF_REQUIRE(g_tune_ty == 0, ENERF_EUNSUPPORTED, "tc_conv: forced tile %dx%d does not fit", P.TZ, P.TY);
     if (P.TY > 2) P.TY /= 2;
     else if (P.TZ > 1) P.TZ /= 2;
     else if (!fits && P.TX > 16) P.TX /= 2;
@@ -331,23 +443,27 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
 
   ENERF_REQUIRE(L.mode != TC_PLAIN || (L.cout % 8 == 0 && bias), ENERF_EINVAL, "tc_conv: plain mode needs cout %% 8 == 0 and a bias");
   dim3 grid(ceil_div(Wn, P.TX), ceil_div(Hn, P.TY), ceil_div(Dn, P.TZ));
-#define TC_LAUNCH(NT, MD)                                                                                          \
+#define TC_LAUNCH(NT, MD, FD)                                                                                        \
   do {                                                                                                             \
     static size_t smem_set = 0;                                                                                    \
     if (smem > smem_set) {                                                                                         \
-      cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<NT, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<NT, MD, FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e)); \
       smem_set = smem;                                                                                             \
     }                                                                                                              \
-    tc_conv_kernel<NT, MD><<<grid, 128, smem, stream>>>(in, L.cin, P);                                             \
+    tc_conv_kernel<NT, MD, FD><<<grid, 128, smem, stream>>>(in, L.cin, P);                                         \
   } while (0)
-  if (L.kind == 1) TC_LAUNCH(8, TC_DECONV);
-  else if (P.n_taps == 27 && L.mode == TC_PLAIN) TC_LAUNCH(27, TC_PLAIN);
-  else if (P.n_taps == 27 && L.mode == TC_HEAD) TC_LAUNCH(27, TC_HEAD);
-  else if (P.n_taps == 27 && L.mode == TC_SINGLE) TC_LAUNCH(27, TC_SINGLE);
-  else if (P.n_taps == 9 && L.mode == TC_PLAIN) TC_LAUNCH(9, TC_PLAIN);
-  else if (P.n_taps == 25 && L.mode == TC_PLAIN) TC_LAUNCH(25, TC_PLAIN);
-  else if (P.n_taps == 1 && L.mode == TC_PLAIN) TC_LAUNCH(1, TC_PLAIN);
+  if (L.kind == 1) TC_LAUNCH(8, TC_DECONV, 0);
+  else if (fold && P.n_taps == 9 && L.mode == TC_PLAIN) TC_LAUNCH(9, TC_PLAIN, 1);
+  else if (fold && P.n_taps == 9 && L.mode == TC_HEAD) TC_LAUNCH(9, TC_HEAD, 1);
+  else if (fold && P.n_taps == 9 && L.mode == TC_SINGLE) TC_LAUNCH(9, TC_SINGLE, 1);
+  else if (fold && P.n_taps == 3 && L.mode == TC_PLAIN) TC_LAUNCH(3, TC_PLAIN, 1);
+  else if (!fold && P.n_taps == 27 && L.mode == TC_PLAIN) TC_LAUNCH(27, TC_PLAIN, 0);
+  else if (!fold && P.n_taps == 27 && L.mode == TC_HEAD) TC_LAUNCH(27, TC_HEAD, 0);
+  else if (!fold && P.n_taps == 27 && L.mode == TC_SINGLE) TC_LAUNCH(27, TC_SINGLE, 0);
+  else if (!fold && P.n_taps == 9 && L.mode == TC_PLAIN) TC_LAUNCH(9, TC_PLAIN, 0);
+  else if (!fold && P.n_taps == 25 && L.mode == TC_PLAIN) TC_LAUNCH(25, TC_PLAIN, 0);
+  else if (!fold && P.n_taps == 1 && L.mode == TC_PLAIN) TC_LAUNCH(1, TC_PLAIN, 0);
   else ENERF_REQUIRE(false, ENERF_EUNSUPPORTED, "tc_conv: no instantiation for %d taps, mode %d", P.n_taps, L.mode);
 #undef TC_LAUNCH
   ENERF_CHECK_LAUNCH("tc_conv");
@@ -371,6 +487,13 @@ extern "C" int enerf_tc_conv(int kind, int KD, int KH, int stride, int cin, int 
   }
   TcConvLayer L{kind, KD, KH, cin, cout, mode, relu, stride};
   return tc_conv_launch(L, in, D, H, W, wpack, bias, skip, out, out2, out_cstride, out_coff, (cudaStream_t)stream);
+}
+
+// Diagnostic / tuning: force the tile (TZ x TY positions, TX = 32) and the kx folding (0 off, 1 on where
+// applicable, -1 default) of every later tc_conv launch; tz = ty = 0 restores the built-in choice.
+extern "C" int enerf_tc_conv_tune(int tz, int ty, int fold) {
+  enerf::g_tune_tz = tz, enerf::g_tune_ty = ty, enerf::g_tune_fold = fold;
+  return ENERF_OK;
 }
 
 // Diagnostic: phase timestamps (64 x u64, ns) of CTA (0,0,0) of subsequent tc_conv launches are

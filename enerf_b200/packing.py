@@ -35,12 +35,19 @@ def _dev(t, device):
 TC_FEATURE_LAYERS = ("conv0.1", "conv1.0", "conv1.1", "conv2.0", "conv2.1", "toplayer", "smooth1", "smooth0")
 
 
+def tc_fold_kx(KD, KH, stride, cout, single=False):
+    """The folding rule of csrc/tc_conv.cu::tc_conv_launch: stride-1 3x3x3 layers with 8 output
+    channels, and the single-channel depth head."""
+    return KD == 3 and KH == 3 and stride == 1 and (cout == 8 or single)
+
+
+
 def pack_feature_net(sd, device, p="feature_net", tensor_cores=False):
     """22 tensors: {w,b} for conv0.0 conv0.1 conv1.0 conv1.1 conv2.0 conv2.1 toplayer lat1 lat0 smooth1 smooth0.
     tensor_cores: the layers in TC_FEATURE_LAYERS get the tcgen05 stage layout (pack_tc_conv)."""
     def lay(name, w_taps):
         if tensor_cores and name in TC_FEATURE_LAYERS:
-            return pack_tc_conv(w_taps).to(device)
+            return pack_tc_conv(w_taps).to(device)     # 2-D layers are never folded (tc_fold_kx)
         return _dev(w_taps, device)
 
     out = []
@@ -65,7 +72,7 @@ def pack_cost_reg(sd, p, in_ch, deep, device, with_feat, tensor_cores=False):
             w, b = _fold(sd[q + ".conv.weight"], sd, q + ".bn", 0)
             wt = _taps_cin_cout(w)
             use_tc = tensor_cores
-            out += [pack_tc_conv(wt).to(device) if use_tc else _dev(wt, device), _dev(b, device)]
+            out += [pack_tc_conv(wt, fold_kx=tc_fold_kx(3, 3, stride, cout)).to(device) if use_tc else _dev(wt, device), _dev(b, device)]
         elif kind == "deconv":
             w, b = _fold(sd[q + ".0.weight"], sd, q + ".1", 1)      # (Cin,Cout,kz,ky,kx)
             wt = w.permute(2, 3, 4, 0, 1).reshape(27, cin, cout)
@@ -73,7 +80,8 @@ def pack_cost_reg(sd, p, in_ch, deep, device, with_feat, tensor_cores=False):
         else:
             head[name] = _taps_cin_cout(sd[q + ".0.weight"].double())   # [27][8][cout]
     hw = torch.cat([head["feat_conv"], head["depth_conv"]], dim=2) if with_feat else head["depth_conv"]
-    out.append(pack_tc_conv(hw).to(device) if tensor_cores else _dev(hw, device))
+    out.append(pack_tc_conv(hw, fold_kx=tc_fold_kx(3, 3, 1, hw.shape[-1], single=not with_feat)).to(device) if tensor_cores
+               else _dev(hw, device))
     return out
 
 
@@ -172,8 +180,14 @@ def pack_nerf_tc(sd, p, feat_ch, viewdir_agg, device):
     return blob.to(device).contiguous()
 
 
-def pack_tc_conv(w_taps, n_pad=None):
-    """[tap][cin][cout] (BN-folded, fp32) -> tcgen05 stage layout [cin/8][tap][2][N][4], TF32 (RNA)."""
+def pack_tc_conv(w_taps, n_pad=None, fold_kx=False):
+    """[tap][cin][cout] (BN-folded, fp32) -> tcgen05 stage layout [cin/8][tap][2][N][4], TF32 (RNA).
+    fold_kx (stride-1 3x3 / 3x3x3 layers, the rule tc_conv_launch applies): the three kx taps move into
+    the N dimension, [KD*KH][cin][kx*cout + co], N = 3*cout padded to 16 (csrc/tc_conv.cu, FOLD)."""
+    if fold_kx:
+        taps, cin, cout = w_taps.shape
+        assert taps in (9, 27)
+        w_taps = w_taps.reshape(taps // 3, 3, cin, cout).permute(0, 2, 1, 3).reshape(taps // 3, cin, 3 * cout)
     taps, cin, cout = w_taps.shape
     N = n_pad or (cout + 15) // 16 * 16
     full = torch.zeros(taps, cin, N, dtype=torch.float32)

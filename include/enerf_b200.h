@@ -260,6 +260,11 @@ ENERF_API int enerf_tc_conv(int kind, int KD, int KH, int stride, int cin, int c
  * %globaltimer phase stamps (ns) into buf (device memory, 64 x u64).  NULL switches it off. */
 ENERF_API int enerf_tc_conv_debug(unsigned long long* buf);
 
+/* Diagnostic / tuning: force the tile (tz x ty rows of 32 positions) and the kx-tap folding (0 off, 1 on
+ * where applicable, -1 built-in) of every later enerf_tc_conv-family launch; (0, 0, -1) restores the
+ * built-in choice.  Weights must be packed for the folding in force (packing.pack_tc_conv fold_kx). */
+ENERF_API int enerf_tc_conv_tune(int tz, int ty, int fold);
+
 /* Diagnostic: like enerf_tc_conv_debug for enerf_render_rays_tc (32 x u64: 16 stamps for each of
  * the first two tiles of CTA 0). */
 ENERF_API int enerf_render_rays_debug(unsigned long long* buf);

@@ -164,6 +164,9 @@ TC_CONV_CASES = [
     (0, 3, 3, 32, 64, 0, 1, (2, 8, 12), 2),  # conv5
     (0, 1, 5, 8, 16, 0, 1, (3, 64, 96), 2),  # FeatureNet conv1.0 (5x5 stride 2)
     (0, 1, 5, 16, 32, 0, 1, (2, 32, 48), 2),  # conv2.0
+    (0, 3, 3, 8, 8, 0, 1, (5, 20, 44)),      # ragged extents: partial tiles in every dimension (folded kx, row exchange)
+    (0, 1, 3, 8, 8, 0, 1, (3, 50, 70)),      # conv0.1-like, ragged
+    (0, 3, 3, 8, 9, 1, 0, (4, 12, 20)),      # head, ragged
 ]
 
 
@@ -186,7 +189,7 @@ def test_tc_conv_layer(case):
         ref = F.conv3d(x, w, b, (stride if KD > 1 else 1, stride, stride), (KD // 2, KH // 2, KH // 2))
         if relu:
             ref = F.relu(ref)
-        wp = packing.pack_tc_conv(packing._taps_cin_cout(w)).cuda()
+        wp = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=packing.tc_fold_kx(KD, KH, stride, cout, single=(mode == 3))).cuda()
         skip = None
     else:
         w = torch.randn(cin, cout, 3, 3, 3, generator=g) / (cin * 27 / 8) ** 0.5

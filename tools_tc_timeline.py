@@ -7,7 +7,7 @@ def run(name, KD, KH, cin, cout, dims, mode=0):
     D, H, W = dims
     x = torch.randn(D, H, W, cin, device="cuda")
     w = torch.randn(cout, cin, KD, KH, KH) / (cin * KD * KH * KH) ** 0.5
-    wp = packing.pack_tc_conv(packing._taps_cin_cout(w)).cuda()
+    wp = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=packing.tc_fold_kx(KD, KH, 1, cout)).cuda()
     b = torch.zeros(cout, device="cuda")
     out = torch.empty(D, H, W, cout, device="cuda")
     buf = torch.zeros(64, dtype=torch.int64, device="cuda")
