@@ -381,6 +381,14 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
     if (L.KD == 1) P.TY = (L.cin == 8) ? 15 : 7;
     else if (fold) P.TZ = 4, P.TY = 4;
   }
+  // strided / transposed layers: small tiles keep the accumulators within 128 TMEM columns, i.e. 4 resident
+  // CTAs per SM whose load / MMA / epilogue phases overlap (conv11 of level 1: 2 x 8 rows = 5 M-tiles x
+  // N 64 = 512 columns = ONE CTA per SM, 50 us; 2 x 3 rows = 128 columns, 19 us)
+  if (L.kind == 0 && stride == 2) {
+    if (L.KD == 1) P.TY = 7;
+    else P.TZ = 2, P.TY = 3;
+  }
+  if (L.kind == 1 && P.N <= 64) P.TZ = 2, P.TY = 3;
   if (g_tune_tz > 0) P.TZ = g_tune_tz;
   if (g_tune_ty > 0) P.TY = g_tune_ty;
   if (P.TZ > Dn) P.TZ = Dn;
