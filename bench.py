@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--mode", default="frames", choices=["frames", "rays"], help="N>1: frame-parallel sequence (default) or intra-frame ray-band sharding")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="replay the forward as a CUDA graph (0 = eager launches)")
-    ap.add_argument("--inflight", type=int, default=3, help="frames rendered concurrently per GPU (one CUDA graph + stream each); "
+    ap.add_argument("--inflight", type=int, default=4, help="frames rendered concurrently per GPU (one CUDA graph + stream each); "
                     "1 = strictly one frame at a time (latency mode)")
     ap.add_argument("--host-rays", type=int, default=0, help="1: ship rays_1 from the host like the reference's data layer (default: generate on device)")
     args = ap.parse_args()

@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const EnerfCam* __rest
   }
 }
 
-__global__ void depth_regress_kernel(const float* __restrict__ prob, const float* __restrict__ ends, int D, int h, int w,
+// one thread per pixel: the large maps (level 1: 81,920 pixels x 8 planes)
+__global__ void depth_regress_px_kernel(const float* __restrict__ prob, const float* __restrict__ ends, int D, int h, int w,
                                      int depth_inv, float* __restrict__ depth_out, float* __restrict__ std_out,
                                      float* __restrict__ mvs_out, int x0, int y0, int wc, int hc) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,6 +178,73 @@ __global__ void depth_regress_kernel(const float* __restrict__ prob, const float
   std_out[pix] = sqrtf(fmaxf(var, 1e-10f));
   if (mvs_out) mvs_out[pix] = depth_inv ? 1.0f / mean : mean;
 #undef PROB_AT
+}
+
+// 8 lanes share a pixel and split the D planes (lane j takes d = j, j+8, ...): the level-0 map has only
+// 5,120 pixels, one thread per pixel left 128 of the 148 SMs idle for 25 us on the frame's critical path.
+// softmax over D, E[v], std: four width-8 shuffle reductions (max, sum, mean, variance).
+__global__ void __launch_bounds__(256) depth_regress_kernel(const float* __restrict__ prob, const float* __restrict__ ends, int D,
+                                                            int h, int w, int depth_inv, float* __restrict__ depth_out,
+                                                            float* __restrict__ std_out, float* __restrict__ mvs_out, int x0, int y0,
+                                                            int wc, int hc) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sub = gid & 7;
+  const int pix = min(gid >> 3, h * w - 1);       // surplus groups of the last block redo the last pixel (all lanes stay in the shuffles)
+  const float a = ends[pix], b = ends[(size_t)h * w + pix];
+  // prob covers the window [x0,x0+wc) x [y0,y0+hc) and is zero-padded to the h x w grid
+  // (network_composite.py:102: F.pad(depth_prob)); outside, softmax of zeros = uniform
+  const int lx = pix % w - x0, ly = pix / w - y0;
+  const bool inside = lx >= 0 && lx < wc && ly >= 0 && ly < hc;
+  const int hw = wc * hc;
+  prob += inside ? ly * wc + lx : 0;
+  auto red_max = [](float v) {
+    for (int o = 4; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  };
+  auto red_sum = [](float v) {
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  constexpr int MAXP = 16;                         // planes per lane held in registers (D <= 128)
+  float pv[MAXP], vv[MAXP];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i) {
+    const int d = sub + 8 * i;
+    pv[i] = (d < D) ? (inside ? __ldg(prob + (size_t)d * hw) : 0.f) : -INFINITY;
+    mx = fmaxf(mx, pv[i]);
+  }
+  mx = red_max(mx);
+  float den = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i) {
+    const int d = sub + 8 * i;
+    pv[i] = (d < D) ? expf(pv[i] - mx) : 0.f;
+    den += pv[i];
+    float v = plane_depth(a, b, min(d, D - 1), D, depth_inv);
+    if (depth_inv) v = 1.0f / fmaxf(v, 1e-6f);
+    vv[i] = v;
+  }
+  den = red_sum(den);
+  float mean = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i) {
+    pv[i] = pv[i] / den;
+    mean += pv[i] * vv[i];
+  }
+  mean = red_sum(mean);
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i) {
+    const float e = vv[i] - mean;
+    var += pv[i] * (e * e);
+  }
+  var = red_sum(var);
+  if (sub == 0 && (gid >> 3) < h * w) {
+    depth_out[pix] = mean;
+    std_out[pix] = sqrtf(fmaxf(var, 1e-10f));
+    if (mvs_out) mvs_out[pix] = depth_inv ? 1.0f / mean : mean;
+  }
 }
 
 }  // namespace enerf
@@ -250,8 +318,13 @@ extern "C" int enerf_depth_regress(const float* depth_prob, const float* ends, i
                                    float* depth, float* std, float* depth_mvs, void* stream) {
   using namespace enerf;
   ENERF_REQUIRE(depth_prob && ends && depth && std, ENERF_EINVAL, "depth_regress: null pointer");
-  depth_regress_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
-                                                                              depth_mvs, 0, 0, w, h);
+  ENERF_REQUIRE(D >= 1 && D <= 128, ENERF_EUNSUPPORTED, "depth_regress: D=%d not in [1,128]", D);
+  if (h * w >= 148 * 256)
+    depth_regress_px_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
+                                                                                   depth_mvs, 0, 0, w, h);
+  else
+    depth_regress_kernel<<<ceil_div(h * w * 8, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
+                                                                                    depth_mvs, 0, 0, w, h);
   ENERF_CHECK_LAUNCH("depth_regress");
   return ENERF_OK;
 }
@@ -260,11 +333,16 @@ extern "C" int enerf_depth_regress_window(const float* depth_prob, const int* wi
                                           int depth_inv, float* depth, float* std, float* depth_mvs, void* stream) {
   using namespace enerf;
   ENERF_REQUIRE(depth_prob && window && ends && depth && std, ENERF_EINVAL, "depth_regress_window: null pointer");
+  ENERF_REQUIRE(D >= 1 && D <= 128, ENERF_EUNSUPPORTED, "depth_regress_window: D=%d not in [1,128]", D);
   const int x0 = window[0], y0 = window[1], wc = window[2], hc = window[3];
   ENERF_REQUIRE(x0 >= 0 && y0 >= 0 && wc > 0 && hc > 0 && x0 + wc <= w && y0 + hc <= h, ENERF_EINVAL,
                 "depth_regress_window: window (%d,%d,%d,%d) outside the %dx%d grid", x0, y0, wc, hc, w, h);
-  depth_regress_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
-                                                                              depth_mvs, x0, y0, wc, hc);
+  if (h * w >= 148 * 256)
+    depth_regress_px_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
+                                                                                   depth_mvs, x0, y0, wc, hc);
+  else
+    depth_regress_kernel<<<ceil_div(h * w * 8, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
+                                                                                    depth_mvs, x0, y0, wc, hc);
   ENERF_CHECK_LAUNCH("depth_regress_window");
   return ENERF_OK;
 }
