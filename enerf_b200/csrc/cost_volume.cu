@@ -58,16 +58,16 @@ __global__ void depth_hypotheses_kernel(const EnerfCam* __restrict__ cam, const 
   nf_out[(size_t)h * w + pix] = v1;
 }
 
-// thread = (voxel, half of the channels): the homography, the perspective divide and the bilinear
-// weights are computed once per view and applied to C/2 channels (C/8 float4 accumulator pairs).
-// Two lanes share a voxel and read adjacent halves of the same source pixel record.
-template <int C>
+// thread = (voxel, C/SPLIT channels): the homography, the perspective divide and the bilinear weights
+// are computed once per view and applied to the thread's float4 slices of the four taps; the SPLIT
+// lanes of a voxel read adjacent slices of the same source pixel record.
+template <int C, int SPLIT>
 __global__ void __launch_bounds__(256) cost_volume_kernel(const EnerfCam* __restrict__ cam, int level,
                                                           const float* __restrict__ feat, int S, int hs, int ws,
                                                           const float* __restrict__ ends, int D, int h, int w,
                                                           int depth_inv, float* __restrict__ var_out, int x0, int y0, int wc,
                                                           int hc) {
-  constexpr int SPLIT = (C >= 16) ? 2 : 1;         // lanes per voxel
+  // SPLIT lanes share a voxel, each owning C/SPLIT channels of every tap
   constexpr int CH = C / SPLIT;                    // channels per thread
   constexpr int NV = CH / 4;                       // float4 per tap per thread
   __shared__ float Hm[ENERF_MAX_VIEWS * 12];
@@ -75,12 +75,13 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const EnerfCam* __rest
   __syncthreads();
   // the volume covers the window [x0,x0+wc) x [y0,y0+hc) of the h x w target grid (the whole grid
   // for enerf_cost_volume; a layer's bbox for enerf_cost_volume_window, utils.py:284-289)
-  const long long total = (long long)D * hc * wc * SPLIT;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = (unsigned)D * hc * wc * SPLIT;      // 32-bit index math (the launcher checks the range)
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int g = (int)(t % SPLIT);
-  const long long vox = t / SPLIT;
-  const int x = x0 + (int)(vox % wc), y = y0 + (int)((vox / wc) % hc), d = (int)(vox / ((long long)wc * hc));
+  const unsigned vox = t / SPLIT;
+  const unsigned vrow = vox / (unsigned)wc;
+  const int x = x0 + (int)(vox - vrow * wc), y = y0 + (int)(vrow % (unsigned)hc), d = (int)(vrow / (unsigned)hc);
   const int pix = y * w + x;
   const float depth = plane_depth(__ldg(ends + pix), __ldg(ends + (size_t)h * w + pix), d, D, depth_inv);
   const float inv_depth = 1.0f / depth;
@@ -302,14 +303,21 @@ static int cost_volume_launch(const EnerfCam* cam, int level, const float* feat,
   ENERF_REQUIRE(cam && feat && ends && variance, ENERF_EINVAL, "cost_volume: null pointer");
   ENERF_REQUIRE(level >= 0 && level < ENERF_MAX_LEVELS, ENERF_EINVAL, "cost_volume: level %d", level);
   ENERF_REQUIRE(S >= 1 && S <= ENERF_MAX_VIEWS, ENERF_EINVAL, "cost_volume: n_views %d not in [1,%d]", S, ENERF_MAX_VIEWS);
-  const long long total = (long long)D * hc * wc * (C >= 16 ? 2 : 1);
+  // lanes per voxel (measured A/B at the headline sizes): C = 32: 8 lanes, one float4 of every tap each, so a
+  // warp instruction reads whole 128 B source records (67 -> 54 us); C = 16: 2 lanes (4 lanes: 53 -> 68 us)
+  const int split = (C == 32) ? 8 : (C >= 16 ? 2 : 1);
+  const long long total = (long long)D * hc * wc * split;
+  ENERF_REQUIRE(total < (1ll << 31), ENERF_EUNSUPPORTED, "cost_volume: %lld work items exceed the 32-bit index range", total);
   const unsigned blocks = (unsigned)((total + 255) / 256);
-  switch (C) {
-    case 8: cost_volume_kernel<8><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance, x0, y0, wc, hc); break;
-    case 16: cost_volume_kernel<16><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance, x0, y0, wc, hc); break;
-    case 32: cost_volume_kernel<32><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance, x0, y0, wc, hc); break;
-    default: ENERF_REQUIRE(false, ENERF_EUNSUPPORTED, "cost_volume: C=%d not in {8,16,32}", C);
-  }
+#define CV_LAUNCH(C_, SP_) cost_volume_kernel<C_, SP_><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance, x0, y0, wc, hc)
+  if (C == 8 && split == 2) CV_LAUNCH(8, 2);
+  else if (C == 8) CV_LAUNCH(8, 1);
+  else if (C == 16 && split == 4) CV_LAUNCH(16, 4);
+  else if (C == 16) CV_LAUNCH(16, 2);
+  else if (C == 32 && split == 8) CV_LAUNCH(32, 8);
+  else if (C == 32) CV_LAUNCH(32, 2);
+  else ENERF_REQUIRE(false, ENERF_EUNSUPPORTED, "cost_volume: C=%d not in {8,16,32}", C);
+#undef CV_LAUNCH
   ENERF_CHECK_LAUNCH("cost_volume");
   return ENERF_OK;
 }

@@ -19,7 +19,9 @@ using Smooth1 = ConvTraits<32, 16, 1, 3, 1, 1, 32, 32, 2, 4, 8, 8, false, false>
 using Smooth0 = ConvTraits<32, 8, 1, 3, 1, 1, 32, 32, 2, 4, 8, 8, false, false>;
 
 // out (N,H,W,32) = bias + W[CIN][32] . lat_in (N,H,W,CIN)  +  bilinear_x2(up_in (N,H/2,W/2,32))
-// thread = (pixel, group of 8 output channels)
+// thread = (pixel, g): output channels [4g, 4g+4) and [16+4g, 16+4g+4), i.e. float4 slices g and g+4 of the
+// 32-channel record -- the four lanes of a pixel then read / write 64 contiguous bytes per instruction
+// (two full sectors) instead of four half-used ones: the kernel is L1-throughput bound (ncu: l1tex 82 %)
 template <int CIN>
 __global__ void __launch_bounds__(256) lateral_upadd_kernel(const float* __restrict__ lat_in, const float* __restrict__ w,
                                                             const float* __restrict__ bias, const float* __restrict__ up_in,
@@ -29,26 +31,26 @@ __global__ void __launch_bounds__(256) lateral_upadd_kernel(const float* __restr
   for (int e = threadIdx.x; e < CIN * 32; e += blockDim.x) w_s[e] = w[e];
   if (threadIdx.x < 32) b_s[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
-  const long long total = (long long)N * H * W * 4;
-  const int hi = H / 2, wi = W / 2;
+  const int total = N * H * W * 4;          // 32-bit index math (launcher checks the range): 64-bit div/mod per thread
+  const int hi = H / 2, wi = W / 2;         // was 2/3 of this kernel's instructions
   const float rh = (H > 1) ? (float)(hi - 1) / (float)(H - 1) : 0.f;
   const float rw = (W > 1) ? (float)(wi - 1) / (float)(W - 1) : 0.f;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(t & 3);
-    const long long pix = t >> 2;
-    const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int g = t & 3;
+    const int pix = t >> 2;
+    const int x = pix % W, row = pix / W, y = row % H, n = row / H;
     float acc[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = b_s[g * 8 + c];
-    const float* ip = lat_in + pix * CIN;
+    for (int c = 0; c < 8; ++c) acc[c] = b_s[(c < 4 ? 0 : 12) + g * 4 + c];
+    const float* ip = lat_in + (size_t)pix * CIN;
 #pragma unroll
     for (int q = 0; q < CIN / 4; ++q) {
       const float4 v = ldg4(ip + 4 * q);
       const float xv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 w0 = *reinterpret_cast<const float4*>(w_s + (4 * q + j) * 32 + g * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(w_s + (4 * q + j) * 32 + g * 8 + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(w_s + (4 * q + j) * 32 + g * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(w_s + (4 * q + j) * 32 + 16 + g * 4);
         acc[0] = fmaf(xv[j], w0.x, acc[0]);
         acc[1] = fmaf(xv[j], w0.y, acc[1]);
         acc[2] = fmaf(xv[j], w0.z, acc[2]);
@@ -64,35 +66,35 @@ __global__ void __launch_bounds__(256) lateral_upadd_kernel(const float* __restr
     const int h1 = (int)h1r, w1 = (int)w1r;
     const int h1p = (h1 < hi - 1) ? 1 : 0, w1p = (w1 < wi - 1) ? 1 : 0;
     const float h1l = h1r - (float)h1, h0l = 1.f - h1l, w1l = w1r - (float)w1, w0l = 1.f - w1l;
-    const float* u00 = up_in + (((size_t)n * hi + h1) * wi + w1) * 32 + g * 8;
+    const float* u00 = up_in + (((size_t)n * hi + h1) * wi + w1) * 32 + g * 4;
     const float* u01 = u00 + (size_t)w1p * 32;
     const float* u10 = u00 + (size_t)h1p * wi * 32;
     const float* u11 = u10 + (size_t)w1p * 32;
     float up[8];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      const float4 a = ldg4(u00 + 4 * q), b = ldg4(u01 + 4 * q), c = ldg4(u10 + 4 * q), dd = ldg4(u11 + 4 * q);
+      const float4 a = ldg4(u00 + 16 * q), b = ldg4(u01 + 16 * q), c = ldg4(u10 + 16 * q), dd = ldg4(u11 + 16 * q);
       up[4 * q + 0] = h0l * (w0l * a.x + w1l * b.x) + h1l * (w0l * c.x + w1l * dd.x);
       up[4 * q + 1] = h0l * (w0l * a.y + w1l * b.y) + h1l * (w0l * c.y + w1l * dd.y);
       up[4 * q + 2] = h0l * (w0l * a.z + w1l * b.z) + h1l * (w0l * c.z + w1l * dd.z);
       up[4 * q + 3] = h0l * (w0l * a.w + w1l * b.w) + h1l * (w0l * c.w + w1l * dd.w);
     }
-    float4* o = reinterpret_cast<float4*>(out + pix * 32 + g * 8);
+    float4* o = reinterpret_cast<float4*>(out + (size_t)pix * 32 + g * 4);
     // reference order: interpolate(x) + lateral(y)   (feature_net.py:25)
     o[0] = make_float4(up[0] + acc[0], up[1] + acc[1], up[2] + acc[2], up[3] + acc[3]);
-    o[1] = make_float4(up[4] + acc[4], up[5] + acc[5], up[6] + acc[6], up[7] + acc[7]);
+    o[4] = make_float4(up[4] + acc[4], up[5] + acc[5], up[6] + acc[6], up[7] + acc[7]);
   }
 }
 
 // cat(feat, unpreprocess(src)) -> (S,Hr,Wr,C+4); thread per output pixel
 __global__ void pack_img_feat_kernel(const float* __restrict__ feat, int C, const float* __restrict__ src, int S, int H,
                                      int W, int Hr, int Wr, float* __restrict__ out) {
-  const long long total = (long long)S * Hr * Wr;
+  const int total = S * Hr * Wr;            // 32-bit index math (launcher checks the range)
   const int CP = C + 4;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(t % Wr), y = (int)((t / Wr) % Hr), s = (int)(t / ((long long)Wr * Hr));
-    const float* f = feat + t * C;
-    float* o = out + t * CP;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int x = t % Wr, row = t / Wr, y = row % Hr, s = row / Hr;
+    const float* f = feat + (size_t)t * C;
+    float* o = out + (size_t)t * CP;
     for (int q = 0; q < C / 4; ++q) reinterpret_cast<float4*>(o)[q] = ldg4(f + 4 * q);
     float rgb[3];
     for (int c = 0; c < 3; ++c) {
@@ -158,6 +160,7 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
   cudaStream_t stream = (cudaStream_t)stream_;
   ENERF_REQUIRE(wts && n_weights == 22, ENERF_EINVAL, "feature_net: expected 22 weight pointers, got %d", n_weights);
   ENERF_REQUIRE(src_inps && feat_l0 && feat_l1 && feat_l2 && workspace, ENERF_EINVAL, "feature_net: null pointer");
+  ENERF_REQUIRE((long long)S * H * W * 4 < (1ll << 31), ENERF_EUNSUPPORTED, "feature_net: %d x %d x %d exceeds the 32-bit index range", S, H, W);
   ENERF_REQUIRE(S >= 1 && H > 0 && W > 0 && H % 4 == 0 && W % 4 == 0, ENERF_EINVAL,
                 "feature_net: H=%d W=%d must be positive multiples of 4 (S=%d)", H, W, S);
   FeatWs ws = carve(workspace, S, H, W);
@@ -238,6 +241,7 @@ extern "C" int enerf_pack_img_feat(const float* feat, int C, const float* src_in
   using namespace enerf;
   ENERF_REQUIRE(feat && src_inps && out, ENERF_EINVAL, "pack_img_feat: null pointer");
   ENERF_REQUIRE(C % 4 == 0 && C > 0, ENERF_EINVAL, "pack_img_feat: C=%d must be a multiple of 4", C);
+  ENERF_REQUIRE((long long)S * Hr * Wr < (1ll << 31), ENERF_EUNSUPPORTED, "pack_img_feat: frame too large for 32-bit indices");
   const long long total = (long long)S * Hr * Wr;
   const int blocks = (int)((total + 255) / 256);
   pack_img_feat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(feat, C, src_inps, S, H, W, Hr, Wr, out);
