@@ -184,6 +184,7 @@ __global__ void depth_regress_px_kernel(const float* __restrict__ prob, const fl
 // 8 lanes share a pixel and split the D planes (lane j takes d = j, j+8, ...): the level-0 map has only
 // 5,120 pixels, one thread per pixel left 128 of the 148 SMs idle for 25 us on the frame's critical path.
 // softmax over D, E[v], std: four width-8 shuffle reductions (max, sum, mean, variance).
+template <int MAXP>   // planes per lane held in registers: D <= 8 * MAXP
 __global__ void __launch_bounds__(256) depth_regress_kernel(const float* __restrict__ prob, const float* __restrict__ ends, int D,
                                                             int h, int w, int depth_inv, float* __restrict__ depth_out,
                                                             float* __restrict__ std_out, float* __restrict__ mvs_out, int x0, int y0,
@@ -206,7 +207,6 @@ __global__ void __launch_bounds__(256) depth_regress_kernel(const float* __restr
     for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   };
-  constexpr int MAXP = 16;                         // planes per lane held in registers (D <= 128)
   float pv[MAXP], vv[MAXP];
   float mx = -INFINITY;
 #pragma unroll
@@ -330,9 +330,12 @@ extern "C" int enerf_depth_regress(const float* depth_prob, const float* ends, i
   if (h * w >= 148 * 256)
     depth_regress_px_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
                                                                                    depth_mvs, 0, 0, w, h);
+  else if (D <= 64)
+    depth_regress_kernel<8><<<ceil_div(h * w * 8, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
+                                                                                       depth_mvs, 0, 0, w, h);
   else
-    depth_regress_kernel<<<ceil_div(h * w * 8, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
-                                                                                    depth_mvs, 0, 0, w, h);
+    depth_regress_kernel<16><<<ceil_div(h * w * 8, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
+                                                                                        depth_mvs, 0, 0, w, h);
   ENERF_CHECK_LAUNCH("depth_regress");
   return ENERF_OK;
 }
@@ -348,9 +351,12 @@ extern "C" int enerf_depth_regress_window(const float* depth_prob, const int* wi
   if (h * w >= 148 * 256)
     depth_regress_px_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
                                                                                    depth_mvs, x0, y0, wc, hc);
+  else if (D <= 64)
+    depth_regress_kernel<8><<<ceil_div(h * w * 8, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
+                                                                                       depth_mvs, x0, y0, wc, hc);
   else
-    depth_regress_kernel<<<ceil_div(h * w * 8, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
-                                                                                    depth_mvs, x0, y0, wc, hc);
+    depth_regress_kernel<16><<<ceil_div(h * w * 8, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
+                                                                                        depth_mvs, x0, y0, wc, hc);
   ENERF_CHECK_LAUNCH("depth_regress_window");
   return ENERF_OK;
 }

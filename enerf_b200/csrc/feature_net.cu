@@ -35,6 +35,17 @@ __global__ void __launch_bounds__(256) lateral_upadd_kernel(const float* __restr
   const int hi = H / 2, wi = W / 2;         // was 2/3 of this kernel's instructions
   const float rh = (H > 1) ? (float)(hi - 1) / (float)(H - 1) : 0.f;
   const float rw = (W > 1) ? (float)(wi - 1) / (float)(W - 1) : 0.f;
+  // the shared-memory weight reads were a third of the L1 data-pipe wavefronts of the full-resolution
+  // instance (ncu): with 4 pixels per thread (the launch's grid-stride) the CIN = 8 slice is read once
+  float4 wreg[CIN == 8 ? 16 : 1];
+  if constexpr (CIN == 8) {
+    const int g0 = threadIdx.x & 3;        // == t & 3 for every t of this thread (the stride is a multiple of 4)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      wreg[2 * k] = *reinterpret_cast<const float4*>(w_s + k * 32 + g0 * 4);
+      wreg[2 * k + 1] = *reinterpret_cast<const float4*>(w_s + k * 32 + 16 + g0 * 4);
+    }
+  }
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const int g = t & 3;
     const int pix = t >> 2;
@@ -49,8 +60,13 @@ __global__ void __launch_bounds__(256) lateral_upadd_kernel(const float* __restr
       const float xv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 w0 = *reinterpret_cast<const float4*>(w_s + (4 * q + j) * 32 + g * 4);
-        const float4 w1 = *reinterpret_cast<const float4*>(w_s + (4 * q + j) * 32 + 16 + g * 4);
+        float4 w0, w1;
+        if constexpr (CIN == 8) {   // this thread's 8 x 8 weight slice lives in registers (g is loop-invariant)
+          w0 = wreg[2 * (4 * q + j)], w1 = wreg[2 * (4 * q + j) + 1];
+        } else {
+          w0 = *reinterpret_cast<const float4*>(w_s + (4 * q + j) * 32 + g * 4);
+          w1 = *reinterpret_cast<const float4*>(w_s + (4 * q + j) * 32 + 16 + g * 4);
+        }
         acc[0] = fmaf(xv[j], w0.x, acc[0]);
         acc[1] = fmaf(xv[j], w0.y, acc[1]);
         acc[2] = fmaf(xv[j], w0.z, acc[2]);
@@ -221,7 +237,7 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
   }
   {
     const long long total = (long long)S * H * W * 4;
-    const int blocks = (int)((total + 255) / 256);
+    const int blocks = (int)((total + 1023) / 1024);     // 4 (pixel, slice) items per thread
     lateral_upadd_kernel<8><<<blocks, 256, 0, stream>>>(ws.c0, wts[16], wts[17], ws.f1, ws.f0, S, H, W);
     ENERF_CHECK_LAUNCH("feature_net.lat0");
   }
