@@ -17,6 +17,7 @@ struct TcConvParams {
   int n_taps;
   int tap_off[27];       // operand start offsets in 16-byte units: phase*(2*npix) + linear pixel offset
   int n_stages;          // Cin / 8
+  int n_slots;           // K-stages resident in shared memory at once (ring depth)
   int N;                 // MMA N (multiple of 16, <= 256)
   int n_mt;              // 128-row M-tiles per CTA
   int cout;              // real channels (per parity for TC_DECONV)
@@ -71,7 +72,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int NTAPS, int MODE, int FOLD>
 __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ in, int cin, const TcConvParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], done_bar;
+  __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], done_bar;
   __shared__ uint32_t tmem_base_s;
   const int t = threadIdx.x, warp = t >> 5;
   unsigned long long* dbg = (g_tc_dbg && t == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_tc_dbg : nullptr;
@@ -82,13 +83,13 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
   const uint32_t w_bytes = (uint32_t)NTAPS * (uint32_t)P.N * 32u;
   const uint32_t stage_bytes = (a_bytes + w_bytes + 127u) & ~127u;
   unsigned char* stage0 = smem_raw;
-  int* pix_off = reinterpret_cast<int*>(smem_raw + (size_t)(P.n_stages > 1 ? 2 : 1) * stage_bytes);   // [npix_tot] input pixel or -1
+  int* pix_off = reinterpret_cast<int*>(smem_raw + (size_t)P.n_slots * stage_bytes);   // [npix_tot] input pixel or -1
 
   if (t == 0) {
-    tc::mbar_init(&full_bar[0], 129);   // 128 copier threads + the weight copy's expect_tx arrival
-    tc::mbar_init(&full_bar[1], 129);
-    tc::mbar_init(&empty_bar[0], 1);
-    tc::mbar_init(&empty_bar[1], 1);
+    for (int i = 0; i < 4; ++i) {
+      tc::mbar_init(&full_bar[i], 129);   // 128 copier threads + the weight copy's expect_tx arrival
+      tc::mbar_init(&empty_bar[i], 1);
+    }
     tc::mbar_init(&done_bar, 1);
     tc::fence_mbar_init();
   }
@@ -111,8 +112,9 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
   const uint32_t tmem = tmem_base_s;
   TC_STAMP(1);
 
+  const int NS = P.n_slots;     // ring depth: min(n_stages, 2 or 4) K-stages resident at once
   auto issue_stage = [&](int st) {
-    const int slot = st & 1;
+    const int slot = st % NS;
     unsigned char* sa = stage0 + (size_t)slot * stage_bytes;
     if (t == 32) {
       tc::mbar_expect_tx(&full_bar[slot], w_bytes);
@@ -130,15 +132,21 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
     cp_async_commit();
   };
 
-  issue_stage(0);
-  if (P.n_stages > 1) issue_stage(1);
+  for (int st = 0; st < NS; ++st) issue_stage(st);
   TC_STAMP(2);
   const uint32_t idesc = tc::idesc_tf32(128, P.N);
   const uint32_t lbo_a = (uint32_t)npix * 16u, lbo_b = (uint32_t)P.N * 16u;
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform copy of the TMEM base
   for (int st = 0; st < P.n_stages; ++st) {
-    const int slot = st & 1;
-    if (st + 1 < P.n_stages) cp_async_wait<1>(); else cp_async_wait<0>();
+    const int slot = st % NS;
+    const uint32_t par = (uint32_t)((st / NS) & 1);
+    {   // copy groups are committed in stage order: allow the ones issued after stage st to stay in flight
+      const int later = min(P.n_stages, st + NS) - st - 1;
+      if (later >= 3) cp_async_wait<3>();
+      else if (later == 2) cp_async_wait<2>();
+      else if (later == 1) cp_async_wait<1>();
+      else cp_async_wait<0>();
+    }
     TC_STAMP(4 + 6 * st);                         // my copies of this stage have landed
     tc::fence_proxy_async();                      // my copies -> visible to the tensor core
     mbar_arrive(&full_bar[slot]);
@@ -146,7 +154,7 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
     // MMA issue: the whole warp 0, converged, warp-uniform operands, one elected lane issues
     // (tc::mma_tf32_elect).  Lanes never spin next to a divergent issuer.
     if (warp == 0) {
-      tc::mbar_wait(&full_bar[slot], (uint32_t)((st >> 1) & 1));
+      tc::mbar_wait(&full_bar[slot], par);
       TC_STAMP(6 + 6 * st);                       // everyone's copies + weights visible
       tc::tc_fence_after_sync();
       const uint32_t sa = tc::smem_u32(stage0 + (size_t)slot * stage_bytes);
@@ -165,10 +173,10 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
       TC_STAMP(7 + 6 * st);                       // MMAs of this stage issued
       __syncwarp();
     }
-    if (st + 2 < P.n_stages) {
-      tc::mbar_wait(&empty_bar[slot], (uint32_t)((st >> 1) & 1));
+    if (st + NS < P.n_stages) {
+      tc::mbar_wait(&empty_bar[slot], par);
       TC_STAMP(8 + 6 * st);                       // MMAs of this stage complete (slot free)
-      issue_stage(st + 2);
+      issue_stage(st + NS);
       TC_STAMP(9 + 6 * st);
     }
   }
@@ -395,6 +403,10 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
   if (P.TY > Hn) P.TY = Hn;
   size_t smem = 0;
   uint32_t stage_bytes = 0;
+  // ring depth: 2 K-stages.  (The kernel supports up to 4; with 4 every stage of a Cin <= 32 layer is in flight
+  // from the start and no slot is recycled, but the larger footprint halves the co-resident CTAs:
+  // measured 911 -> 867 FPS, FeatureNet 0.44 -> 0.48 ms.)
+  const int slots_max = 2;
   for (;;) {
     P.IZ = P.TZ + hz, P.IY = P.TY + hy, P.IX = P.TX + hx;
     const int pmax = ((P.TZ - 1) * P.IY + (P.TY - 1)) * P.IX + P.TX - 1;
@@ -432,7 +444,9 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
     stage_bytes = ((uint32_t)npix_tot * 32u + (uint32_t)P.n_taps * (uint32_t)P.N * 32u + 127u) & ~127u;
     // [stage 0][stage 1][pixel table][tail]: the dropped garbage rows of the last M-tile may read past
     // the end of a phase block; keep those reads inside the allocation
-    smem = (size_t)(P.n_stages > 1 ? 2 : 1) * stage_bytes + (size_t)npix_tot * 4 + 64 + (size_t)(P.n_mt * 128 + 64) * 16;
+    P.n_slots = std::min(P.n_stages, slots_max);
+    if ((size_t)P.n_slots * stage_bytes > 96 * 1024) P.n_slots = std::min(P.n_stages, 2);   // wide-N layers: weights alone fill the ring
+    smem = (size_t)P.n_slots * stage_bytes + (size_t)npix_tot * 4 + 64 + (size_t)(P.n_mt * 128 + 64) * 16;
     const long long n_cta = (long long)ceil_div(Wn, P.TX) * ceil_div(Hn, P.TY) * ceil_div(Dn, P.TZ);
     if (fold) smem = std::max(smem, (size_t)(P.n_mt * 4 + 1) * 2 * P.N * 4 + 128);   // epilogue row exchange reuses the stage buffers
     const bool fits = P.n_mt * P.N <= 512 && smem <= 200 * 1024;
