@@ -326,8 +326,8 @@ extern "C" int enerf_depth_regress(const float* depth_prob, const float* ends, i
                                    float* depth, float* std, float* depth_mvs, void* stream) {
   using namespace enerf;
   ENERF_REQUIRE(depth_prob && ends && depth && std, ENERF_EINVAL, "depth_regress: null pointer");
-  ENERF_REQUIRE(D >= 1 && D <= 128, ENERF_EUNSUPPORTED, "depth_regress: D=%d not in [1,128]", D);
-  if (h * w >= 148 * 256)
+  ENERF_REQUIRE(D >= 1, ENERF_EINVAL, "depth_regress: D=%d", D);
+  if (h * w >= 148 * 256 || D > 128)     // large maps, or more planes than the 8-lane kernel holds in registers
     depth_regress_px_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
                                                                                    depth_mvs, 0, 0, w, h);
   else if (D <= 64)
@@ -344,11 +344,11 @@ extern "C" int enerf_depth_regress_window(const float* depth_prob, const int* wi
                                           int depth_inv, float* depth, float* std, float* depth_mvs, void* stream) {
   using namespace enerf;
   ENERF_REQUIRE(depth_prob && window && ends && depth && std, ENERF_EINVAL, "depth_regress_window: null pointer");
-  ENERF_REQUIRE(D >= 1 && D <= 128, ENERF_EUNSUPPORTED, "depth_regress_window: D=%d not in [1,128]", D);
+  ENERF_REQUIRE(D >= 1, ENERF_EINVAL, "depth_regress_window: D=%d", D);
   const int x0 = window[0], y0 = window[1], wc = window[2], hc = window[3];
   ENERF_REQUIRE(x0 >= 0 && y0 >= 0 && wc > 0 && hc > 0 && x0 + wc <= w && y0 + hc <= h, ENERF_EINVAL,
                 "depth_regress_window: window (%d,%d,%d,%d) outside the %dx%d grid", x0, y0, wc, hc, w, h);
-  if (h * w >= 148 * 256)
+  if (h * w >= 148 * 256 || D > 128)
     depth_regress_px_kernel<<<ceil_div(h * w, 256), 256, 0, (cudaStream_t)stream>>>(depth_prob, ends, D, h, w, depth_inv, depth, std,
                                                                                    depth_mvs, x0, y0, wc, hc);
   else if (D <= 64)

@@ -133,3 +133,36 @@ def test_composite_state_dict_and_packing_match_reference_golden():
     assert tuple(pn[8].shape) == (24, 64) and tuple(pn[12].shape) == (103, 64)
     assert pn[8][:8].abs().max() == 0 and pn[12][64:72].abs().max() == 0
     assert torch.equal(pn[8][8:], sd["nerf_1_bg.lr0.0.weight"].t()) and torch.equal(pn[12][72:], sd["nerf_1_bg.color.0.weight"].t()[64:])
+
+
+def test_folded_tc_conv_packing_is_a_shifted_sum_of_partial_convolutions():
+    """packing.pack_tc_conv(fold_kx=True) (the layout csrc/tc_conv.cu consumes for the 3-D layers with 8
+    or 1 output channels): un-packing it and evaluating  out[x] = sum_kx P[x + kx][kx]  with
+    P[x][kx] = sum_{kz,ky,c} in[z+kz-1, y+ky-1, x-1][c] * W[kz][ky][kx][c]  reproduces conv3d -- the
+    identity the kernel's epilogue relies on (two lane shifts)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    cin, cout, D, H, W = 16, 8, 3, 5, 7
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g)
+    x = torch.randn(1, cin, D, H, W, generator=g)
+    assert packing.tc_fold_kx(3, 3, 1, cout) and not packing.tc_fold_kx(3, 3, 2, cout) and not packing.tc_fold_kx(1, 3, 1, cout)
+    assert packing.tc_fold_kx(3, 3, 1, 1, single=True) and not packing.tc_fold_kx(3, 3, 1, 9)
+    taps = packing._taps_cin_cout(w)                                   # [27][cin][cout], taps ordered (kz,ky,kx)
+    packed = packing.pack_tc_conv(taps, fold_kx=True)
+    N = 32                                                             # 3 * 8 = 24 padded to 16-multiples
+    assert packed.numel() == (cin // 8) * 9 * 2 * N * 4
+    # [cin/8][tap_zy][2][N][4] -> [tap_zy][cin][N]
+    wz = packed.view(cin // 8, 9, 2, N, 4).permute(1, 0, 2, 4, 3).reshape(9, cin, N)
+    assert wz[:, :, 24:].abs().max() == 0
+    ref_w = packing.tf32_round(taps.float()).view(9, 3, cin, cout)
+    assert torch.equal(wz[:, :, :24].reshape(9, cin, 3, cout).permute(0, 2, 1, 3), ref_w)
+    # partial convolutions over (kz,ky) only, evaluated at input column x-1 (zero padded), then the shifted sum
+    xp = F.pad(x[0].permute(1, 2, 3, 0), (0, 0, 1, 3, 1, 1, 1, 1))     # (D+2, H+2, W+4, cin): x index i <-> column i-1
+    P = torch.zeros(D, H, W + 2, 3, cout)
+    for kz in range(3):
+        for ky in range(3):
+            blk = xp[kz:kz + D, ky:ky + H, 0:W + 2]                    # column j holds in[.., .., j-1]
+            P += torch.einsum("zyxc,ckn->zyxkn", blk, wz[kz * 3 + ky, :, :24].reshape(cin, 3, cout))
+    out = sum(P[:, :, kx:kx + W, kx] for kx in range(3))               # out[x] = sum_kx P[x+kx][kx]
+    ref = F.conv3d(x, packing.tf32_round(w), None, 1, 1)[0].permute(1, 2, 3, 0)
+    assert (out - ref).abs().max().item() < 1e-4
