@@ -60,6 +60,8 @@ _SIGS = {
     "enerf_tc_mma_bench": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "enerf_render_rays_debug": (_i, [_vp]),
     "enerf_tc_selftest": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "enerf_tc_swz_selftest": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "enerf_tma_box_bench": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -245,6 +247,16 @@ def tc_conv_tune(tz=0, ty=0, fold=-1):
 def tc_selftest(A, B, D):
     """D[128,N] = A[128,K] @ B[N,K]^T on tcgen05 (TF32 operands, fp32 accumulate in TMEM)."""
     _check(lib().enerf_tc_selftest(ptr(A), ptr(B), A.shape[1], B.shape[0], ptr(D), stream()), "enerf_tc_selftest")
+
+
+def tc_swz_selftest(A, B, D, row_off, bo_mode):
+    """D[128,N] = A[row_off:row_off+128] @ B^T with A staged by a swizzled TMA box (see enerf_b200.h)."""
+    _check(lib().enerf_tc_swz_selftest(ptr(A), A.shape[0], A.shape[1], ptr(B), B.shape[0], row_off, bo_mode, ptr(D), stream()), "enerf_tc_swz_selftest")
+
+
+def tma_box_bench(x, tx, ty, tz, depth, iters, grid, sink):
+    Dd, H, W, C = x.shape
+    _check(lib().enerf_tma_box_bench(ptr(x), Dd, H, W, C, tx, ty, tz, depth, iters, grid, ptr(sink), stream()), "enerf_tma_box_bench")
 
 
 def render_rays_tc(cam, level, wblob, rays, depth, std, near_far, feat_vol, img_feat_rgb, feat_ch, num_samples, depth_inv,

@@ -28,6 +28,26 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are PER DEVICE: a process that
+// drives several GPUs (net.to('cuda:1'), one thread per device) must set / query them on each.
+constexpr int ENERF_MAX_DEVICES = 64;
+struct PerDeviceSize {
+  size_t v[ENERF_MAX_DEVICES] = {};
+  size_t& cur() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return v[(d >= 0 && d < ENERF_MAX_DEVICES) ? d : 0];
+  }
+};
+static inline int device_sm_count() {
+  static int n[ENERF_MAX_DEVICES] = {};
+  int d = 0;
+  cudaGetDevice(&d);
+  if (d < 0 || d >= ENERF_MAX_DEVICES) d = 0;
+  if (n[d] == 0) cudaDeviceGetAttribute(&n[d], cudaDevAttrMultiProcessorCount, d);
+  return n[d];
+}
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // torch.linspace(0, 1, steps) element i, same two-sided formula as ATen's RangeFactories kernel

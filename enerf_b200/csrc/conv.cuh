@@ -230,14 +230,14 @@ int launch_conv(const char* name, const float* in, const float* w, const float* 
   d.Ho = (Hi + 2 * T::PAD - T::KH) / T::STRIDE + 1;
   d.Wo = (Wi + 2 * T::PAD - T::KH) / T::STRIDE + 1;
   d.out_cstride = out_cstride, d.out_coff = out_coff;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceSize attr_set;   // the attribute is per device
+  if (attr_set.cur() < T::SMEM) {
     cudaError_t e = cudaFuncSetAttribute(conv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
     if (e != cudaSuccess) {
       set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", name, T::SMEM, cudaGetErrorString(e));
       return ENERF_ECUDA;
     }
-    attr_set = true;
+    attr_set.cur() = T::SMEM;
   }
   dim3 grid(ceil_div(d.Wo, T::TX), ceil_div(d.Ho, T::TY), ceil_div(d.Do, T::TZ));
   conv_kernel<T><<<grid, T::THREADS, T::SMEM, stream>>>(in, w, bias, out, out2, d);

@@ -472,14 +472,14 @@ __global__ void __launch_bounds__(128) render_rays_kernel(const RayParams p) {
 template <int FC, int SMAX, bool STATIC_S>
 int launch_rays(const RayParams& p, cudaStream_t stream) {
   constexpr size_t smem = RayW<FC>::total * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceSize attr_set;   // the attribute is per device
+  if (attr_set.cur() < smem) {
     cudaError_t e = cudaFuncSetAttribute(render_rays_kernel<FC, SMAX, STATIC_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("render_rays: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
       return ENERF_ECUDA;
     }
-    attr_set = true;
+    attr_set.cur() = smem;
   }
   render_rays_kernel<FC, SMAX, STATIC_S><<<ceil_div(p.n_rays, 128), 128, smem, stream>>>(p);
   ENERF_CHECK_LAUNCH("render_rays");

@@ -559,19 +559,16 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
 template <int S>
 static int launch_rays_tc(const RayTcParams& P, cudaStream_t stream) {
   constexpr size_t smem = TcSmem<S>::bytes;
-  static bool attr_set = false;
-  static int n_sm = 0;
-  if (!attr_set) {
+  static PerDeviceSize attr_set;   // the attribute (and the SM count) is per device
+  if (attr_set.cur() < smem) {
     cudaError_t e = cudaFuncSetAttribute(render_rays_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("render_rays_tc: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
       return ENERF_ECUDA;
     }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    attr_set = true;
+    attr_set.cur() = smem;
   }
+  const int n_sm = device_sm_count();
   const int grid = P.n_tiles < 2 * n_sm ? P.n_tiles : 2 * n_sm;  // persistent: 2 CTAs per SM
   render_rays_tc_kernel<S><<<grid, 128, smem, stream>>>(P);
   ENERF_CHECK_LAUNCH("render_rays_tc");

@@ -467,7 +467,8 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
   dim3 grid(ceil_div(Wn, P.TX), ceil_div(Hn, P.TY), ceil_div(Dn, P.TZ));
 #define TC_LAUNCH(NT, MD, FD)                                                                                        \
   do {                                                                                                             \
-    static size_t smem_set = 0;                                                                                    \
+    static PerDeviceSize smem_set_pd;                                                                              \
+    size_t& smem_set = smem_set_pd.cur();                                                                          \
     if (smem > smem_set) {                                                                                         \
       cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<NT, MD, FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e)); \

@@ -1,0 +1,147 @@
+// tc_probe.cu -- diagnostics that pin the two hardware conventions tc_conv2.cu is built on, and measure
+// the TMA box rate (exported through the C ABI so tests/ and tools_* can run them on the B200):
+//
+//  enerf_tc_swz_selftest : a [rows x Kf] fp32 matrix is brought into shared memory by ONE TMA box load with
+//      SWIZZLE_{32,64,128}B (Kf*4 = the swizzle span), then D[128 x N] = A[row_off : row_off+128] * B^T is
+//      computed by tcgen05.mma with a K-major SWIZZLED A descriptor whose start address is advanced by
+//      row_off whole rows (NOT a multiple of the 8-row swizzle atom) and by 32 bytes per K-step.  This is
+//      how tc_conv2 expresses filter taps; the test decides how the descriptor's base_offset field must be
+//      set for such starts (mode 0: zero, mode 1: (start >> 7) & 7).
+//  enerf_tma_box_bench   : every CTA streams `iters` halo-tile boxes {C, IX, IY, IZ} of a channels-last tensor
+//      into shared memory (ring of `depth` boxes in flight); reports nothing itself -- time it with events.
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace enerf {
+
+__global__ void __launch_bounds__(128) swz_selftest_kernel(const __grid_constant__ CUtensorMap map, int Kf, int rows_box, const float* __restrict__ B,
+                                                           int N, int row_off, int bo_mode, float* __restrict__ D) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bar_tma, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int t = threadIdx.x, warp = t >> 5;
+  unsigned char* a_s = sm;                                                   // [rows_box][Kf*4 B] swizzled by TMA
+  float* b_s = reinterpret_cast<float*>(sm + (((size_t)rows_box * Kf * 4 + 1023) & ~(size_t)1023));   // [Kf/4][N][4] no swizzle
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (t == 0) {
+    tc::mbar_init(&bar_tma, 1);
+    tc::mbar_init(&bar_mma, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, ncols);
+  for (int e = t; e < N * (Kf / 4); e += 128) {
+    const int n = e % N, c = e / N;
+    const float4 v = *reinterpret_cast<const float4*>(B + (size_t)n * Kf + 4 * c);
+    *reinterpret_cast<float4*>(b_s + ((size_t)c * N + n) * 4) = make_float4(tc::to_tf32(v.x), tc::to_tf32(v.y), tc::to_tf32(v.z), tc::to_tf32(v.w));
+  }
+  tc::fence_proxy_async();
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (t == 0) {
+    tc::mbar_expect_tx(&bar_tma, (uint32_t)rows_box * (uint32_t)Kf * 4u);
+    tma::load_2d(a_s, &map, 0, 0, &bar_tma);
+    tc::mbar_wait(&bar_tma, 0);
+    tc::tc_fence_after_sync();
+    const uint32_t idesc = tc::idesc_tf32(128, N);
+    const uint32_t row_bytes = (uint32_t)Kf * 4u;
+    for (int k8 = 0; k8 < Kf / 8; ++k8) {
+      const uint32_t start = tc::smem_u32(a_s) + (uint32_t)row_off * row_bytes + (uint32_t)k8 * 32u;
+      const uint32_t bo = bo_mode == 0 ? 0u : ((start >> 7) & 7u);
+      const uint64_t ad = tma::smem_desc_swz(start, row_bytes, bo);
+      const uint64_t bd = tc::smem_desc(tc::smem_u32(b_s) + (uint32_t)(2 * k8) * (uint32_t)N * 16u, (uint32_t)N * 16u, 128u);
+      tc::mma_tf32(tmem, ad, bd, idesc, k8 > 0);
+    }
+    tc::mma_commit(&bar_mma);
+  }
+  tc::mbar_wait(&bar_mma, 0);
+  tc::tc_fence_after_sync();
+  for (int c0 = 0; c0 < N; c0 += 8) {
+    float v[8];
+    tc::tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) D[(size_t)t * N + c0 + j] = v[j];
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, ncols);
+}
+
+__global__ void __launch_bounds__(128) tma_box_bench_kernel(const __grid_constant__ CUtensorMap map, uint32_t box_bytes, int depth, int iters,
+                                                            int nx, int ny, int nz, int tx, int ty, int tz, float* __restrict__ sink) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bar[8];
+  const int t = threadIdx.x;
+  const uint32_t slot_bytes = (box_bytes + 1023u) & ~1023u;
+  if (t == 0) {
+    for (int i = 0; i < depth; ++i) tc::mbar_init(&bar[i], 1);
+    tc::fence_mbar_init();
+  }
+  __syncthreads();
+  float acc = 0.f;
+  if (t == 0) {
+    auto issue = [&](int i) {
+      const int tile = (blockIdx.x + i * gridDim.x) % (nx * ny * nz);
+      const int bx = tile % nx, by = (tile / nx) % ny, bz = tile / (nx * ny);
+      const int s = i % depth;
+      tc::mbar_expect_tx(&bar[s], box_bytes);
+      tma::load_4d(tc::smem_u32(sm + (size_t)s * slot_bytes), &map, 0, bx * tx - 1, by * ty - 1, bz * tz - (tz > 1 ? 1 : 0), &bar[s]);
+    };
+    for (int i = 0; i < depth && i < iters; ++i) issue(i);
+    for (int i = 0; i < iters; ++i) {
+      const int s = i % depth;
+      tc::mbar_wait(&bar[s], (uint32_t)((i / depth) & 1));
+      acc += *reinterpret_cast<volatile float*>(sm + (size_t)s * slot_bytes);
+      if (i + depth < iters) issue(i + depth);
+    }
+  }
+  if (t == 0 && acc == 123.456f) *sink = acc;
+}
+
+}  // namespace enerf
+
+extern "C" int enerf_tc_swz_selftest(const float* A, int rows, int Kf, const float* B, int N, int row_off, int bo_mode, float* D, void* stream) {
+  using namespace enerf;
+  ENERF_REQUIRE(A && B && D, ENERF_EINVAL, "tc_swz_selftest: null pointer");
+  ENERF_REQUIRE((Kf == 8 || Kf == 16 || Kf == 32) && N >= 16 && N % 16 == 0 && N <= 256, ENERF_EINVAL, "tc_swz_selftest: Kf=%d N=%d", Kf, N);
+  const int rows_box = row_off + 128 + 8;
+  ENERF_REQUIRE(row_off >= 0 && rows_box <= 256 && rows >= rows_box, ENERF_EINVAL, "tc_swz_selftest: row_off %d needs %d <= min(256, rows=%d) box rows",
+                row_off, rows_box, rows);
+  CUtensorMap map;
+  const uint64_t dims[2] = {(uint64_t)Kf, (uint64_t)rows}, strides[1] = {(uint64_t)Kf * 4};
+  const uint32_t box[2] = {(uint32_t)Kf, (uint32_t)rows_box};
+  const int rc = tma::encode_f32(&map, A, 2, dims, strides, box, nullptr, tma::swizzle_for_bytes(Kf * 4));
+  ENERF_REQUIRE(rc == 0, ENERF_ECUDA, "tc_swz_selftest: cuTensorMapEncodeTiled failed (%d)", rc);
+  const size_t smem = (((size_t)rows_box * Kf * 4 + 1023) & ~(size_t)1023) + (size_t)Kf * N * 4 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(swz_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_swz_selftest: smem attr: %s", cudaGetErrorString(e));
+  swz_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(map, Kf, rows_box, B, N, row_off, bo_mode, D);
+  ENERF_CHECK_LAUNCH("tc_swz_selftest");
+  return ENERF_OK;
+}
+
+// x: (D,H,W,C) fp32 channels-last; boxes {C, tx+2, ty+2, tz+2 (tz>1) | 1}; grid CTAs x iters boxes each, `depth` in flight.
+extern "C" int enerf_tma_box_bench(const float* x, int D, int H, int W, int C, int tx, int ty, int tz, int depth, int iters, int grid, float* sink,
+                                   void* stream) {
+  using namespace enerf;
+  ENERF_REQUIRE(x && sink && (C == 8 || C == 16 || C == 32) && depth >= 1 && depth <= 8 && iters > 0 && grid > 0, ENERF_EINVAL, "tma_box_bench: bad args");
+  const int ix = tx + 2, iy = ty + 2, iz = tz > 1 ? tz + 2 : 1;
+  ENERF_REQUIRE(ix <= 256 && iy <= 256 && iz <= 256, ENERF_EINVAL, "tma_box_bench: box too large");
+  CUtensorMap map;
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)D};
+  const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+  const uint32_t box[4] = {(uint32_t)C, (uint32_t)ix, (uint32_t)iy, (uint32_t)iz};
+  const int rc = tma::encode_f32(&map, x, 4, dims, strides, box, nullptr, tma::swizzle_for_bytes(C * 4));
+  ENERF_REQUIRE(rc == 0, ENERF_ECUDA, "tma_box_bench: cuTensorMapEncodeTiled failed (%d)", rc);
+  const uint32_t box_bytes = (uint32_t)(ix * iy * iz * C * 4);
+  const size_t smem = (size_t)depth * ((box_bytes + 1023u) & ~1023u) + 1024;
+  ENERF_REQUIRE(smem <= 220 * 1024, ENERF_EINVAL, "tma_box_bench: %zu B of shared memory", smem);
+  cudaError_t e = cudaFuncSetAttribute(tma_box_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tma_box_bench: smem attr: %s", cudaGetErrorString(e));
+  tma_box_bench_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(map, box_bytes, depth, iters, ceil_div(W, tx), ceil_div(H, ty), ceil_div(D, tz), tx, ty, tz, sink);
+  ENERF_CHECK_LAUNCH("tma_box_bench");
+  return ENERF_OK;
+}

@@ -45,6 +45,13 @@ class GraphedNetwork:
                 name, lvl = k.rsplit("_level", 1)
                 views.setdefault(int(lvl), {})[name] = self.flat_out[o:o + int(torch.tensor(shp).prod())].view(shp[1:])
             net.output_views = views
+        # The captured kernels keep the ADDRESSES of the Network's scratch (camera struct, workspaces,
+        # variance / probability volumes, packed image features).  Graphs of the same net replayed
+        # concurrently on different streams (StreamedRenderer, bench.py replicas) must not share them:
+        # the capture runs with a fresh scratch cache that this graph then owns.
+        shared_scratch = getattr(net, "_buffers_cache", None)
+        if shared_scratch is not None:
+            net._buffers_cache = {}
         self.graph = torch.cuda.CUDAGraph()
         try:
             with torch.cuda.graph(self.graph), torch.no_grad():
@@ -52,6 +59,8 @@ class GraphedNetwork:
         finally:
             if hasattr(net, "output_views"):
                 net.output_views = saved_views
+            if shared_scratch is not None:
+                self.scratch, net._buffers_cache = net._buffers_cache, shared_scratch
 
     def load(self, batch, non_blocking=True):
         if _signature(batch) != self.sig:

@@ -95,21 +95,22 @@ def make_batch(H, W, S, cfg, seed=2, near_far=(2.0, 6.0), B=1):
     return batch
 
 
-def make_composite_batch(H, W, S, cfg, seed=2):
+def make_composite_batch(H, W, S, cfg, seed=2, boxes=None):
     """``make_batch`` + the extra keys of lib/datasets/enerf_outdoor/enerf.py:183-190: one bbox (x,y,w,h;
     w,h multiples of 32 as read_tar :161-162 pads them) and one [near, far] per foreground layer, the
-    background [near, far] last, and the background plates ``bg_src_inps``."""
+    background [near, far] last, and the background plates ``bg_src_inps``.  ``boxes`` overrides the
+    default (x, y, w, h) per layer (w, h multiples of 32)."""
     L = int(cfg.num_fg_layers)
     batch = make_batch(H, W, S, cfg, seed=seed)
     g = torch.Generator().manual_seed(seed + 7)
     batch["bg_src_inps"] = 2.0 * torch.rand((1, S, 3, H, W), generator=g) - 1.0
-    boxes, nfs = [], []
+    given, boxes, nfs = boxes, [], []
     for l in range(L):
         w = max(32, (W * 2 // 3) // 32 * 32) if l == 0 else 32
         h = max(32, (H // 2) // 32 * 32)
         x = min(W - w, 20 if l == 0 else 4)
         y = min(H - h, 8 if l == 0 else 24)
-        boxes.append([x, y, w, h])
+        boxes.append(list(given[l]) if given is not None else [x, y, w, h])
         nfs.append([2.5 + 0.5 * l, 4.5 + 1.0 * l])
     nfs.append([2.0, 6.0])
     batch["bbox"] = torch.tensor([boxes], dtype=torch.float32)
@@ -132,3 +133,28 @@ def make_mask_at_box(H, W, seed=9):
     m[torch.rand(H, W, generator=g) < 0.07] = 0
     m[0, :3] = 1
     return m[None]
+
+
+# BASELINE.json configs[3] / [4] at the shapes SURVEY.md section 8d fixes (shared by tests and bench.py)
+C4 = dict(H=1024, W=1024, S=4, planes=[48, 8], render_if=[False, True])          # ZJU-MoCap shape, network_human + mask_at_box
+C5 = dict(H=1088, W=1920, S=6, layers=3,                                          # ENeRF-Outdoor shape (1080 padded to /32)
+          boxes=[[256, 224, 384, 736], [768, 192, 416, 768], [1312, 256, 352, 704]])   # three actors, xywh multiples of 32
+
+
+def c4_case(seed=2):
+    """(cfg, batch) of BASELINE config 4: 1024x1024, 4 source views, 48+8 planes, masked rays."""
+    from . import config as bcfg
+    cfg = bcfg.make_cfg(volume_planes=list(C4["planes"]), render_if=list(C4["render_if"]))
+    batch = make_batch(C4["H"], C4["W"], C4["S"], cfg, seed=seed)
+    batch.pop("rays_0", None)
+    batch["mask_at_box"] = make_mask_at_box(C4["H"], C4["W"])
+    return cfg, batch
+
+
+def c5_case(seed=2):
+    """(cfg, batch) of BASELINE config 5: 1920x1088, 6 source views, 3 foreground actors + background
+    (configs/enerf/enerf_outdoor/actor1.yaml: planes [32, 8] (+ background [16, 4]), samples [2, 1], no view-dir MLP)."""
+    from . import config as bcfg
+    cfg = bcfg.composite_cfg(num_fg_layers=C5["layers"])
+    batch = make_composite_batch(C5["H"], C5["W"], C5["S"], cfg, seed=seed, boxes=C5["boxes"])
+    return cfg, batch

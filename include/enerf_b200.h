@@ -278,6 +278,18 @@ ENERF_API int enerf_tc_mma_bench(int layout, int N, int n_mma, int accs, unsigne
  * K multiple of 8 (<=128), N multiple of 16 (<=256); A, B row-major.  No reference counterpart. */
 ENERF_API int enerf_tc_selftest(const float* A, const float* B, int K, int N, float* D, void* stream);
 
+/* Diagnostic: the convention enerf_tc_conv's TMA-fed kernel rests on.  A [rows x Kf] (Kf = 8|16|32 floats =
+ * a 32|64|128-byte swizzle span) is loaded by ONE TMA box with the matching swizzle; D[128 x N] =
+ * A[row_off : row_off+128] * B[N x Kf]^T is computed with a K-major SWIZZLED operand descriptor whose start
+ * address is advanced by row_off whole rows.  bo_mode: the descriptor's base_offset field, 0 = zero,
+ * 1 = (start >> 7) & 7.  No reference counterpart. */
+ENERF_API int enerf_tc_swz_selftest(const float* A, int rows, int Kf, const float* B, int N, int row_off, int bo_mode, float* D, void* stream);
+
+/* Diagnostic: TMA box rate.  `grid` CTAs each stream `iters` halo boxes {C, tx+2, ty+2, tz+2 (1 if tz == 1)}
+ * of the channels-last fp32 tensor x (D,H,W,C), C = 8|16|32, with `depth` boxes in flight. */
+ENERF_API int enerf_tma_box_bench(const float* x, int D, int H, int W, int C, int tx, int ty, int tz, int depth, int iters, int grid,
+                                  float* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,23 @@ CASES = {
                                    "enerf.cas_config.render_if", "False,True"],
                              kind="composite", over=dict(volume_planes=[8, 8], num_samples=[2, 2], render_if=[False, True]),
                              H=64, W=96, S=2, composite=2),
+    # oracle branches the other cases leave unpinned: white background (utils.py:596-599) ...
+    "c2_white_bkgd": dict(yaml="configs/enerf/dtu_pretrain.yaml",
+                          opts=["enerf.cas_config.volume_planes", "8,8", "enerf.cas_config.render_if", "False,True", "enerf.white_bkgd", "True"],
+                          kind="cascade", over=dict(volume_planes=[8, 8], render_if=[False, True], white_bkgd=True), H=64, W=96, S=3),
+    # ... Agg without the view-direction MLP (nerf.py:74-78) ...
+    "c2_no_viewdir": dict(yaml="configs/enerf/dtu_pretrain.yaml",
+                          opts=["enerf.cas_config.volume_planes", "8,8", "enerf.cas_config.render_if", "False,True", "enerf.viewdir_agg", "False"],
+                          kind="cascade", over=dict(volume_planes=[8, 8], render_if=[False, True], viewdir_agg=False), H=64, W=96, S=3),
+    # ... and five source views (beyond the tensor-core ray kernel's former S <= 4 limit)
+    "c2_five_views": dict(yaml="configs/enerf/dtu_pretrain.yaml",
+                          opts=["enerf.cas_config.volume_planes", "8,8", "enerf.cas_config.render_if", "False,True"],
+                          kind="cascade", over=dict(volume_planes=[8, 8], render_if=[False, True]), H=64, W=96, S=5),
+    # BASELINE.json configs[4] in miniature: 6 source views, 3 foreground layers + background
+    "c5_composite_3fg_s6": dict(yaml="configs/enerf/enerf_outdoor/actor1.yaml",
+                                opts=["num_fg_layers", "3", "enerf.cas_config.volume_planes", "8,8", "enerf.cas_config.render_if", "False,True"],
+                                kind="composite", over=dict(volume_planes=[8, 8], render_if=[False, True]),
+                                H=64, W=128, S=6, composite=3),
 }
 
 

@@ -7,8 +7,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["c1_nocascade", "c2_small_cascade", "c2_headline_small", "c4_human_small"]
-COMPOSITE_CASES = ["c5_composite_1fg", "c5_composite_2fg"]
+GOLDEN_CASES = ["c1_nocascade", "c2_small_cascade", "c2_headline_small", "c4_human_small", "c2_white_bkgd", "c2_no_viewdir", "c2_five_views"]
+COMPOSITE_CASES = ["c5_composite_1fg", "c5_composite_2fg", "c5_composite_3fg_s6"]
 
 
 def load_golden(name):

@@ -278,6 +278,55 @@ def test_forward_without_rays_graph_and_streamed(harness):
             assert torch.equal(o[k], gen[k].cpu()), k
 
 
+def test_streamed_distinct_frames_do_not_share_scratch(harness):
+    """Frames in flight must not share the Network's scratch (camera struct, workspaces, volumes):
+    DIFFERENT frames (other images, other cameras) streamed with depth 3 / replayed concurrently as
+    graph replicas must each equal their own eager forward (the captures used to alias)."""
+    from enerf_b200 import config as bcfg
+    from enerf_b200.network import Network
+    from enerf_b200.pipeline import GraphedNetwork, StreamedRenderer
+    cfg = bcfg.make_cfg(volume_planes=[16, 8], render_if=[False, True])
+    sd, _ = harness.make_case(128, 160, 3, cfg, seed=3)
+    net = Network()
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    from enerf_b200 import synthetic
+    hosts, want = [], []
+    for i in range(6):
+        b = synthetic.make_batch(128, 160, 3, cfg, seed=20 + 7 * i)
+        b = {k: v for k, v in b.items() if not k.startswith("rays_")}
+        hosts.append({k: v.pin_memory() for k, v in b.items()})
+        with torch.no_grad():
+            want.append({k: v.clone().cpu() for k, v in net({k: v.cuda() for k, v in b.items()}).items()})
+    assert (want[0]["rgb_level1"] - want[1]["rgb_level1"]).abs().max().item() > 1e-2     # the frames really differ
+    got = {}
+    sr = StreamedRenderer(net, hosts[0], torch.device("cuda"), depth=3)
+    for _ in range(3):                                   # several passes: any aliasing shows up as a race
+        sr.render(hosts, lambda i, o: got.__setitem__(i, {k: v.clone() for k, v in o.items()}))
+        for i in range(6):
+            for k in want[i]:
+                assert torch.equal(got[i][k], want[i][k]), (i, k)
+    # graph replicas replayed concurrently on their own streams (what bench.py does)
+    reps = []
+    for j in range(3):
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            reps.append((GraphedNetwork(net, {k: v.cuda() for k, v in hosts[j].items()}), st))
+    torch.cuda.synchronize()
+    ptrs = [r.scratch["cam"].data_ptr() for r, _ in reps]
+    assert len(set(ptrs)) == len(ptrs), "graph replicas share the camera scratch"
+    for _ in range(5):
+        outs = []
+        for j, (r, st) in enumerate(reps):
+            with torch.cuda.stream(st):
+                r.load({k: v.cuda() for k, v in hosts[j + 3].items()}, non_blocking=False)
+                outs.append(r.replay())
+        torch.cuda.synchronize()
+        for j, o in enumerate(outs):
+            for k in want[j + 3]:
+                assert torch.equal(o[k].cpu(), want[j + 3][k]), (j, k)
+
+
 def test_mask_compaction_edge_cases():
     """Order-preserving compaction == rays[mask] for empty / full / single / ragged masks and every
     mask dtype the data layer produces (bool, uint8, int32, int64)."""
