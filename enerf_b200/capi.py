@@ -37,8 +37,8 @@ _SIGS = {
     "enerf_cost_reg_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "enerf_cost_reg": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "enerf_depth_regress": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "enerf_render_rays": (_i, [_vp, _i, ctypes.POINTER(_vp), _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i,
-                               _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "enerf_render_rays": (_i, [_vp, _i, ctypes.POINTER(_vp), _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _i, _i,
+                               _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "enerf_depth_hypotheses_layer": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "enerf_cost_volume_window": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, ctypes.POINTER(_i), _i, _vp, _vp]),
     "enerf_depth_regress_window": (_i, [_vp, ctypes.POINTER(_i), _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
@@ -49,11 +49,11 @@ _SIGS = {
     "enerf_composite_layers": (_i, [_vp, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(_i), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "enerf_mask_compact_workspace_bytes": (_sz, [_i]),
     "enerf_mask_compact": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "enerf_scatter_rows": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "enerf_scatter_rows": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "enerf_psnr_accumulate": (_i, [_vp, _vp, _vp, _i, ctypes.c_longlong, _vp, _vp]),
     "enerf_pack_rgb8": (_i, [_vp, _i, _i, _i, _vp, _vp]),
-    "enerf_render_rays_tc": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i,
-                                  _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "enerf_render_rays_tc": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _i, _i,
+                                  _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "enerf_tc_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "enerf_tc_conv_debug": (_i, [_vp]),
     "enerf_tc_conv_tune": (_i, [_i, _i, _i]),
@@ -77,7 +77,7 @@ def lib():
         for name, (res, args) in _SIGS.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.enerf_abi_version() != 1:
+        if handle.enerf_abi_version() != 2:
             raise ImportError("libenerf_b200.so ABI version mismatch")
         _lib = handle
     return _lib
@@ -171,16 +171,25 @@ def depth_regress(depth_prob, ends, depth_inv, depth, std, depth_mvs):
                                      stream()), "enerf_depth_regress")
 
 
+def _count_ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != torch.int32:
+        raise ValueError("device-side counts must be CUDA int32 tensors")
+    return t.data_ptr()
+
+
 def render_rays(cam, level, weights, rays, depth, std, near_far, feat_vol, img_feat_rgb, feat_ch, num_samples, depth_inv,
-                white_bkgd, viewdir_agg, out_rgb, out_depth, out_weights):
+                white_bkgd, viewdir_agg, out_rgb, out_depth, out_weights, vol_row0=0, n_rays_dev=None):
+    """feat_vol (D, rows, wv, 8): rows [vol_row0, vol_row0 + rows) of the level's volume (the full grid by default)."""
     n_rays = rays.shape[0]
     hv, wv = depth.shape[-2:]
-    D = feat_vol.shape[0]
+    D, vol_rows = feat_vol.shape[0], feat_vol.shape[1]
     S, Hr, Wr, _ = img_feat_rgb.shape
     _check(lib().enerf_render_rays(ptr(cam), level, ptr_array(weights), len(weights), ptr(rays), n_rays, ptr(depth), ptr(std),
-                                   ptr(near_far), hv, wv, ptr(feat_vol), D, ptr(img_feat_rgb), S, Hr, Wr, feat_ch, num_samples,
-                                   int(depth_inv), int(white_bkgd), int(viewdir_agg), ptr(out_rgb), ptr(out_depth),
-                                   ptr(out_weights), stream()), "enerf_render_rays")
+                                   ptr(near_far), hv, wv, ptr(feat_vol), D, vol_row0, vol_rows, ptr(img_feat_rgb), S, Hr, Wr, feat_ch,
+                                   num_samples, int(depth_inv), int(white_bkgd), int(viewdir_agg), _count_ptr(n_rays_dev), ptr(out_rgb),
+                                   ptr(out_depth), ptr(out_weights), stream()), "enerf_render_rays")
 
 
 def _ints(vals):
@@ -260,14 +269,15 @@ def tma_box_bench(x, tx, ty, tz, depth, iters, grid, sink):
 
 
 def render_rays_tc(cam, level, wblob, rays, depth, std, near_far, feat_vol, img_feat_rgb, feat_ch, num_samples, depth_inv,
-                   white_bkgd, viewdir_agg, out_rgb, out_depth, out_weights):
+                   white_bkgd, viewdir_agg, out_rgb, out_depth, out_weights, vol_row0=0, n_rays_dev=None):
     n_rays = rays.shape[0]
     hv, wv = depth.shape[-2:]
-    D = feat_vol.shape[0]
+    D, vol_rows = feat_vol.shape[0], feat_vol.shape[1]
     S, Hr, Wr, _ = img_feat_rgb.shape
     _check(lib().enerf_render_rays_tc(ptr(cam), level, ptr(wblob), ptr(rays), n_rays, ptr(depth), ptr(std), ptr(near_far), hv, wv,
-                                      ptr(feat_vol), D, ptr(img_feat_rgb), S, Hr, Wr, feat_ch, num_samples, int(depth_inv),
-                                      int(white_bkgd), int(viewdir_agg), ptr(out_rgb), ptr(out_depth), ptr(out_weights), stream()),
+                                      ptr(feat_vol), D, vol_row0, vol_rows, ptr(img_feat_rgb), S, Hr, Wr, feat_ch, num_samples,
+                                      int(depth_inv), int(white_bkgd), int(viewdir_agg), _count_ptr(n_rays_dev), ptr(out_rgb),
+                                      ptr(out_depth), ptr(out_weights), stream()),
            "enerf_render_rays_tc")
 
 
@@ -317,9 +327,10 @@ def mask_compact_workspace_bytes(n):
     return lib().enerf_mask_compact_workspace_bytes(n)
 
 
-def scatter_rows(src, idx, m, dst):
+def scatter_rows(src, idx, m, dst, m_dev=None):
     C = dst.shape[-1]
-    _check(lib().enerf_scatter_rows(ptr(src) if m else None, idx.data_ptr() if m else None, m, C, ptr(dst), stream()), "enerf_scatter_rows")
+    _check(lib().enerf_scatter_rows(ptr(src) if m else None, idx.data_ptr() if m else None, m, _count_ptr(m_dev), C, ptr(dst), stream()),
+           "enerf_scatter_rows")
 
 
 def psnr_accumulate(pred, gt, mask, acc):

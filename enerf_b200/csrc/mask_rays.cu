@@ -85,8 +85,13 @@ __global__ void __launch_bounds__(MC_BLOCK) mask_scatter_kernel(const unsigned c
   }
 }
 
-__global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, int m, int C, float* __restrict__ dst) {
+__global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, int m, const int* __restrict__ m_dev, int C,
+                                    float* __restrict__ dst) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m_dev != nullptr) {                              // device-side row count: the launch covers the upper bound
+    m = min(m, __ldg(m_dev));
+    if (m <= 1) return;                                // `if mask_at_box.sum() > 1` (network_human.py:104): one ray is NOT scattered
+  }
   if (t >= (long long)m * C) return;
   const int i = (int)(t / C), c = (int)(t % C);
   dst[(size_t)idx[i] * C + c] = src[t];
@@ -113,12 +118,12 @@ extern "C" int enerf_mask_compact(const void* mask, int elem_size, const float* 
   return ENERF_OK;
 }
 
-extern "C" int enerf_scatter_rows(const float* src, const int* idx, int m, int C, float* dst, void* stream) {
+extern "C" int enerf_scatter_rows(const float* src, const int* idx, int m, const int* m_dev, int C, float* dst, void* stream) {
   using namespace enerf;
   ENERF_REQUIRE(dst && (m == 0 || (src && idx)), ENERF_EINVAL, "scatter_rows: null pointer");
   if (m <= 0) return ENERF_OK;
   const long long total = (long long)m * C;
-  scatter_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, idx, m, C, dst);
+  scatter_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, idx, m, m_dev, C, dst);
   ENERF_CHECK_LAUNCH("scatter_rows");
   return ENERF_OK;
 }

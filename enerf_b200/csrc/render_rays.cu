@@ -30,9 +30,10 @@ static int dispatch_rays(const enerf::RayParams& p, int feat_ch, int n_views, cu
 
 extern "C" int enerf_render_rays(const EnerfCam* cam, int level, const float* const* weights, int n_weights,
                                  const float* rays, int n_rays, const float* depth, const float* std, const float* near_far,
-                                 int hv, int wv, const float* feat_vol, int D, const float* img_feat_rgb, int n_views, int Hr,
-                                 int Wr, int feat_ch, int num_samples, int depth_inv, int white_bkgd, int viewdir_agg,
-                                 float* out_rgb, float* out_depth, float* out_weights, void* stream_) {
+                                 int hv, int wv, const float* feat_vol, int D, int vol_row0, int vol_rows, const float* img_feat_rgb,
+                                 int n_views, int Hr, int Wr, int feat_ch, int num_samples, int depth_inv, int white_bkgd,
+                                 int viewdir_agg, const int* n_rays_dev, float* out_rgb, float* out_depth, float* out_weights,
+                                 void* stream_) {
   using namespace enerf;
   cudaStream_t stream = (cudaStream_t)stream_;
   ENERF_REQUIRE(cam && weights && rays && depth && std && near_far && feat_vol && img_feat_rgb && out_rgb && out_depth && out_weights,
@@ -43,12 +44,15 @@ extern "C" int enerf_render_rays(const EnerfCam* cam, int level, const float* co
   ENERF_REQUIRE(num_samples >= 1 && num_samples <= 8, ENERF_EUNSUPPORTED, "render_rays: num_samples %d not in [1,8]", num_samples);
   ENERF_REQUIRE(level >= 0 && level < ENERF_MAX_LEVELS, ENERF_EINVAL, "render_rays: level %d", level);
   ENERF_REQUIRE(feat_ch == 8 || feat_ch == 32, ENERF_EUNSUPPORTED, "render_rays: feat_ch %d not in {8,32}", feat_ch);
+  ENERF_REQUIRE(vol_row0 >= 0 && vol_rows > 0 && vol_row0 + vol_rows <= hv, ENERF_EINVAL, "render_rays: volume rows [%d,%d) outside [0,%d)",
+                vol_row0, vol_row0 + vol_rows, hv);
   if (n_rays <= 0) return ENERF_OK;
   RayParams p;
   p.cam = cam, p.level = level;
   for (int i = 0; i < 16; ++i) p.w[i] = weights[i];
   p.rays = rays, p.n_rays = n_rays, p.depth = depth, p.std = std, p.near_far = near_far, p.hv = hv, p.wv = wv;
-  p.feat_vol = feat_vol, p.D = D, p.img = img_feat_rgb, p.S = n_views, p.Hr = Hr, p.Wr = Wr;
+  p.feat_vol = feat_vol, p.D = D, p.vol_y0 = vol_row0, p.vol_h = vol_rows, p.n_rays_dev = n_rays_dev;
+  p.img = img_feat_rgb, p.S = n_views, p.Hr = Hr, p.Wr = Wr;
   p.num_samples = num_samples, p.depth_inv = depth_inv, p.white_bkgd = white_bkgd, p.viewdir_agg = viewdir_agg;
   p.out_rgb = out_rgb, p.out_depth = out_depth, p.out_weights = out_weights;
   p.win_x = p.win_y = p.win_w = 0, p.out_raw = p.out_z = nullptr, p.out_stride = p.out_off = 0;
@@ -80,7 +84,8 @@ extern "C" int enerf_render_rays_raw(const EnerfCam* cam, int level, const float
   p.cam = cam, p.level = level;
   for (int i = 0; i < 16; ++i) p.w[i] = weights[i];
   p.rays = rays, p.n_rays = w * h, p.depth = depth, p.std = std, p.near_far = near_far, p.hv = hv, p.wv = wv;
-  p.feat_vol = nullptr, p.D = 1, p.img = img_feat_rgb, p.S = n_views, p.Hr = Hr, p.Wr = Wr;
+  p.feat_vol = nullptr, p.D = 1, p.vol_y0 = 0, p.vol_h = hv, p.n_rays_dev = nullptr;
+  p.img = img_feat_rgb, p.S = n_views, p.Hr = Hr, p.Wr = Wr;
   p.num_samples = num_samples, p.depth_inv = depth_inv, p.white_bkgd = 0, p.viewdir_agg = viewdir_agg;
   p.out_rgb = p.out_depth = p.out_weights = nullptr;
   p.win_x = x, p.win_y = y, p.win_w = w, p.out_raw = out_raw, p.out_z = out_z, p.out_stride = out_stride, p.out_off = out_off;

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(128) render_rays_kernel(const RayParams p) {
   __syncthreads();
 
   int ray = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ray >= p.n_rays) return;
+  if (ray >= p.n_rays || (p.n_rays_dev != nullptr && ray >= __ldg(p.n_rays_dev))) return;
   if (p.out_raw) ray = (p.win_y + ray / p.win_w) * p.Wr + p.win_x + ray % p.win_w;   // window -> frame pixel
   const int S = STATIC_S ? SMAX : p.S;
   const int Ns = p.num_samples;
@@ -171,9 +171,9 @@ __global__ void __launch_bounds__(128) render_rays_kernel(const RayParams p) {
 #pragma unroll
             for (int cx = 0; cx < 2; ++cx) {
               const int xx = x0 + cx, yy = y0 + cy, zz = z0 + cz;
-              if (xx >= 0 && xx < p.wv && yy >= 0 && yy < p.hv && zz >= 0 && zz < p.D) {
+              if (xx >= 0 && xx < p.wv && yy >= 0 && yy < p.hv && zz >= 0 && zz < p.D && yy >= p.vol_y0 && yy < p.vol_y0 + p.vol_h) {
                 const float wgt = wx[cx] * wy[cy] * wz[cz];
-                const float* q = p.feat_vol + (((size_t)zz * p.hv + yy) * p.wv + xx) * 8;
+                const float* q = p.feat_vol + (((size_t)zz * p.vol_h + (yy - p.vol_y0)) * p.wv + xx) * 8;
                 const float4 a = ldg4(q), b = ldg4(q + 4);
                 vif[0] = fmaf(a.x, wgt, vif[0]), vif[1] = fmaf(a.y, wgt, vif[1]), vif[2] = fmaf(a.z, wgt, vif[2]),
                 vif[3] = fmaf(a.w, wgt, vif[3]);

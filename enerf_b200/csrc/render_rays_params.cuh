@@ -14,6 +14,11 @@ struct RayParams {
   int hv, wv;
   const float* feat_vol;
   int D;
+  // rows [vol_y0, vol_y0 + vol_h) of the (D,hv,wv,8) feature volume are resident (feat_vol = that crop, (D,vol_h,wv,8));
+  // the full grid is vol_y0 = 0, vol_h = hv.  Used by the row-band multi-GPU layout (enerf_b200/dist.py).
+  int vol_y0, vol_h;
+  // optional device-side ray count: the launch covers n_rays (an upper bound), rays >= *n_rays_dev are skipped
+  const int* n_rays_dev;
   const float* img;
   int S, Hr, Wr;
   int num_samples, depth_inv, white_bkgd, viewdir_agg;

@@ -147,12 +147,15 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
 
   unsigned long long* dbg = (g_ray_dbg && t == 0 && blockIdx.x == 0) ? g_ray_dbg : nullptr;
   int tile_i = -1;
-  for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+  // device-side ray count (masked rays without a host read-back): the grid was sized for the upper bound p.n_rays
+  const int n_rays = p.n_rays_dev ? min(__ldg(p.n_rays_dev), p.n_rays) : p.n_rays;
+  const int n_tiles = p.n_rays_dev ? (int)(((long long)n_rays * Ns + 127) / 128) : P.n_tiles;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     ++tile_i;
     RAY_STAMP(0);
     const long long pt = (long long)tile * 128 + t;
-    const bool valid = pt < (long long)p.n_rays * Ns;
-    int ray = valid ? (int)(pt / Ns) : p.n_rays - 1;
+    const bool valid = pt < (long long)n_rays * Ns;
+    int ray = valid ? (int)(pt / Ns) : n_rays - 1;
     if (p.out_raw) ray = (p.win_y + ray / p.win_w) * p.Wr + p.win_x + ray % p.win_w;   // layered mode: window -> frame pixel
     const int k = (int)(pt % Ns);
 
@@ -202,9 +205,9 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
 #pragma unroll
             for (int cx = 0; cx < 2; ++cx) {
               const int xx = x0 + cx, yy = y0 + cy, zz = z0 + cz;
-              if (xx >= 0 && xx < p.wv && yy >= 0 && yy < p.hv && zz >= 0 && zz < p.D) {
+              if (xx >= 0 && xx < p.wv && yy >= 0 && yy < p.hv && zz >= 0 && zz < p.D && yy >= p.vol_y0 && yy < p.vol_y0 + p.vol_h) {
                 const float wgt = wx[cx] * wy[cy] * wz[cz];
-                const float* q = p.feat_vol + (((size_t)zz * p.hv + yy) * p.wv + xx) * 8;
+                const float* q = p.feat_vol + (((size_t)zz * p.vol_h + (yy - p.vol_y0)) * p.wv + xx) * 8;
                 const float4 a = ldg4(q), b = ldg4(q + 4);
                 vox[0] = fmaf(a.x, wgt, vox[0]), vox[1] = fmaf(a.y, wgt, vox[1]), vox[2] = fmaf(a.z, wgt, vox[2]),
                 vox[3] = fmaf(a.w, wgt, vox[3]);
@@ -579,9 +582,9 @@ static int launch_rays_tc(const RayTcParams& P, cudaStream_t stream) {
 
 extern "C" int enerf_render_rays_tc(const EnerfCam* cam, int level, const float* wblob, const float* rays, int n_rays,
                                     const float* depth, const float* std, const float* near_far, int hv, int wv,
-                                    const float* feat_vol, int D, const float* img_feat_rgb, int n_views, int Hr, int Wr,
-                                    int feat_ch, int num_samples, int depth_inv, int white_bkgd, int viewdir_agg, float* out_rgb,
-                                    float* out_depth, float* out_weights, void* stream_) {
+                                    const float* feat_vol, int D, int vol_row0, int vol_rows, const float* img_feat_rgb, int n_views,
+                                    int Hr, int Wr, int feat_ch, int num_samples, int depth_inv, int white_bkgd, int viewdir_agg,
+                                    const int* n_rays_dev, float* out_rgb, float* out_depth, float* out_weights, void* stream_) {
   using namespace enerf;
   cudaStream_t stream = (cudaStream_t)stream_;
   ENERF_REQUIRE(cam && wblob && rays && depth && std && near_far && feat_vol && img_feat_rgb && out_rgb && out_depth && out_weights,
@@ -591,13 +594,16 @@ extern "C" int enerf_render_rays_tc(const EnerfCam* cam, int level, const float*
   ENERF_REQUIRE(num_samples == 1 || num_samples == 2 || num_samples == 4 || num_samples == 8, ENERF_EUNSUPPORTED,
                 "render_rays_tc: num_samples %d not in {1,2,4,8}", num_samples);
   ENERF_REQUIRE(level >= 0 && level < ENERF_MAX_LEVELS, ENERF_EINVAL, "render_rays_tc: level %d", level);
+  ENERF_REQUIRE(vol_row0 >= 0 && vol_rows > 0 && vol_row0 + vol_rows <= hv, ENERF_EINVAL, "render_rays_tc: volume rows [%d,%d) outside [0,%d)",
+                vol_row0, vol_row0 + vol_rows, hv);
   if (n_rays <= 0) return ENERF_OK;
   RayTcParams P;
   RayParams& p = P.r;
   p.cam = cam, p.level = level;
   for (int i = 0; i < 18; ++i) p.w[i] = nullptr;
   p.rays = rays, p.n_rays = n_rays, p.depth = depth, p.std = std, p.near_far = near_far, p.hv = hv, p.wv = wv;
-  p.feat_vol = feat_vol, p.D = D, p.img = img_feat_rgb, p.S = n_views, p.Hr = Hr, p.Wr = Wr;
+  p.feat_vol = feat_vol, p.D = D, p.vol_y0 = vol_row0, p.vol_h = vol_rows, p.n_rays_dev = n_rays_dev;
+  p.img = img_feat_rgb, p.S = n_views, p.Hr = Hr, p.Wr = Wr;
   p.num_samples = num_samples, p.depth_inv = depth_inv, p.white_bkgd = white_bkgd, p.viewdir_agg = viewdir_agg;
   p.out_rgb = out_rgb, p.out_depth = out_depth, p.out_weights = out_weights;
   p.win_x = p.win_y = p.win_w = 0, p.out_raw = p.out_z = nullptr, p.out_stride = p.out_off = 0;
@@ -635,7 +641,8 @@ extern "C" int enerf_render_rays_raw_tc(const EnerfCam* cam, int level, const fl
   p.cam = cam, p.level = level;
   for (int i = 0; i < 18; ++i) p.w[i] = nullptr;
   p.rays = rays, p.n_rays = w * h, p.depth = depth, p.std = std, p.near_far = near_far, p.hv = hv, p.wv = wv;
-  p.feat_vol = nullptr, p.D = 1, p.img = img_feat_rgb, p.S = n_views, p.Hr = Hr, p.Wr = Wr;
+  p.feat_vol = nullptr, p.D = 1, p.vol_y0 = 0, p.vol_h = hv, p.n_rays_dev = nullptr;
+  p.img = img_feat_rgb, p.S = n_views, p.Hr = Hr, p.Wr = Wr;
   p.num_samples = num_samples, p.depth_inv = depth_inv, p.white_bkgd = 0, p.viewdir_agg = viewdir_agg;
   p.out_rgb = p.out_depth = p.out_weights = nullptr;
   p.win_x = x, p.win_y = y, p.win_w = w, p.out_raw = out_raw, p.out_z = out_z, p.out_stride = out_stride, p.out_off = out_off;

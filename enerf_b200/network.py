@@ -54,6 +54,14 @@ class Network(nn.Module):
         # (None = the full frame); set by the ray-sharding renderer (enerf_b200/dist.py)
         self.ray_rows = None
         self.output_views = None   # {level: {"rgb","depth","weights"}} pre-allocated ray outputs (enerf_b200/dist.py)
+        # Row-band layout of the LAST level (enerf_b200/dist.py, SURVEY.md section 8e option 1): with ray_rows set and
+        # band_shard True, the cost volume / CostRegNet / regression of that level run only on the volume rows the
+        # band's rays touch plus a halo that covers the regulariser's receptive field (+-30 rows for CostRegNet,
+        # +-14 for MinCostRegNet, +1 for the bilinear / trilinear taps), so the band is bit-identical to the full frame.
+        self.band_shard = False
+        # masked path without the host read-back of the ray count (graph-capturable): outputs keep the reference's
+        # keys, depth / weights are padded to the full ray count and `mask_count` (device int32) says how many are valid
+        self.static_mask = False
         self.profile = False       # when True, CUDA events bracket every stage (see stage_times_ms)
         self._events = []
 
@@ -99,6 +107,20 @@ class Network(nn.Module):
             t = torch.empty(numel, device=device, dtype=dtype)
             self._buffers_cache[name] = t
         return t[:numel]
+
+    # ---------------------------------------------------------------- row-band layout (enerf_b200/dist.py)
+    HALO = {True: 32, False: 16}     # CostRegNet: receptive field +-30 rows; MinCostRegNet: +-14
+
+    def _band_rows(self, lv, H, h, deep):
+        """Volume rows [y0, y1) a rank must regularise so that its ray rows ``self.ray_rows`` come out exactly."""
+        Hr = int(H * lv.render_scale)
+        r0, r1 = self.ray_rows
+        div = 8 if deep else 4
+        if (r0 * h) % Hr or (r1 * h) % Hr or ((r0 * h) // Hr) % div or ((r1 * h) // Hr) % div:
+            raise ValueError(f"band rows {r0}:{r1} of {Hr} do not map onto volume rows aligned to the regulariser's stride {div}")
+        v0, v1 = r0 * h // Hr, r1 * h // Hr
+        halo = self.HALO[deep]
+        return max(0, v0 - halo), min(h, v1 + halo)
 
     # ---------------------------------------------------------------- per-stage CUDA-event timing
     def _mark(self, name):
@@ -193,13 +215,21 @@ class Network(nn.Module):
             nf_new = torch.empty((2, h, w), **f32)
             capi.depth_hypotheses(cam, depth, std, nf, h, w, D, lv.depth_inv, ends, nf_new)
             nf = nf_new
-            var = self._scratch(f"var{i}", D * h * w * feat.shape[-1], dev).view(D, h, w, feat.shape[-1])
+            # rows [y0, y1) of the volume this call regularises: everything, or the rank's band + halo
+            y0, y1 = 0, h
+            if self.band_shard and self.ray_rows is not None and i == len(levels) - 1 and lv.render_if:
+                y0, y1 = self._band_rows(lv, H, h, deep)
+            hc = y1 - y0
+            var = self._scratch(f"var{i}", D * hc * w * feat.shape[-1], dev).view(D, hc, w, feat.shape[-1])
             self._mark(f"depth_hypotheses_{i}")
-            capi.cost_volume(cam, i, feat, ends, D, h, w, lv.depth_inv, var)
+            if hc == h:
+                capi.cost_volume(cam, i, feat, ends, D, h, w, lv.depth_inv, var)
+            else:
+                capi.cost_volume_window(cam, i, feat, ends, D, h, w, [0, y0, w, hc], lv.depth_inv, var)
             self._mark(f"cost_volume_{i}")
-            vol = torch.empty((D, h, w, 8), **f32) if lv.render_if else None
-            prob = self._scratch(f"prob{i}", D * h * w, dev).view(D, h, w)
-            rws = self._scratch(f"reg_ws{i}", capi.cost_reg_workspace_bytes(deep, D, h, w) // 4, dev)
+            vol = torch.empty((D, hc, w, 8), **f32) if lv.render_if else None
+            prob = self._scratch(f"prob{i}", D * hc * w, dev).view(D, hc, w)
+            rws = self._scratch(f"reg_ws{i}", capi.cost_reg_workspace_bytes(deep, D, hc, w) // 4, dev)
             capi.cost_reg(pk[f"reg{i}"], deep, var, vol, prob, rws, tensor_cores=tcs)
             self._mark(f"cost_reg_{i}")
             lvl_views = (self.output_views or {}).get(i) or {}
@@ -208,7 +238,10 @@ class Network(nn.Module):
             mvs = lvl_views["depth_mvs"] if "depth_mvs" in lvl_views else torch.empty((h, w), **f32)
             if std.shape != (h, w) or mvs.shape != (h, w):
                 raise ValueError("output_views std / depth_mvs shapes do not match the level's volume resolution")
-            capi.depth_regress(prob, ends, lv.depth_inv, depth, std, mvs)
+            if hc == h:
+                capi.depth_regress(prob, ends, lv.depth_inv, depth, std, mvs)
+            else:   # rows outside [y0, y1) are NOT this rank's (they come out as the uniform-probability value)
+                capi.depth_regress_window(prob, [0, y0, w, hc], ends, lv.depth_inv, depth, std, mvs)
             self._mark(f"depth_regress_{i}")
             if not lv.render_if:
                 continue
@@ -243,9 +276,12 @@ class Network(nn.Module):
                 cnt = torch.empty(1, device=dev, dtype=torch.int32)
                 mws = self._scratch("mask_ws", capi.mask_compact_workspace_bytes(n_full) // 4 + 1, dev)
                 capi.mask_compact(mask, rays, midx, rays_c, cnt, mws)
-                # the output shapes depend on the count: one D2H read, as the reference's boolean indexing implies
-                n_sel = int(cnt.item())
-                rays = rays_c[:n_sel]
+                if self.static_mask:   # no read-back: launches sized for n_full, the kernels stop at the device-side count
+                    rays = rays_c
+                else:                  # the output shapes depend on the count: one D2H read, as the reference's boolean indexing implies
+                    n_sel = int(cnt.item())
+                    rays = rays_c[:n_sel]
+            n_dev = cnt if (use_mask and self.static_mask) else None
             N = rays.shape[0]
             views = (self.output_views or {}).get(i)
             if views is not None and "rgb" in views:   # write straight into the caller's (gather) buffer
@@ -253,21 +289,26 @@ class Network(nn.Module):
                 if rgb.shape != (N, 3) or dmap.shape != (N,) or wts.shape != (N, lv.num_samples):
                     raise ValueError("output_views shapes do not match the ray batch")
             else:
-                rgb = torch.empty((N, 3), **f32)
-                dmap = torch.empty((N,), **f32)
-                wts = torch.empty((N, lv.num_samples), **f32)
+                alloc = torch.zeros if n_dev is not None else torch.empty     # static mask: rows past the count stay zero
+                rgb = alloc((N, 3), **f32)
+                dmap = alloc((N,), **f32)
+                wts = alloc((N, lv.num_samples), **f32)
             if N == 0:
                 pass
             elif self.precision == "tf32" and capi.tc_ray_kernel_supports(lv.feat_ch, S, lv.num_samples):
                 capi.render_rays_tc(cam, i, pk[f"nerf_tc{i}"], rays, depth, std, nf, vol, img, lv.feat_ch, lv.num_samples,
-                                    lv.depth_inv, bool(cfg.enerf.white_bkgd), bool(cfg.enerf.viewdir_agg), rgb, dmap, wts)
+                                    lv.depth_inv, bool(cfg.enerf.white_bkgd), bool(cfg.enerf.viewdir_agg), rgb, dmap, wts,
+                                    vol_row0=y0, n_rays_dev=n_dev)
             else:
                 capi.render_rays(cam, i, pk[f"nerf{i}"], rays, depth, std, nf, vol, img, lv.feat_ch, lv.num_samples, lv.depth_inv,
-                                 bool(cfg.enerf.white_bkgd), bool(cfg.enerf.viewdir_agg), rgb, dmap, wts)
+                                 bool(cfg.enerf.white_bkgd), bool(cfg.enerf.viewdir_agg), rgb, dmap, wts, vol_row0=y0, n_rays_dev=n_dev)
             self._mark(f"render_rays_{i}")
             if use_mask:   # rgb scattered into a zero image, depth / weights stay compact (network_human.py:102-106)
                 rgb_full = torch.zeros((n_full, 3), **f32)
-                if N > 1:
+                if n_dev is not None:
+                    capi.scatter_rows(rgb, midx, N, rgb_full, m_dev=n_dev)
+                    ret["mask_count"] = cnt
+                elif N > 1:
                     capi.scatter_rows(rgb, midx, N, rgb_full)
                 rgb = rgb_full
             ret.update({f"rgb_level{i}": rgb[None], f"depth_level{i}": dmap[None], f"weights_level{i}": wts[None],

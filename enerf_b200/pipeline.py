@@ -14,23 +14,35 @@ Both produce exactly what ``Network.forward`` produces (same kernels, same order
 import torch
 
 
+# launch geometry the Networks read on the HOST (network_composite: one bbox per foreground layer); such
+# keys stay CPU tensors, are not copied per frame and must not change under a captured graph
+HOST_KEYS = ("bbox",)
+
+
 def _signature(batch):
     return tuple(sorted((k, tuple(v.shape)) for k, v in batch.items() if torch.is_tensor(v)))
 
 
+def _is_dev_input(k, v):
+    return torch.is_tensor(v) and k not in HOST_KEYS
+
+
 class GraphedNetwork:
-    def __init__(self, net, example_batch, warmup=3, flat_outputs=False):
+    def __init__(self, net, example_batch, warmup=3, flat_outputs=False, fn=None):
         """example_batch: CUDA tensors; defines the static signature.
         flat_outputs: every output tensor of the captured forward lives in ONE device buffer
-        (``self.flat_out``), so a consumer can fetch the whole result with a single copy."""
+        (``self.flat_out``), so a consumer can fetch the whole result with a single copy.
+        fn: what to capture instead of ``net(batch)`` (a callable of the static batch that drives ``net``,
+        e.g. BandShardedRenderer.render_local); ``net`` still provides the scratch cache to privatise."""
         self.net = net
+        call = fn if fn is not None else net
         self.sig = _signature(example_batch)
-        self.static_in = {k: v.clone() for k, v in example_batch.items() if torch.is_tensor(v)}
+        self.static_in = {k: (v.clone() if _is_dev_input(k, v) else v) for k, v in example_batch.items() if torch.is_tensor(v)}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(warmup):           # builds packed weights / scratch, sets kernel attributes
-                probe = net(self.static_in)
+                probe = call(self.static_in)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.flat_out, self.out_layout, saved_views = None, None, getattr(net, "output_views", None)
@@ -55,7 +67,7 @@ class GraphedNetwork:
         self.graph = torch.cuda.CUDAGraph()
         try:
             with torch.cuda.graph(self.graph), torch.no_grad():
-                self.static_out = net(self.static_in)
+                self.static_out = call(self.static_in)
         finally:
             if hasattr(net, "output_views"):
                 net.output_views = saved_views
@@ -66,6 +78,10 @@ class GraphedNetwork:
         if _signature(batch) != self.sig:
             raise ValueError("batch signature differs from the captured graph")
         for k, dst in self.static_in.items():
+            if k in HOST_KEYS:
+                if not torch.equal(dst.cpu(), batch[k].cpu()):
+                    raise ValueError(f"{k} is launch geometry baked into the captured graph; re-capture for a new value")
+                continue
             dst.copy_(batch[k], non_blocking=non_blocking)
 
     def replay(self):
@@ -88,13 +104,13 @@ class StreamedRenderer:
         self.dev, self.depth = device, depth
         self.copy_in, self.copy_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
         shared = torch.cuda.Stream(device)
-        ex = {k: v.to(device) for k, v in example_host_batch.items() if torch.is_tensor(v)}
+        ex = {k: (v.to(device) if _is_dev_input(k, v) else v) for k, v in example_host_batch.items() if torch.is_tensor(v)}
         self.slots = []
         for _ in range(depth):
             cs = torch.cuda.Stream(device) if use_graph else shared
             with torch.cuda.stream(cs):
                 g = GraphedNetwork(net, ex, flat_outputs=True) if use_graph else None
-            slot = {"g": g, "cs": cs, "in": g.static_in if g else {k: v.clone() for k, v in ex.items()},
+            slot = {"g": g, "cs": cs, "in": g.static_in if g else {k: (v.clone() if _is_dev_input(k, v) else v) for k, v in ex.items()},
                     "h2d": torch.cuda.Event(), "done": torch.cuda.Event(), "d2h": torch.cuda.Event(), "free": torch.cuda.Event(),
                     "host_out": None, "host_flat": None}
             if g is not None and g.flat_out is not None:   # one pinned buffer mirrors the flat device buffer
@@ -108,7 +124,8 @@ class StreamedRenderer:
         with torch.cuda.stream(self.copy_in):
             self.copy_in.wait_event(slot["free"])          # previous forward of this slot finished reading the inputs
             for k, dst in slot["in"].items():
-                dst.copy_(host_batch[k], non_blocking=True)
+                if k not in HOST_KEYS:
+                    dst.copy_(host_batch[k], non_blocking=True)
             slot["h2d"].record(self.copy_in)
         cs = slot["cs"]
         with torch.cuda.stream(cs), torch.no_grad():
@@ -122,11 +139,12 @@ class StreamedRenderer:
             if slot["host_flat"] is not None:              # the whole result in one D2H copy
                 slot["host_flat"].copy_(slot["g"].flat_out, non_blocking=True)
             else:
-                if slot["host_out"] is None:
-                    slot["host_out"] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+                if slot["host_out"] is None or any(slot["host_out"][k].shape != v.shape for k, v in out.items() if torch.is_tensor(v)):
+                    slot["host_out"] = {k: (torch.empty(v.shape, dtype=v.dtype).pin_memory() if torch.is_tensor(v) else v) for k, v in out.items()}
                 for k, v in out.items():
-                    v.record_stream(self.copy_out)
-                    slot["host_out"][k].copy_(v, non_blocking=True)
+                    if torch.is_tensor(v):
+                        v.record_stream(self.copy_out)
+                        slot["host_out"][k].copy_(v, non_blocking=True)
             slot["d2h"].record(self.copy_out)
 
     def render(self, host_batches, on_frame=None):

@@ -35,7 +35,7 @@ extern "C" {
 #define ENERF_API
 #endif
 
-#define ENERF_ABI_VERSION 1
+#define ENERF_ABI_VERSION 2
 #define ENERF_MAX_VIEWS 8
 #define ENERF_MAX_LEVELS 4
 
@@ -153,13 +153,20 @@ ENERF_API int enerf_depth_regress(const float* depth_prob /*D,h,w*/, const float
  *     color0{w[88+fc+4][64],b}, color2{w[64],b}   (all transposed to [in][out]).
  *   outputs: rgb (n_rays,3), depth (n_rays), weights (n_rays,num_samples).
  * feat_ch (without the 3 rgb channels) in {8,32}; n_views in [2,ENERF_MAX_VIEWS];
- * num_samples in [1,8]. */
+ * num_samples in [1,8].
+ *
+ * ABI 2 additions:
+ *   vol_row0 / vol_rows: feat_vol holds only rows [vol_row0, vol_row0 + vol_rows) of the volume, i.e. it is a
+ *     (D,vol_rows,wv,8) crop (the full grid is 0 / hv).  The row-band multi-GPU layout regularises a band + halo
+ *     of the cost volume per rank (enerf_b200/dist.py); the rays passed must only touch resident rows.
+ *   n_rays_dev: optional DEVICE int.  When non-NULL the launch is sized for n_rays (an upper bound) and rays
+ *     >= *n_rays_dev are skipped: the masked path (network_human) then needs no host read-back of the count. */
 ENERF_API int enerf_render_rays(const EnerfCam* cam, int level, const float* const* weights, int n_weights,
                       const float* rays, int n_rays, const float* depth, const float* std,
-                      const float* near_far, int hv, int wv, const float* feat_vol, int D,
+                      const float* near_far, int hv, int wv, const float* feat_vol, int D, int vol_row0, int vol_rows,
                       const float* img_feat_rgb, int n_views, int Hr, int Wr, int feat_ch,
-                      int num_samples, int depth_inv, int white_bkgd, int viewdir_agg, float* out_rgb,
-                      float* out_depth, float* out_weights, void* stream);
+                      int num_samples, int depth_inv, int white_bkgd, int viewdir_agg, const int* n_rays_dev,
+                      float* out_rgb, float* out_depth, float* out_weights, void* stream);
 
 /* Masked-ray path (network_human.py:90-107).
  * enerf_mask_compact: order-preserving compaction of the rays whose mask element is non-zero
@@ -171,7 +178,9 @@ ENERF_API int enerf_render_rays(const EnerfCam* cam, int level, const float* con
 ENERF_API size_t enerf_mask_compact_workspace_bytes(int n);
 ENERF_API int enerf_mask_compact(const void* mask, int elem_size, const float* rays, int n, int* idx_out, float* rays_out,
                                  int* count_out, void* workspace, size_t workspace_bytes, void* stream);
-ENERF_API int enerf_scatter_rows(const float* src, const int* idx, int m, int C, float* dst, void* stream);
+/* m_dev (ABI 2): optional DEVICE row count, rows >= *m_dev are skipped (m is then the launch's upper bound) and,
+ * as the reference does (`if mask_at_box.sum() > 1`, network_human.py:104), nothing is scattered unless *m_dev > 1. */
+ENERF_API int enerf_scatter_rows(const float* src, const int* idx, int m, const int* m_dev, int C, float* dst, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Layered ("composite") rendering, lib/networks/enerf/network_composite.py (SURVEY.md section 8f
@@ -238,10 +247,10 @@ ENERF_API int enerf_pack_rgb8(const float* rgb, int H, int W, int flip_vertical,
  * 16-byte-chunk layout of csrc/tc.cuh, followed by the fp32 bias / 1-wide vectors). */
 ENERF_API int enerf_render_rays_tc(const EnerfCam* cam, int level, const float* wblob, const float* rays, int n_rays,
                                    const float* depth, const float* std, const float* near_far, int hv, int wv,
-                                   const float* feat_vol, int D, const float* img_feat_rgb, int n_views, int Hr,
-                                   int Wr, int feat_ch, int num_samples, int depth_inv, int white_bkgd,
-                                   int viewdir_agg, float* out_rgb, float* out_depth, float* out_weights,
-                                   void* stream);
+                                   const float* feat_vol, int D, int vol_row0, int vol_rows, const float* img_feat_rgb,
+                                   int n_views, int Hr, int Wr, int feat_ch, int num_samples, int depth_inv, int white_bkgd,
+                                   int viewdir_agg, const int* n_rays_dev, float* out_rgb, float* out_depth,
+                                   float* out_weights, void* stream);
 
 /* One convolution layer on the tensor cores (tcgen05 implicit GEMM, csrc/tc_conv.cuh): the building
  * block enerf_feature_net / enerf_cost_reg use in TF32 mode, exported for layer-level parity tests.

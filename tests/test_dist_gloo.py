@@ -7,7 +7,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from enerf_b200.dist import FrameParallelRenderer, RayShardedRenderer, row_band, segment_layout
+from enerf_b200.dist import (BandShardedRenderer, FrameParallelRenderer, RayShardedRenderer, amdahl_bound, band_segment_layout, row_band,
+                             segment_layout)
 
 W, H, NS = 12, 8, 2
 
@@ -26,6 +27,26 @@ def _full_rays():
     return rays[None]
 
 
+class _FakeNet:
+    """Stands in for enerf_b200.network.Network on CPU: honours ray_rows / output_views / band_shard the way the
+    real forward does (its band is a deterministic function of the pixel coordinates)."""
+    output_views, ray_rows, band_shard = None, None, False
+
+    def __call__(self, batch):
+        r0, r1 = self.ray_rows
+        ys, xs = torch.meshgrid(torch.arange(r0, r1, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+        rays = torch.zeros((r1 - r0) * W, 8)
+        rays[:, 6], rays[:, 7] = xs.reshape(-1), ys.reshape(-1)
+        _fake_render({"rays_1": rays[None]}, self.output_views[1])
+        hv, wv = H // 2, W // 2
+        vy, vx = torch.meshgrid(torch.arange(hv, dtype=torch.float32), torch.arange(wv, dtype=torch.float32), indexing="ij")
+        mvs, std = vy * 10 + vx, vy - vx
+        if self.band_shard:          # rows outside the band are not this rank's: poison them
+            v0, v1 = r0 // 2, r1 // 2
+            mvs[:v0], mvs[v1:], std[:v0], std[v1:] = -1.0, -1.0, -1.0, -1.0
+        return {"depth_mvs_level1": mvs[None], "std_level1": std[None]}
+
+
 def _worker(rank, world, port):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -37,6 +58,17 @@ def _worker(rank, world, port):
         out = r(batch)
         assert torch.equal(out["rgb"][0], ref["rgb"]) and torch.equal(out["depth"][0], ref["depth"])
         assert torch.equal(out["weights"][0], ref["weights"])
+        # band layout: ray outputs + the band rows of depth_mvs / std travel in ONE all-gather
+        net = _FakeNet()
+        b = BandShardedRenderer(net, 1, NS, W, H, W // 2, H // 2, rank, world)
+        got = b.render({"src_inps": torch.zeros(1)})
+        assert net.ray_rows is None and net.output_views is None and net.band_shard is False
+        assert torch.equal(got["rgb_level1"][0], ref["rgb"]) and torch.equal(got["depth_level1"][0], ref["depth"])
+        assert torch.equal(got["weights_level1"][0], ref["weights"])
+        net1 = _FakeNet()
+        net1.ray_rows, net1.output_views = (0, H), {1: {k: torch.empty_like(v) for k, v in ref.items()}}
+        whole = net1({})
+        assert torch.equal(got["depth_mvs_level1"], whole["depth_mvs_level1"]) and torch.equal(got["std_level1"], whole["std_level1"])
         # frame parallel: rank r renders frame r (rays offset by r), everyone receives both frames
         fb = {"rays_1": _full_rays() + rank}
         f = FrameParallelRenderer(_fake_render, H * W, NS, rank, world)
@@ -57,6 +89,10 @@ def test_row_band_partition():
         sizes = [b - a for a, b in bands]
         assert max(sizes) - min(sizes) <= 1
     assert segment_layout(10, 2) == (0, 30, 40, 60)
+    assert band_segment_layout(10, 2, 4) == (0, 30, 40, 60, 64, 68)
+    st = {"feature_net": 0.4, "cost_volume_0": 0.05, "cost_reg_0": 0.2, "cost_volume_1": 0.05, "cost_reg_1": 0.35, "render_rays_1": 0.3}
+    assert abs(amdahl_bound(st, 1, 1.0) - 1.0) < 1e-12
+    assert abs(amdahl_bound(st, 8, 0.375) - 1.35 / (0.65 + 0.4 * 0.375 + 0.3 / 8)) < 1e-12
 
 
 def test_ray_sharding_and_frame_parallel_world2_gloo():

@@ -74,7 +74,7 @@ def test_library_exports_every_declared_symbol():
     handle = ctypes.CDLL(capi.LIB_PATH)
     for name in declared:
         assert hasattr(handle, name), name
-    assert capi.lib().enerf_abi_version() == 1
+    assert capi.lib().enerf_abi_version() == 2
     # the EnerfCam struct size the Python side assumes
     m = re.search(r"typedef struct EnerfCam \{(.*?)\} EnerfCam;", hdr, re.S)
     dims = re.findall(r"float \w+((?:\[\w+\])+);", m.group(1))

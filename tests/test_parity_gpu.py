@@ -137,6 +137,29 @@ def test_tcgen05_selftest_gemm(K, N):
     assert err < 1e-4 * max(1.0, ref.abs().max().item()), f"K={K} N={N}: max abs err {err}"
 
 
+@pytest.mark.parametrize("Kf", [8, 16, 32])
+def test_tcgen05_swizzled_tma_operand_with_row_offsets(Kf):
+    """The convention the TMA-fed convolution kernel rests on (csrc/tma.cuh, tc_conv2.cu): an operand tile written by ONE
+    TMA box with SWIZZLE_{32,64,128}B is read by tcgen05.mma through a K-major swizzled descriptor whose start address is
+    advanced by an arbitrary number of whole rows (a filter tap) and by 32 bytes per K-step, base_offset = 0 -- the swizzle
+    XOR is a function of the absolute shared-memory address on both sides.  One-hot B: D must EQUAL the shifted rows of A."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from enerf_b200 import capi
+    g = torch.Generator().manual_seed(Kf)
+    A = _tf32_rna(torch.randn(256, Kf, generator=g)).cuda()
+    N = max(16, Kf)
+    B = torch.zeros(N, Kf)
+    B[torch.arange(Kf), torch.arange(Kf)] = 1.0
+    B = B.cuda()
+    for row_off in (0, 1, 3, 8, 13, 34, 70, 105):
+        D = torch.full((128, N), float("nan"), device="cuda")
+        capi.tc_swz_selftest(A, B, D, row_off, 0)
+        torch.cuda.synchronize()
+        assert torch.equal(D[:, :Kf], A[row_off:row_off + 128]), f"Kf={Kf} row_off={row_off}"
+        assert not D[:, Kf:].any()
+
+
 def test_e2e_tf32_tensor_core_path(harness, golden):
     """Default precision: the ray-stage MLP runs on tcgen05 (TF32 operands).  Same oracle, wider
     element-wise bound, same |dPSNR| < 0.01 dB criterion."""
@@ -325,6 +348,79 @@ def test_streamed_distinct_frames_do_not_share_scratch(harness):
         for j, o in enumerate(outs):
             for k in want[j + 3]:
                 assert torch.equal(o[k].cpu(), want[j + 3][k]), (j, k)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+def test_band_sharding_is_bit_identical(harness, world, precision):
+    """The row-band multi-GPU layout (level-1 cost volume / CostRegNet / regression on band + halo, rays banded):
+    every rank's band must EQUAL the rows of the single-GPU frame bit for bit -- the halo covers the regulariser's
+    receptive field and the kernels' arithmetic does not depend on where a tile sits.  All ranks simulated on one GPU."""
+    from enerf_b200 import config as bcfg
+    from enerf_b200.dist import BandShardedRenderer
+    from enerf_b200.network import Network
+    cfg = bcfg.make_cfg(volume_planes=[16, 8], render_if=[False, True])
+    H, W = 256, 160
+    sd, batch = harness.make_case(H, W, 3, cfg, seed=4)
+    net = Network()
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    net.precision = precision
+    gb = {k: v.cuda() for k, v in batch.items() if not k.startswith("rays_")}
+    with torch.no_grad():
+        full = {k: v.clone() for k, v in net(gb).items()}
+        for rank in range(world):
+            r = BandShardedRenderer(net, 1, 2, W, H, W // 2, H // 2, rank, world, device="cuda")
+            r.buf.fill_(float("nan"))
+            r.render_local(gb)
+            torch.cuda.synchronize()
+            v = r.local_views()
+            n, nv = r.n_local, r.n_vol
+            assert torch.equal(v["rgb"], full["rgb_level1"][0, rank * n:(rank + 1) * n]), (rank, "rgb")
+            assert torch.equal(v["depth"], full["depth_level1"][0, rank * n:(rank + 1) * n]), (rank, "depth")
+            assert torch.equal(v["weights"], full["weights_level1"][0, rank * n:(rank + 1) * n]), (rank, "weights")
+            assert torch.equal(v["mvs_band"].reshape(-1), full["depth_mvs_level1"].reshape(-1)[rank * nv:(rank + 1) * nv]), (rank, "mvs")
+            assert torch.equal(v["std_band"].reshape(-1), full["std_level1"].reshape(-1)[rank * nv:(rank + 1) * nv]), (rank, "std")
+    assert net.band_shard is False and net.ray_rows is None and net.output_views is None
+
+
+def test_static_mask_is_graph_capturable_and_equal(harness):
+    """network_human without the host read-back of the masked-ray count: same rgb, depth / weights equal on the
+    first `mask_count` rows (zeros after), and the whole forward replays as one CUDA graph."""
+    from _helpers import load_golden
+    from enerf_b200 import config as bcfg
+    from enerf_b200.network_human import Network
+    from enerf_b200.pipeline import GraphedNetwork
+    fx = load_golden("c4_human_small")
+    bcfg.set_cfg(fx["cfg"])
+    net = Network()
+    net.load_state_dict(fx["state_dict"])
+    net = net.cuda().eval()
+    gb = {k: v.cuda() for k, v in fx["batch"].items()}
+    with torch.no_grad():
+        ref = {k: v.clone() for k, v in net(gb).items()}
+        net.static_mask = True
+        out = {k: v.clone() for k, v in net(gb).items()}
+        g = GraphedNetwork(net, gb)
+        rep = g(gb)
+    torch.cuda.synchronize()
+    n = int(out["mask_count"].item())
+    assert n == ref["depth_level1"].shape[1] == int(fx["batch"]["mask_at_box"].bool().sum())
+    for o in (out, rep):
+        assert torch.equal(o["rgb_level1"], ref["rgb_level1"])
+        assert torch.equal(o["depth_level1"][:, :n], ref["depth_level1"]) and not o["depth_level1"][:, n:].any()
+        assert torch.equal(o["weights_level1"][:, :n], ref["weights_level1"]) and not o["weights_level1"][:, n:].any()
+        assert torch.equal(o["depth_mvs_level1"], ref["depth_mvs_level1"])
+    # a single masked ray is not scattered (network_human.py:104) and an empty mask renders zeros
+    for keep in (1, 0):
+        m = torch.zeros_like(gb["mask_at_box"])
+        if keep:
+            m.view(-1)[777] = 1
+        b2 = dict(gb)
+        b2["mask_at_box"] = m
+        with torch.no_grad():
+            o = net(b2)
+        assert int(o["mask_count"].item()) == keep and not o["rgb_level1"].any()
 
 
 def test_mask_compaction_edge_cases():

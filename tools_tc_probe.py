@@ -19,7 +19,8 @@ def swz_report():
     out = []
     for Kf in (8, 16, 32):
         rows = 256
-        A = (torch.arange(rows, dtype=torch.float32)[:, None] + torch.arange(Kf, dtype=torch.float32)[None, :] / 64.0).cuda().contiguous()
+        # TF32-exact values (11 significant bits): (row % 32) * 32 + k  <= 1023
+        A = ((torch.arange(rows, dtype=torch.float32)[:, None] % 32) * 32 + torch.arange(Kf, dtype=torch.float32)[None, :]).cuda().contiguous()
         N = max(16, Kf)
         B = torch.zeros(N, Kf)
         for k in range(Kf):
@@ -39,12 +40,12 @@ def swz_report():
                 ok = bool(torch.equal(got, ref))
                 rec = {"Kf": Kf, "row_off": row_off, "bo_mode": bo, "ok": ok}
                 if not ok:
-                    r = torch.floor(got + 1e-3)
-                    k = torch.round((got - r) * 64.0)
+                    r = torch.floor(got / 32.0)
+                    k = got - 32.0 * r
                     bad = (got != ref)
                     rec["n_bad"] = int(bad.sum())
                     # decoded source (row - expected row, k) for the first rows
-                    rec["decoded_first_rows"] = [[(int(r[m, n] - (row_off + m)) if got[m, n] == got[m, n] else None, int(k[m, n]) if got[m, n] == got[m, n] else None)
+                    rec["decoded_first_rows"] = [[(int(r[m, n] - ((row_off + m) % 32)) if got[m, n] == got[m, n] else None, int(k[m, n]) if got[m, n] == got[m, n] else None)
                                                   for n in range(0, Kf, 4)] for m in range(0, 16)]
                 out.append(rec)
     return out
