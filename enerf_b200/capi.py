@@ -57,10 +57,12 @@ _SIGS = {
     "enerf_tc_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "enerf_tc_conv_debug": (_i, [_vp]),
     "enerf_tc_conv_tune": (_i, [_i, _i, _i]),
+    "enerf_tc_conv2_tune": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "enerf_tc_mma_bench": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "enerf_render_rays_debug": (_i, [_vp]),
     "enerf_tc_selftest": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "enerf_tc_swz_selftest": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "enerf_tc_mma_bench2": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "enerf_tma_box_bench": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
@@ -253,6 +255,10 @@ def tc_conv_tune(tz=0, ty=0, fold=-1):
     _check(lib().enerf_tc_conv_tune(int(tz), int(ty), int(fold)), "enerf_tc_conv_tune", launches=0)
 
 
+def tc_conv2_tune(impl=0, nmma=1, ctas_per_sm=1, tz=0, ty=0, kbc=0, slots=0):
+    _check(lib().enerf_tc_conv2_tune(int(impl), int(nmma), int(ctas_per_sm), int(tz), int(ty), int(kbc), int(slots)), "enerf_tc_conv2_tune", launches=0)
+
+
 def tc_selftest(A, B, D):
     """D[128,N] = A[128,K] @ B[N,K]^T on tcgen05 (TF32 operands, fp32 accumulate in TMEM)."""
     _check(lib().enerf_tc_selftest(ptr(A), ptr(B), A.shape[1], B.shape[0], ptr(D), stream()), "enerf_tc_selftest")
@@ -261,6 +267,14 @@ def tc_selftest(A, B, D):
 def tc_swz_selftest(A, B, D, row_off, bo_mode):
     """D[128,N] = A[row_off:row_off+128] @ B^T with A staged by a swizzled TMA box (see enerf_b200.h)."""
     _check(lib().enerf_tc_swz_selftest(ptr(A), A.shape[0], A.shape[1], ptr(B), B.shape[0], row_off, bo_mode, ptr(D), stream()), "enerf_tc_swz_selftest")
+
+
+def tc_mma_bench2(layout, N, n_mma, n_issuers, ksteps=1, grid=1, pad_bytes=0):
+    """Returns the (grid, 4) int64 tensor of per-issuer elapsed ns."""
+    out = torch.zeros(grid * 4, dtype=torch.int64, device="cuda")
+    _check(lib().enerf_tc_mma_bench2(layout, N, n_mma, n_issuers, ksteps, grid, pad_bytes, out.data_ptr(), stream()), "enerf_tc_mma_bench2")
+    torch.cuda.synchronize()
+    return out.view(grid, 4).cpu()
 
 
 def tma_box_bench(x, tx, ty, tz, depth, iters, grid, sink):

@@ -361,6 +361,10 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
   bool fold = (L.kind == 0 && stride == 1 && L.KH == 3 && L.KD == 3 && ((L.mode == TC_PLAIN && L.cout == 8) || L.mode == TC_SINGLE));
   if (g_tune_fold == 0) fold = false;
   if (g_tune_fold == 1) fold = (L.kind == 0 && stride == 1 && L.KH == 3);
+  if (tc_conv2_impl() != 1 && g_tune_tz == 0 && g_tune_ty == 0) {   // the persistent TMA-fed kernel takes the layers it supports
+    const int rc2 = tc_conv2_try_launch(L, in, Dn, Hn, Wn, wpack, bias, skip, out, out2, out_cstride, out_coff, fold, stream);
+    if (rc2 != 1) return rc2;
+  }
   int n_real = (L.kind == 1) ? 8 * L.cout : fold ? 3 * L.cout : L.cout;
   P.N = (n_real + 15) / 16 * 16;
   ENERF_REQUIRE(P.N <= 256, ENERF_EUNSUPPORTED, "tc_conv: N=%d > 256", P.N);

@@ -37,6 +37,12 @@ struct TcConvLayer {
   int stride = 1;    // 1 | 2 (kind 0 only).  Dn,Hn,Wn passed to tc_conv_launch are ALWAYS the output grid.
 };
 
+// tc_conv2.cu: the persistent TMA-fed kernel.  Returns ENERF_OK when it launched the layer, 1 when the layer is
+// not eligible (stride 2, weights beyond shared memory, ...) -- the caller then uses tc_conv.cu's kernel -- or an error.
+int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias, const float* skip,
+                        float* out, float* out2, int out_cstride, int out_coff, bool fold, cudaStream_t stream);
+int tc_conv2_impl();   // 0 auto, 1 tc_conv.cu only, 2 tc_conv2.cu where eligible
+
 int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias,
                    const float* skip, float* out, float* out2, int out_cstride, int out_coff, cudaStream_t stream);
 

@@ -1,0 +1,466 @@
+// tc_conv2.cu -- the persistent, warp-specialised, TMA-fed form of the tcgen05 implicit-GEMM convolution
+// (stride-1 convolutions and the sub-pixel transposed convolutions of FeatureNet / (Min)CostRegNet whose
+// weights fit in shared memory; everything else stays on tc_conv.cu's kernel).
+//
+// What changed against tc_conv.cu (same GEMM formulation: rows = linear halo positions, taps = operand
+// start-address offsets, TF32 operands, fp32 accumulators in TMEM):
+//   * The halo tile of a K-block (8 / 16 / 32 input channels of EVERY pixel) arrives by ONE TMA tensor-map box
+//     {C, IX, IY, IZ} of the channels-last tensor, written as rows of C*4 bytes with SWIZZLE_{32,64,128}B -- the
+//     K-major swizzled operand layout (csrc/tma.cuh).  Pixel p is operand row p, so a filter tap is still a
+//     start-address offset (of whole rows), a K-step of 8 channels is +32 bytes inside the row, and the
+//     volume's zero padding is the box's out-of-bounds fill.  (tests: tcgen05_swizzled_tma_operand_with_row_offsets)
+//   * Persistent CTAs (static round-robin over tiles) with three roles:
+//       warp 0            producer : waits for a free ring slot, issues the box of the next (tile, K-block)
+//       warps 1..NMMA     MMA      : wait for the slot, issue taps x K-steps x M-tiles tcgen05.mma, commit -> slot free,
+//                                    after the last K-block commit -> accumulator full
+//       last 4 warps      epilogue : tcgen05.ld, bias / ReLU / fold shift / pixel shuffle + skip, coalesced stores,
+//                                    then hand the accumulator back
+//     The accumulators are double buffered in TMEM (2 x n_mt x N columns), so the epilogue of tile i runs under the
+//     MMAs of tile i+1, and the ring keeps 2-4 boxes in flight.  The layer's weights are loaded once per CTA.
+#include <algorithm>
+
+#include "tc_conv.cuh"
+#include "tma.cuh"
+
+namespace enerf {
+
+struct TcConv2Params {
+  int Dn, Hn, Wn;        // row grid (output grid of a conv; INPUT grid of a transposed conv)
+  int TZ, TY, TX;        // tile
+  int IZ, IY, IX;        // tile + halo
+  int oz, oy, ox;        // halo origin = tile origin - (oz,oy,ox)
+  int nx, ny, nz, n_tiles;
+  int tap_off[27];       // operand start offsets of the taps in 16-byte units (rows * row_bytes / 16)
+  int kbc, n_kb;         // channels per K-block (box channel extent: 8 | 16 | 32), K-blocks per tile (cin / kbc)
+  int n_slots;           // ring depth
+  uint32_t slot_bytes, box_bytes, w_bytes, xch_bytes;
+  int N, n_mt, n_acc;    // MMA N, 128-row M-tiles per tile, accumulator stages (1 | 2)
+  int cout, relu, mode;
+  int out_cstride, out_coff;
+  uint32_t tmem_cols;
+  const float* wpack;    // [cin/8][tap][2][N][4] TF32 (packing.pack_tc_conv / pack_tc_deconv)
+  const float* bias;
+  const float* skip;
+  float* out;
+  float* out2;
+};
+
+__device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+  return p != 0;
+}
+
+template <int NTAPS, int MODE, int FOLD, int NMMA>
+__global__ void __launch_bounds__(32 * (5 + NMMA)) tc_conv2_kernel(const __grid_constant__ CUtensorMap map, const TcConv2Params P) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], accf_bar[2], acce_bar[2], w_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  // dynamic shared memory: [ring][weights][fold exchange x2]; the ring base is 1024-aligned (swizzle pattern phase)
+  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* w_s = ring + (size_t)P.n_slots * P.slot_bytes;
+  float* xch0 = reinterpret_cast<float*>(w_s + ((P.w_bytes + 127u) & ~127u));
+
+  if (t == 0) {
+    for (int i = 0; i < 8; ++i) {
+      tc::mbar_init(&full_bar[i], 1);        // the producer's expect_tx arrival (+ the box's bytes)
+      tc::mbar_init(&empty_bar[i], NMMA);    // one tcgen05.commit per MMA warp
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&accf_bar[i], NMMA);
+      tc::mbar_init(&acce_bar[i], 128);      // every epilogue thread
+    }
+    tc::mbar_init(&w_bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(&tmem_base_s, P.tmem_cols);
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t row_bytes = (uint32_t)P.kbc * 4u;
+
+  if (warp == 0) {
+    // ============================== producer ==============================
+    if (lane == 0) {
+      tma::prefetch_desc(&map);
+      tc::mbar_expect_tx(&w_bar, P.w_bytes);
+      tc::tma_load_1d(w_s, P.wpack, P.w_bytes, &w_bar);
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      const int bx = tile % P.nx, by = (tile / P.nx) % P.ny, bz = tile / (P.nx * P.ny);
+      const int x0 = bx * P.TX - P.ox, y0 = by * P.TY - P.oy, z0 = bz * P.TZ - P.oz;
+      for (int kb = 0; kb < P.n_kb; ++kb, ++it) {
+        const int slot = it % P.n_slots;
+        tc::mbar_wait(&empty_bar[slot], (uint32_t)(((it / P.n_slots) & 1) ^ 1));
+        if (lane == 0) {
+          tc::mbar_expect_tx(&full_bar[slot], P.box_bytes);
+          tma::load_4d(tc::smem_u32(ring + (size_t)slot * P.slot_bytes), &map, kb * P.kbc, x0, y0, z0, &full_bar[slot]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp <= NMMA) {
+    // ============================== MMA issue (converged warp, one elected lane issues) ==============================
+    const int mw = warp - 1;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = tc::idesc_tf32(128, P.N);
+    const uint64_t a_hi = tma::smem_desc_swz(0, row_bytes, 0), b_hi = tc::smem_desc(0, (uint32_t)P.N * 16u, 128u);
+    const uint32_t w0 = tc::smem_u32(w_s) >> 4, b_step = ((uint32_t)P.N * 32u) >> 4;      // one (K-stage, tap) B block = N*32 bytes
+    const uint32_t m_step = (128u * row_bytes) >> 4;
+    const int ksteps = P.kbc / 8;
+    tc::mbar_wait(&w_bar, 0);
+    int it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++ti) {
+      const int acc = ti % P.n_acc;
+      tc::mbar_wait(&acce_bar[acc], (uint32_t)(((ti / P.n_acc) & 1) ^ 1));      // the epilogue has drained this accumulator
+      tc::tc_fence_after_sync();
+      const uint32_t td0 = tmem_u + (uint32_t)(acc * P.n_mt * P.N);
+      for (int kb = 0; kb < P.n_kb; ++kb, ++it) {
+        const int slot = it % P.n_slots;
+        tc::mbar_wait(&full_bar[slot], (uint32_t)((it / P.n_slots) & 1));
+        tc::tc_fence_after_sync();
+        const uint32_t a0 = tc::smem_u32(ring + (size_t)slot * P.slot_bytes) >> 4;
+        for (int m = mw; m < P.n_mt; m += NMMA) {
+          const uint32_t td = td0 + (uint32_t)(m * P.N);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t am = a0 + (uint32_t)m * m_step + (uint32_t)ks * 2u;
+            const uint32_t bk = w0 + (uint32_t)((kb * ksteps + ks) * NTAPS) * b_step;
+#pragma unroll
+            for (int tp = 0; tp < NTAPS; ++tp)
+              tc::mma_tf32_elect(td, a_hi | (uint64_t)((am + (uint32_t)P.tap_off[tp]) & 0x3FFFu), b_hi | (uint64_t)((bk + (uint32_t)tp * b_step) & 0x3FFFu), idesc,
+                                 (kb > 0 || ks > 0 || tp > 0) ? 1u : 0u);
+          }
+        }
+        tc::mma_commit_elect(&empty_bar[slot]);                 // the slot is free once these MMAs have read it
+        if (kb + 1 == P.n_kb) tc::mma_commit_elect(&accf_bar[acc]);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ============================== epilogue: 128 threads = 128 accumulator rows ==============================
+    const int g = warp & 3;                                   // TMEM lane group this warp may read
+    const int r = g * 32 + lane;                              // row of the M-tile
+    const uint32_t trow0 = tmem + ((uint32_t)(g * 32) << 16);
+    const int plane = P.IY * P.IX;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++ti) {
+      const int acc = ti % P.n_acc;
+      const int bx = tile % P.nx, by = (tile / P.nx) % P.ny, bz = tile / (P.nx * P.ny);
+      const int x0 = bx * P.TX, y0 = by * P.TY, z0 = bz * P.TZ;
+      tc::mbar_wait(&accf_bar[acc], (uint32_t)((ti / P.n_acc) & 1));
+      tc::tc_fence_after_sync();
+      const uint32_t trow = trow0 + (uint32_t)(acc * P.n_mt * P.N);
+      float* xch = xch0 + (size_t)(ti & 1) * (P.xch_bytes / 8);      // [n_mt*4 + 1][2 rows][N], double buffered
+      if constexpr (FOLD) {
+        // rows 0 and 1 of every 32-row group, for the two last lanes of the group before it
+        for (int m = 0; m < P.n_mt; ++m)
+          for (int c = 0; c < P.N; c += 8) {
+            float v[8];
+            tc::tmem_ld8(trow + (uint32_t)(m * P.N + c), v);
+            tc::tmem_ld_wait();
+            if (lane < 2) {
+              float4* d = reinterpret_cast<float4*>(xch + ((size_t)((m * 4 + g) * 2 + lane)) * P.N + c);
+              d[0] = make_float4(v[0], v[1], v[2], v[3]);
+              d[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+          }
+        epi_bar_sync();
+      }
+      for (int m = 0; m < P.n_mt; ++m) {
+        const int q = m * 128 + r;                              // linear halo position of this thread's row
+        const int z = q / plane, rem = q - z * plane, y = rem / P.IX, x = rem - y * P.IX;
+        const int gz = z0 + z, gy = y0 + y, gx = x0 + x;
+        const bool valid = (z < P.TZ) && (y < P.TY) && (x < P.TX) && (gz < P.Dn) && (gy < P.Hn) && (gx < P.Wn);
+        const size_t pix = ((size_t)gz * P.Hn + gy) * P.Wn + gx;
+        const float* nxr = xch + (size_t)((m * 4 + g + 1) * 2) * P.N;   // rows 0,1 of the next 32-row group
+        auto shifted = [&](float b, float c, int colb, int colc, float& b1, float& c2) {
+          b1 = __shfl_down_sync(0xffffffffu, b, 1);
+          c2 = __shfl_down_sync(0xffffffffu, c, 2);
+          if (lane == 31) b1 = nxr[colb];
+          if (lane >= 30) c2 = nxr[(lane - 30) * P.N + colc];
+        };
+        if constexpr (FOLD && MODE == TC_PLAIN) {
+          const int C = P.cout;
+          for (int c0 = 0; c0 < C; c0 += 8) {
+            float a[8], b[8], c[8];
+            tc::tmem_ld8(trow + (uint32_t)(m * P.N + c0), a);
+            tc::tmem_ld8(trow + (uint32_t)(m * P.N + C + c0), b);
+            tc::tmem_ld8(trow + (uint32_t)(m * P.N + 2 * C + c0), c);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float b1, c2;
+              shifted(b[j], c[j], C + c0 + j, 2 * C + c0 + j, b1, c2);
+              a[j] = (a[j] + b1) + c2;
+            }
+            if (valid) {
+              const float4 b0v = ldg4(P.bias + c0), b1v = ldg4(P.bias + c0 + 4);
+              float4 o0 = make_float4(a[0] + b0v.x, a[1] + b0v.y, a[2] + b0v.z, a[3] + b0v.w);
+              float4 o1 = make_float4(a[4] + b1v.x, a[5] + b1v.y, a[6] + b1v.z, a[7] + b1v.w);
+              if (P.relu) {
+                o0 = make_float4(fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f));
+                o1 = make_float4(fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f));
+              }
+              float4* o = reinterpret_cast<float4*>(P.out + pix * P.out_cstride + P.out_coff + c0);
+              o[0] = o0;
+              o[1] = o1;
+            }
+          }
+        } else if constexpr (FOLD && MODE == TC_HEAD) {   // columns kx*9 + co: 8 feat + 1 prob per kx
+          float v[32];
+          tc::tmem_ld32(trow + (uint32_t)(m * P.N), v);
+          tc::tmem_ld_wait();
+          float rr[9];
+#pragma unroll
+          for (int j = 0; j < 9; ++j) {
+            float b1, c2;
+            shifted(v[9 + j], v[18 + j], 9 + j, 18 + j, b1, c2);
+            rr[j] = (v[j] + b1) + c2;
+          }
+          if (valid) {
+            float4* o = reinterpret_cast<float4*>(P.out + pix * 8);
+            o[0] = make_float4(rr[0], rr[1], rr[2], rr[3]);
+            o[1] = make_float4(rr[4], rr[5], rr[6], rr[7]);
+            P.out2[pix] = rr[8];
+          }
+        } else if constexpr (FOLD && MODE == TC_SINGLE) {
+          float v[8];
+          tc::tmem_ld8(trow + (uint32_t)(m * P.N), v);
+          tc::tmem_ld_wait();
+          float b1, c2;
+          shifted(v[1], v[2], 1, 2, b1, c2);
+          if (valid) P.out[pix] = (v[0] + b1) + c2;
+        } else if constexpr (MODE == TC_PLAIN) {
+          for (int c0 = 0; c0 < P.cout; c0 += 8) {       // cout is a multiple of 8
+            float v[8];
+            tc::tmem_ld8(trow + (uint32_t)(m * P.N + c0), v);
+            tc::tmem_ld_wait();
+            if (valid) {
+              const float4 b0v = ldg4(P.bias + c0), b1v = ldg4(P.bias + c0 + 4);
+              float4 o0 = make_float4(v[0] + b0v.x, v[1] + b0v.y, v[2] + b0v.z, v[3] + b0v.w);
+              float4 o1 = make_float4(v[4] + b1v.x, v[5] + b1v.y, v[6] + b1v.z, v[7] + b1v.w);
+              if (P.relu) {
+                o0 = make_float4(fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f));
+                o1 = make_float4(fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f));
+              }
+              float4* o = reinterpret_cast<float4*>(P.out + pix * P.out_cstride + P.out_coff + c0);
+              o[0] = o0;
+              o[1] = o1;
+            }
+          }
+        } else if constexpr (MODE == TC_HEAD) {          // feat_conv (8) + depth_conv (1), no bias
+          float v[16];
+          tc::tmem_ld16(trow + (uint32_t)(m * P.N), v);
+          tc::tmem_ld_wait();
+          if (valid) {
+            float4* o = reinterpret_cast<float4*>(P.out + pix * 8);
+            o[0] = make_float4(v[0], v[1], v[2], v[3]);
+            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+            P.out2[pix] = v[8];
+          }
+        } else if constexpr (MODE == TC_SINGLE) {
+          float v[8];
+          tc::tmem_ld8(trow + (uint32_t)(m * P.N), v);
+          tc::tmem_ld_wait();
+          if (valid) P.out[pix] = v[0];
+        } else {  // TC_DECONV: columns = parity * cout + co ; out[2b+e] = skip + (acc + bias)
+          const int Ho = 2 * P.Hn, Wo = 2 * P.Wn;
+          for (int c = 0; c < P.N; c += 8) {
+            float v[8];
+            tc::tmem_ld8(trow + (uint32_t)(m * P.N + c), v);
+            tc::tmem_ld_wait();
+            if (valid) {
+              const int e = c / P.cout, co = c - e * P.cout;
+              const size_t opix = ((size_t)(2 * gz + (e >> 2)) * Ho + (2 * gy + ((e >> 1) & 1))) * Wo + (2 * gx + (e & 1));
+              const float* sk = P.skip + opix * P.cout + co;
+              const float4 s0 = ldg4(sk), s1 = ldg4(sk + 4);
+              const float4 b0v = ldg4(P.bias + co), b1v = ldg4(P.bias + co + 4);
+              float4* o = reinterpret_cast<float4*>(P.out + opix * P.cout + co);
+              o[0] = make_float4(s0.x + (v[0] + b0v.x), s0.y + (v[1] + b0v.y), s0.z + (v[2] + b0v.z), s0.w + (v[3] + b0v.w));
+              o[1] = make_float4(s1.x + (v[4] + b1v.x), s1.y + (v[5] + b1v.y), s1.z + (v[6] + b1v.z), s1.w + (v[7] + b1v.w));
+            }
+          }
+        }
+      }
+      // every TMEM read of this accumulator is complete (tcgen05.wait::ld above): hand it back to the MMA warps
+      tc::tc_fence_before_sync();
+      mbar_arrive1(&acce_bar[acc]);
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem, P.tmem_cols);
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+static int g_impl = 0;          // 0 auto, 1 force tc_conv.cu's kernel, 2 force this kernel where eligible
+static int g_nmma = 1;          // MMA-issuing warps per CTA (1 | 2)
+static int g_ctas_per_sm = 1;   // persistent CTAs per SM (1 | 2)
+static int g_tune2_tz = 0, g_tune2_ty = 0, g_tune2_fold = -1, g_tune2_kbc = 0, g_tune2_slots = 0;
+
+int tc_conv2_impl() { return g_impl; }
+
+// returns ENERF_OK when launched, 1 when the layer is not eligible (caller falls back to tc_conv_launch)
+int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias, const float* skip,
+                        float* out, float* out2, int out_cstride, int out_coff, bool fold_default, cudaStream_t stream) {
+  const int stride = (L.kind == 0) ? L.stride : 1;
+  if (L.cin % 8 != 0 || L.cin > 64 || stride != 1) return 1;
+  if (tma::encode_fn() == nullptr) return 1;
+  TcConv2Params P;
+  P.Dn = Dn, P.Hn = Hn, P.Wn = Wn;
+  P.cout = L.cout, P.relu = L.relu, P.mode = L.mode;
+  P.out_cstride = out_cstride, P.out_coff = out_coff;
+  P.wpack = wpack, P.bias = bias, P.skip = skip, P.out = out, P.out2 = out2;
+  bool fold = fold_default;      // the weights are packed for the default rule (packing.tc_fold_kx): keep it
+  const int n_real = (L.kind == 1) ? 8 * L.cout : fold ? 3 * L.cout : L.cout;
+  P.N = (n_real + 15) / 16 * 16;
+  if (P.N > 256) return 1;
+  const int n_taps = (L.kind == 1) ? 8 : fold ? L.KD * L.KH : L.KD * L.KH * L.KH;
+  P.w_bytes = (uint32_t)(L.cin / 8) * (uint32_t)n_taps * (uint32_t)P.N * 32u;
+  if (P.w_bytes > 72 * 1024) return 1;
+  if (L.mode == TC_DECONV && !(L.cout % 8 == 0 && skip && bias)) return 1;
+  if (L.mode == TC_PLAIN && !(L.cout % 8 == 0 && bias)) return 1;
+
+  int hz, hy, hx;
+  if (L.kind == 1) hz = hy = hx = 1, P.oz = P.oy = P.ox = 0;
+  else hz = L.KD - 1, hy = L.KH - 1, hx = L.KH - 1, P.oz = L.KD / 2, P.oy = L.KH / 2, P.ox = L.KH / 2;
+  const bool is2d = (L.kind == 0 && L.KD == 1);
+  P.TX = 32;
+  P.TY = is2d ? 16 : 8;
+  P.TZ = is2d ? 1 : 2;
+  if (L.kind == 0 && L.KH == 3) {
+    if (is2d) P.TY = (L.cin == 8) ? 15 : 7;
+    else if (fold) P.TZ = 4, P.TY = 4;
+  }
+  if (L.kind == 0 && L.KH == 1) P.TY = 8;
+  if (L.kind == 1) P.TZ = 2, P.TY = (P.N <= 64) ? 3 : 4;
+  if (g_tune2_tz > 0) P.TZ = g_tune2_tz;
+  if (g_tune2_ty > 0) P.TY = g_tune2_ty;
+  P.TZ = std::min(P.TZ, Dn), P.TY = std::min(P.TY, Hn);
+
+  const int n_sm = device_sm_count();
+  const size_t budget = (g_ctas_per_sm >= 2 ? 110 : 216) * 1024;
+  for (;;) {
+    P.IZ = P.TZ + hz, P.IY = P.TY + hy, P.IX = P.TX + hx;
+    const int npix = P.IZ * P.IY * P.IX;
+    if (P.IZ > 256 || P.IY > 256 || P.IX > 256) return 1;
+    const int pmax = ((P.TZ - 1) * P.IY + (P.TY - 1)) * P.IX + P.TX - 1;
+    P.n_mt = (pmax + (fold ? 2 : 0)) / 128 + 1;
+    int max_tap_rows = 0, tap_rows[27];
+    if (L.kind == 1) {
+      for (int d = 0; d < 8; ++d) tap_rows[d] = (((d >> 2) & 1) * P.IY + ((d >> 1) & 1)) * P.IX + (d & 1);
+    } else if (fold) {
+      for (int kz = 0, i = 0; kz < L.KD; ++kz)
+        for (int ky = 0; ky < L.KH; ++ky) tap_rows[i++] = (kz * P.IY + ky) * P.IX;
+    } else {
+      int i = 0;
+      for (int kz = 0; kz < L.KD; ++kz)
+        for (int ky = 0; ky < L.KH; ++ky)
+          for (int kx = 0; kx < L.KH; ++kx) tap_rows[i++] = (kz * P.IY + ky) * P.IX + kx;
+    }
+    for (int i = 0; i < n_taps; ++i) max_tap_rows = std::max(max_tap_rows, tap_rows[i]);
+    P.n_acc = (2 * P.n_mt * P.N <= (g_ctas_per_sm >= 2 ? 256 : 512)) ? 2 : 1;
+    const bool tmem_ok = P.n_acc * P.n_mt * P.N <= (g_ctas_per_sm >= 2 ? 256 : 512);
+    P.xch_bytes = fold ? (uint32_t)align_up((size_t)(P.n_mt * 4 + 1) * 2 * P.N * 4, 64) * 2u : 0u;
+    // K-block = the widest channel group whose ring still holds >= 2 slots (3-4 preferred)
+    bool placed = false;
+    const int cands[3] = {32, 16, 8};
+    for (int ci = 0; ci < 3 && !placed && tmem_ok; ++ci) {
+      const int kbc = g_tune2_kbc > 0 ? g_tune2_kbc : cands[ci];
+      if (kbc > L.cin || L.cin % kbc) {
+        if (g_tune2_kbc > 0) break;
+        continue;
+      }
+      const uint32_t rb = (uint32_t)kbc * 4u;
+      // garbage rows of the last M-tile read past the box: keep them inside the slot
+      const uint32_t rows_alloc = (uint32_t)std::max(npix, P.n_mt * 128 + max_tap_rows + 2);
+      const uint32_t slot = (uint32_t)align_up((size_t)rows_alloc * rb, 1024);
+      const size_t fixed = 1024 + align_up(P.w_bytes, 128) + P.xch_bytes + 256;
+      int slots = (int)((budget - std::min(budget, fixed)) / slot);
+      slots = std::min(slots, 4);
+      if (g_tune2_slots > 0) slots = std::min(slots, g_tune2_slots);
+      const int want = (ci == 2 || g_tune2_kbc > 0) ? 2 : 3;      // fall to narrower K-blocks rather than a 2-deep ring
+      if (slots >= want || (slots >= 2 && kbc == 8)) {
+        P.kbc = kbc, P.n_kb = L.cin / kbc, P.n_slots = slots, P.slot_bytes = slot, P.box_bytes = (uint32_t)npix * rb;
+        for (int i = 0; i < n_taps; ++i) P.tap_off[i] = tap_rows[i] * (int)(rb / 16);
+        placed = true;
+      }
+      if (g_tune2_kbc > 0) break;
+    }
+    P.nx = ceil_div(Wn, P.TX), P.ny = ceil_div(Hn, P.TY), P.nz = ceil_div(Dn, P.TZ);
+    P.n_tiles = P.nx * P.ny * P.nz;
+    // small layers: shrink the tile until every SM has work
+    if (placed && (P.n_tiles >= n_sm || (P.TY <= 2 && P.TZ <= 1) || g_tune2_ty > 0)) break;
+    if (g_tune2_ty > 0) return 1;
+    if (P.TY > 2) P.TY = (P.TY + 1) / 2;
+    else if (P.TZ > 1) P.TZ /= 2;
+    else if (!placed && P.TX > 16) P.TX /= 2;
+    else return 1;
+  }
+  uint32_t cols = 32;
+  while ((int)cols < P.n_acc * P.n_mt * P.N) cols <<= 1;
+  P.tmem_cols = cols;
+
+  // tensor map of the input: channels-last (D,H,W,C) fp32 -> dims {C, W, H, D}, box {kbc, IX, IY, IZ}
+  CUtensorMap map;
+  {
+    const uint64_t dims[4] = {(uint64_t)L.cin, (uint64_t)Wn, (uint64_t)Hn, (uint64_t)Dn};
+    const uint64_t strides[3] = {(uint64_t)L.cin * 4, (uint64_t)Wn * L.cin * 4, (uint64_t)Hn * Wn * L.cin * 4};
+    const uint32_t box[4] = {(uint32_t)P.kbc, (uint32_t)P.IX, (uint32_t)P.IY, (uint32_t)P.IZ};
+    const int rc = tma::encode_f32(&map, in, 4, dims, strides, box, nullptr, tma::swizzle_for_bytes(P.kbc * 4));
+    ENERF_REQUIRE(rc == 0, ENERF_ECUDA, "tc_conv2: cuTensorMapEncodeTiled failed (%d) for a (%d,%d,%d,%d) tensor, box (%d,%d,%d,%d)", rc, Dn, Hn, Wn, L.cin,
+                  P.kbc, P.IX, P.IY, P.IZ);
+  }
+  const size_t smem = 1024 + (size_t)P.n_slots * P.slot_bytes + align_up(P.w_bytes, 128) + P.xch_bytes + 128;
+  const int grid = std::min(P.n_tiles, n_sm * g_ctas_per_sm);
+#define TC2_LAUNCH(NT, MD, FD, NM)                                                                                                        \
+  do {                                                                                                                                    \
+    static PerDeviceSize smem_set_pd;                                                                                                     \
+    size_t& smem_set = smem_set_pd.cur();                                                                                                 \
+    if (smem > smem_set) {                                                                                                                \
+      cudaError_t e = cudaFuncSetAttribute(tc_conv2_kernel<NT, MD, FD, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+      ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv2: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));               \
+      smem_set = smem;                                                                                                                    \
+    }                                                                                                                                     \
+    tc_conv2_kernel<NT, MD, FD, NM><<<grid, 32 * (5 + NM), smem, stream>>>(map, P);                                                       \
+  } while (0)
+#define TC2_DISPATCH(NT, MD, FD)             \
+  do {                                       \
+    if (g_nmma >= 2) TC2_LAUNCH(NT, MD, FD, 2); \
+    else TC2_LAUNCH(NT, MD, FD, 1);          \
+  } while (0)
+  if (L.kind == 1) TC2_DISPATCH(8, TC_DECONV, 0);
+  else if (fold && n_taps == 9 && L.mode == TC_PLAIN) TC2_DISPATCH(9, TC_PLAIN, 1);
+  else if (fold && n_taps == 9 && L.mode == TC_HEAD) TC2_DISPATCH(9, TC_HEAD, 1);
+  else if (fold && n_taps == 9 && L.mode == TC_SINGLE) TC2_DISPATCH(9, TC_SINGLE, 1);
+  else if (fold && n_taps == 3 && L.mode == TC_PLAIN) TC2_DISPATCH(3, TC_PLAIN, 1);
+  else if (!fold && n_taps == 27 && L.mode == TC_PLAIN) TC2_DISPATCH(27, TC_PLAIN, 0);
+  else if (!fold && n_taps == 27 && L.mode == TC_HEAD) TC2_DISPATCH(27, TC_HEAD, 0);
+  else if (!fold && n_taps == 27 && L.mode == TC_SINGLE) TC2_DISPATCH(27, TC_SINGLE, 0);
+  else if (!fold && n_taps == 9 && L.mode == TC_PLAIN) TC2_DISPATCH(9, TC_PLAIN, 0);
+  else if (!fold && n_taps == 1 && L.mode == TC_PLAIN) TC2_DISPATCH(1, TC_PLAIN, 0);
+  else return 1;
+#undef TC2_DISPATCH
+#undef TC2_LAUNCH
+  ENERF_CHECK_LAUNCH("tc_conv2");
+  return ENERF_OK;
+}
+
+}  // namespace enerf
+
+// Diagnostic / tuning of the TMA-fed kernel: impl 0 auto | 1 tc_conv.cu only | 2 this kernel where eligible;
+// nmma = MMA-issuing warps (1|2); ctas_per_sm (1|2); tz/ty/kbc/slots = forced tile / K-block / ring depth (0 = built-in).
+extern "C" int enerf_tc_conv2_tune(int impl, int nmma, int ctas_per_sm, int tz, int ty, int kbc, int slots) {
+  using namespace enerf;
+  ENERF_REQUIRE(impl >= 0 && impl <= 2 && nmma >= 1 && nmma <= 2 && ctas_per_sm >= 1 && ctas_per_sm <= 2 && (kbc == 0 || kbc == 8 || kbc == 16 || kbc == 32),
+                ENERF_EINVAL, "tc_conv2_tune: bad arguments");
+  g_impl = impl, g_nmma = nmma, g_ctas_per_sm = ctas_per_sm, g_tune2_tz = tz, g_tune2_ty = ty, g_tune2_kbc = kbc, g_tune2_slots = slots;
+  return ENERF_OK;
+}

@@ -145,3 +145,70 @@ extern "C" int enerf_tma_box_bench(const float* x, int D, int H, int W, int C, i
   ENERF_CHECK_LAUNCH("tma_box_bench");
   return ENERF_OK;
 }
+
+// ---- enerf_tc_mma_bench2: does the ~89-cycle cost of an M=128,K=8 TF32 MMA with shared-memory operands belong to
+// the tensor pipe or to ONE issuing stream?  `n_issuers` warps of a CTA (1..4) each issue n_mma MMAs back to back on
+// their own operands and accumulator; `grid` CTAs with `pad_bytes` of extra dynamic shared memory control how many
+// CTAs share an SM.  out_ns[cta*4 + w] = the issuer's own elapsed ns (%globaltimer).
+namespace enerf {
+__global__ void __launch_bounds__(128) tc_mma_bench2_kernel(int layout, int N, int n_mma, int n_issuers, int ksteps, unsigned long long* out_ns) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bar[4];
+  __shared__ uint32_t tmem_base_s;
+  const int t = threadIdx.x, warp = t >> 5;
+  for (int e = t; e < 96 * 1024 / 4; e += 128) reinterpret_cast<float*>(sm)[e] = 1.0f;
+  uint32_t ncols = 32;
+  while ((int)ncols < n_issuers * N) ncols <<= 1;
+  if (t == 0) {
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&bar[i], 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, ncols);
+  tc::fence_proxy_async();
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+  if (warp < n_issuers) {
+    const uint32_t a = tc::smem_u32(sm) + (uint32_t)warp * 16384u, b = tc::smem_u32(sm) + 65536u + (uint32_t)warp * 8192u;
+    uint64_t ad, bd;
+    if (layout == 0) {
+      ad = tc::smem_desc(a, 2048u, 128u);
+      bd = tc::smem_desc(b, (uint32_t)N * 16u, 128u);
+    } else {
+      const uint32_t rb = (layout == 2) ? 128u : (layout == 4) ? 64u : 32u;
+      ad = tma::smem_desc_swz(a, rb, 0);
+      bd = tc::smem_desc(b, (uint32_t)N * 16u, 128u);
+    }
+    const uint32_t idesc = tc::idesc_tf32(128, N);
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    for (int i = 0; i < n_mma; ++i) {
+      // walk the A start address like a convolution does (taps = row offsets, K-steps = +32 B): distinct operand rows per MMA
+      const uint32_t off = (layout == 0) ? (uint32_t)((i % 9) * 16) : (uint32_t)((i % 9) * 8 * ((layout == 2) ? 128 : (layout == 4) ? 64 : 32) / 16 + (i % ksteps) * 2);
+      tc::mma_tf32_elect(tmem + (uint32_t)(warp * N), ad + off, bd, idesc, 1u);
+    }
+    tc::mma_commit_elect(&bar[warp]);
+    tc::mbar_wait(&bar[warp], 0);
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    if ((t & 31) == 0) out_ns[blockIdx.x * 4 + warp] = t1 - t0;
+    __syncwarp();
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, ncols);
+}
+}  // namespace enerf
+
+extern "C" int enerf_tc_mma_bench2(int layout, int N, int n_mma, int n_issuers, int ksteps, int grid, int pad_bytes, unsigned long long* out_ns, void* stream) {
+  using namespace enerf;
+  ENERF_REQUIRE(out_ns && N >= 16 && N <= 128 && N % 16 == 0 && n_issuers >= 1 && n_issuers <= 4 && grid >= 1 && ksteps >= 1 && ksteps <= 4, ENERF_EINVAL,
+                "tc_mma_bench2: bad args");
+  const size_t smem = 96 * 1024 + 1024 + (size_t)(pad_bytes > 0 ? pad_bytes : 0);
+  ENERF_REQUIRE(smem <= 226 * 1024, ENERF_EINVAL, "tc_mma_bench2: pad too large");
+  cudaError_t e = cudaFuncSetAttribute(tc_mma_bench2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_mma_bench2: %s", cudaGetErrorString(e));
+  tc_mma_bench2_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(layout, N, n_mma, n_issuers, ksteps, out_ns);
+  ENERF_CHECK_LAUNCH("tc_mma_bench2");
+  return ENERF_OK;
+}

@@ -265,6 +265,12 @@ ENERF_API int enerf_tc_conv(int kind, int KD, int KH, int stride, int cin, int c
                             int W, const float* wpack, const float* bias, const float* skip, float* out, float* out2,
                             int out_cstride, int out_coff, void* stream);
 
+/* Diagnostic / tuning of the persistent TMA-fed convolution kernel (csrc/tc_conv2.cu) behind enerf_tc_conv and the
+ * conv stacks: impl 0 = auto (it takes every stride-1 / transposed layer whose weights fit in shared memory),
+ * 1 = csrc/tc_conv.cu's kernel only, 2 = same as 0; nmma = MMA-issuing warps per CTA (1|2); ctas_per_sm (1|2);
+ * tz, ty, kbc (8|16|32), slots: forced tile / K-block width / ring depth, 0 = built-in choice. */
+ENERF_API int enerf_tc_conv2_tune(int impl, int nmma, int ctas_per_sm, int tz, int ty, int kbc, int slots);
+
 /* Diagnostic: when buf != NULL, CTA (0,0,0) of every later enerf_tc_conv-family launch writes 64
  * %globaltimer phase stamps (ns) into buf (device memory, 64 x u64).  NULL switches it off. */
 ENERF_API int enerf_tc_conv_debug(unsigned long long* buf);
@@ -296,6 +302,10 @@ ENERF_API int enerf_tc_swz_selftest(const float* A, int rows, int Kf, const floa
 
 /* Diagnostic: TMA box rate.  `grid` CTAs each stream `iters` halo boxes {C, tx+2, ty+2, tz+2 (1 if tz == 1)}
  * of the channels-last fp32 tensor x (D,H,W,C), C = 8|16|32, with `depth` boxes in flight. */
+/* Diagnostic: MMA issue rate with several issuing warps per CTA (1..4) and several CTAs per SM (grid, pad_bytes of extra
+ * dynamic shared memory set the co-residency); out_ns[cta*4 + warp] = that issuer's elapsed ns. */
+ENERF_API int enerf_tc_mma_bench2(int layout, int N, int n_mma, int n_issuers, int ksteps, int grid, int pad_bytes, unsigned long long* out_ns,
+                                  void* stream);
 ENERF_API int enerf_tma_box_bench(const float* x, int D, int H, int W, int C, int tx, int ty, int tz, int depth, int iters, int grid,
                                   float* sink, void* stream);
 

@@ -190,13 +190,28 @@ TC_CONV_CASES = [
     (0, 3, 3, 8, 8, 0, 1, (5, 20, 44)),      # ragged extents: partial tiles in every dimension (folded kx, row exchange)
     (0, 1, 3, 8, 8, 0, 1, (3, 50, 70)),      # conv0.1-like, ragged
     (0, 3, 3, 8, 9, 1, 0, (4, 12, 20)),      # head, ragged
+    # full-size layers: many tiles per persistent CTA (ring wrap-around, both accumulator stages, K-block pipelining)
+    (0, 1, 3, 32, 8, 0, 0, (3, 512, 640)),   # smooth0 at the headline size
+    (0, 3, 3, 16, 8, 0, 1, (8, 256, 320)),   # CostRegNet conv0 (folded) at the headline size
+    (0, 3, 3, 32, 8, 0, 1, (16, 64, 80)),    # MinCostRegNet conv0: 32 channels = two 16-channel K-blocks
+    (0, 3, 3, 8, 9, 1, 0, (8, 128, 160)),    # head
+    (1, 3, 3, 16, 8, 2, 0, (4, 64, 80)),     # conv11 (transposed), many tiles
 ]
 
+# which kernel runs the layer: csrc/tc_conv.cu ("v1"), or the persistent TMA-fed csrc/tc_conv2.cu where it is eligible
+# (auto = the shipped policy; + 2 MMA-issuing warps; + 2 persistent CTAs per SM)
+TC_CONV_IMPLS = {"v1": dict(impl=1), "auto": dict(impl=0), "nmma2": dict(impl=0, nmma=2), "2cta": dict(impl=0, ctas_per_sm=2)}
 
+
+@pytest.mark.parametrize("impl", list(TC_CONV_IMPLS))
 @pytest.mark.parametrize("case", TC_CONV_CASES)
-def test_tc_conv_layer(case):
+def test_tc_conv_layer(case, impl):
     kind, KD, KH, cin, cout, mode, relu, dims = case[:8]
     stride = case[8] if len(case) > 8 else 1
+    if impl != "v1" and stride != 1:
+        pytest.skip("stride-2 layers always run on csrc/tc_conv.cu")
+    if impl in ("nmma2", "2cta") and dims[1] * dims[2] < 64 * 80:
+        pytest.skip("variant exercised on the larger cases")
     """tcgen05 implicit-GEMM convolution vs torch's fp32 conv on the same (TF32-rounded) operands.
     Bound: 2e-3 * max|ref| (TF32 operand rounding of activations; weights are pre-rounded)."""
     if not torch.cuda.is_available():
@@ -231,9 +246,13 @@ def test_tc_conv_layer(case):
         out = torch.full((Do, Ho, Wo), float("nan"), device="cuda")
     else:
         out = torch.full((Do, Ho, Wo, cout), float("nan"), device="cuda")
-    capi.tc_conv(kind, KD, KH, cout, mode, relu, xin, wp, b.cuda() if b is not None else None, skip, out, out2,
-                 out_cstride=(8 if mode == 1 else cout), stride=stride)
-    torch.cuda.synchronize()
+    capi.tc_conv2_tune(**TC_CONV_IMPLS[impl])
+    try:
+        capi.tc_conv(kind, KD, KH, cout, mode, relu, xin, wp, b.cuda() if b is not None else None, skip, out, out2,
+                     out_cstride=(8 if mode == 1 else cout), stride=stride)
+        torch.cuda.synchronize()
+    finally:
+        capi.tc_conv2_tune()
     refc = ref[0].permute(1, 2, 3, 0)
     if mode == 1:
         got = torch.cat([out.cpu(), out2.cpu()[..., None]], dim=-1)
