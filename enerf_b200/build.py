@@ -27,7 +27,7 @@ RAY_INSTANCES = [(11, 2, 1), (11, 3, 1), (11, 4, 1), (11, 8, 0), (35, 2, 1), (35
 
 
 def units():
-    u = [(n, n + ".cu", []) for n in ("camera", "feature_net", "cost_volume", "cost_reg", "render_rays", "render_rays_tc", "tc_selftest", "tc_probe", "tc_conv", "tc_conv2", "mask_rays", "eval_ops", "composite")]
+    u = [(n, n + ".cu", []) for n in ("camera", "feature_net", "cost_volume", "cost_reg", "render_rays", "render_rays_tc", "render_rays_ws", "tc_selftest", "tc_probe", "tc_conv", "tc_conv2", "mask_rays", "eval_ops", "composite")]
     for fc, s, st in RAY_INSTANCES:
         u.append((f"rr_{fc}_{s}_{st}", "render_rays_inst.cu", [f"-DRR_FC={fc}", f"-DRR_S={s}", f"-DRR_STATIC={st}"]))
     extra = os.path.join(CSRC, "units.txt")  # optional additional units: "<name> <source> [-Dflags...]"

@@ -54,6 +54,7 @@ _SIGS = {
     "enerf_pack_rgb8": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "enerf_render_rays_tc": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _i, _i, _i,
                                   _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "enerf_render_rays_tc_select": (_i, [_i]),
     "enerf_tc_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "enerf_tc_conv_debug": (_i, [_vp]),
     "enerf_tc_conv_tune": (_i, [_i, _i, _i]),
@@ -293,6 +294,10 @@ def render_rays_tc(cam, level, wblob, rays, depth, std, near_far, feat_vol, img_
                                       int(depth_inv), int(white_bkgd), int(viewdir_agg), _count_ptr(n_rays_dev), ptr(out_rgb),
                                       ptr(out_depth), ptr(out_weights), stream()),
            "enerf_render_rays_tc")
+
+
+def render_rays_tc_select(impl=0):
+    _check(lib().enerf_render_rays_tc_select(int(impl)), "enerf_render_rays_tc_select", launches=0)
 
 
 def tc_ray_kernel_supports(feat_ch, n_views, num_samples):

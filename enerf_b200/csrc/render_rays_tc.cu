@@ -559,6 +559,9 @@ __global__ void __launch_bounds__(128, 2) render_rays_tc_kernel(const RayTcParam
   if (warp == 0) tc::tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// render_rays_ws.cu: the warp-specialised kernel (2-3 views); returns 1 when it does not take the configuration
+int render_rays_ws_try_launch(const RayParams& r, const float* wblob, int n_tiles, cudaStream_t stream);
+
 template <int S>
 static int launch_rays_tc(const RayTcParams& P, cudaStream_t stream) {
   constexpr size_t smem = TcSmem<S>::bytes;
@@ -607,8 +610,12 @@ extern "C" int enerf_render_rays_tc(const EnerfCam* cam, int level, const float*
   p.num_samples = num_samples, p.depth_inv = depth_inv, p.white_bkgd = white_bkgd, p.viewdir_agg = viewdir_agg;
   p.out_rgb = out_rgb, p.out_depth = out_depth, p.out_weights = out_weights;
   p.win_x = p.win_y = p.win_w = 0, p.out_raw = p.out_z = nullptr, p.out_stride = p.out_off = 0;
-  P.wblob = wblob;
+  P.wblob = wblob, P.dbg = nullptr;
   P.n_tiles = (int)(((long long)n_rays * num_samples + 127) / 128);
+  {
+    const int rc = render_rays_ws_try_launch(P.r, wblob, P.n_tiles, stream);
+    if (rc != 1) return rc;
+  }
   switch (n_views) {
     case 2: return launch_rays_tc<2>(P, stream);
     case 3: return launch_rays_tc<3>(P, stream);
@@ -646,8 +653,12 @@ extern "C" int enerf_render_rays_raw_tc(const EnerfCam* cam, int level, const fl
   p.num_samples = num_samples, p.depth_inv = depth_inv, p.white_bkgd = 0, p.viewdir_agg = viewdir_agg;
   p.out_rgb = p.out_depth = p.out_weights = nullptr;
   p.win_x = x, p.win_y = y, p.win_w = w, p.out_raw = out_raw, p.out_z = out_z, p.out_stride = out_stride, p.out_off = out_off;
-  P.wblob = wblob;
+  P.wblob = wblob, P.dbg = nullptr;
   P.n_tiles = (int)(((long long)p.n_rays * num_samples + 127) / 128);
+  {
+    const int rc = render_rays_ws_try_launch(P.r, wblob, P.n_tiles, stream);
+    if (rc != 1) return rc;
+  }
   switch (n_views) {
     case 2: return launch_rays_tc<2>(P, stream);
     case 3: return launch_rays_tc<3>(P, stream);

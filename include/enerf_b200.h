@@ -265,6 +265,11 @@ ENERF_API int enerf_tc_conv(int kind, int KD, int KH, int stride, int cin, int c
                             int W, const float* wpack, const float* bias, const float* skip, float* out, float* out2,
                             int out_cstride, int out_coff, void* stream);
 
+/* Diagnostic: which kernel serves enerf_render_rays_tc / enerf_render_rays_raw_tc.  0 = auto: the warp-specialised
+ * kernel (csrc/render_rays_ws.cu: gather warpgroups + a consumer warpgroup, factored MLP) for 2-3 source views, the
+ * single-role kernel (csrc/render_rays_tc.cu) for 4; 1 = the single-role kernel always. */
+ENERF_API int enerf_render_rays_tc_select(int impl);
+
 /* Diagnostic / tuning of the persistent TMA-fed convolution kernel (csrc/tc_conv2.cu) behind enerf_tc_conv and the
  * conv stacks: impl 0 = auto (it takes every stride-1 / transposed layer whose weights fit in shared memory),
  * 1 = csrc/tc_conv.cu's kernel only, 2 = same as 0; nmma = MMA-issuing warps per CTA (1|2); ctas_per_sm (1|2);
