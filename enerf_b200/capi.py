@@ -59,6 +59,7 @@ _SIGS = {
     "enerf_tc_conv_debug": (_i, [_vp]),
     "enerf_tc_conv_tune": (_i, [_i, _i, _i]),
     "enerf_tc_conv2_tune": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "enerf_tc_conv2_fuse_lateral": (_i, [_i]),
     "enerf_tc_mma_bench": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "enerf_render_rays_debug": (_i, [_vp]),
     "enerf_tc_selftest": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
@@ -135,7 +136,7 @@ def feature_net(weights, src_inps, feat_l0, feat_l1, feat_l2, workspace, tensor_
     _check(lib().enerf_feature_net(ptr_array(weights), len(weights), ptr(src_inps), S, H, W, ptr(feat_l0), ptr(feat_l1),
                                    ptr(feat_l2), workspace.data_ptr(), workspace.numel() * workspace.element_size(),
                                    int(tensor_cores), part, stream()),
-           "enerf_feature_net", launches={0: 11, 1: 7, 2: 4}[part])
+           "enerf_feature_net", launches={0: 11, 1: 7, 2: 4}[part] - (1 if (tensor_cores and part != 1 and _FUSE_LAT and _CONV_IMPL != 1) else 0))
 
 
 def pack_img_feat(feat, src_inps, out):
@@ -256,8 +257,19 @@ def tc_conv_tune(tz=0, ty=0, fold=-1):
     _check(lib().enerf_tc_conv_tune(int(tz), int(ty), int(fold)), "enerf_tc_conv_tune", launches=0)
 
 
+_FUSE_LAT, _CONV_IMPL = True, 0     # mirrors of the library's switches, for the launch count only
+
+
 def tc_conv2_tune(impl=0, nmma=1, ctas_per_sm=1, tz=0, ty=0, kbc=0, slots=0):
+    global _CONV_IMPL
+    _CONV_IMPL = int(impl)
     _check(lib().enerf_tc_conv2_tune(int(impl), int(nmma), int(ctas_per_sm), int(tz), int(ty), int(kbc), int(slots)), "enerf_tc_conv2_tune", launches=0)
+
+
+def tc_conv2_fuse_lateral(on=True):
+    global _FUSE_LAT
+    _FUSE_LAT = bool(on)
+    _check(lib().enerf_tc_conv2_fuse_lateral(int(bool(on))), "enerf_tc_conv2_fuse_lateral", launches=0)
 
 
 def tc_selftest(A, B, D):

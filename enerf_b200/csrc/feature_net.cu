@@ -235,7 +235,18 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
     lateral_upadd_kernel<16><<<blocks, 256, 0, stream>>>(ws.c1, wts[14], wts[15], feat_l0, ws.f1, S, H2, W2);
     ENERF_CHECK_LAUNCH("feature_net.lat1");
   }
-  {
+  // lat0 + smooth0: on the tensor-core path the lateral (1x1 conv + bilinear x2 + add) is computed by smooth0's producer
+  // warps straight into the operand tile (tc_conv2.cu, PROD = 1): the 32-channel full-resolution map (126 MB at 512x640x3)
+  // is neither written nor re-read.  Same arithmetic in the same order as lateral_upadd_kernel -> bit-identical features.
+  bool fused0 = false;
+  if (tensor_cores && tc_conv2_fuse_lateral()) {
+    TcConvLayer L{0, 1, 3, 32, 8, TC_PLAIN, 0};
+    TcLateral lat{ws.c0, wts[16], wts[17], ws.f1};
+    rc = tc_conv2_try_launch(L, nullptr, S, H, W, wts[20], wts[21], nullptr, feat_l2, nullptr, 8, 0, false, stream, &lat);
+    if (rc == ENERF_OK) fused0 = true;
+    else if (rc != 1) return rc;
+  }
+  if (!fused0) {
     const long long total = (long long)S * H * W * 4;
     const int blocks = (int)((total + 1023) / 1024);     // 4 (pixel, slice) items per thread
     lateral_upadd_kernel<8><<<blocks, 256, 0, stream>>>(ws.c0, wts[16], wts[17], ws.f1, ws.f0, S, H, W);
@@ -243,7 +254,7 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
   }
   if (tensor_cores) {
     RUN(tc("feature_net.smooth1", 3, 32, 16, 0, ws.f1, H2, W2, wts[18], wts[19], feat_l1));
-    RUN(tc("feature_net.smooth0", 3, 32, 8, 0, ws.f0, H, W, wts[20], wts[21], feat_l2));
+    if (!fused0) RUN(tc("feature_net.smooth0", 3, 32, 8, 0, ws.f0, H, W, wts[20], wts[21], feat_l2));
   } else {
     RUN(launch_conv<Smooth1>("feature_net.smooth1", ws.f1, wts[18], wts[19], feat_l1, nullptr, S, H2, W2, 16, 0, stream));
     RUN(launch_conv<Smooth0>("feature_net.smooth0", ws.f0, wts[20], wts[21], feat_l2, nullptr, S, H, W, 8, 0, stream));

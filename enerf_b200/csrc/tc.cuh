@@ -1,6 +1,6 @@
 // tc.cuh -- hand-written sm_100a tensor-core plumbing (inline PTX): mbarrier, TMEM allocation,
 // tcgen05.mma (kind::tf32, cta_group::1, operands from shared memory, accumulator in TMEM),
-// tcgen05.commit / tcgen05.ld, TMA bulk copies.  No CUTLASS/CuTe: descriptor bit layouts follow
+// tcgen05.commit / tcgen05.ld, TMA bulk (1-D) copies; the tensor-map (tiled) TMA lives in tma.cuh.  No CUTLASS/CuTe: descriptor bit layouts follow
 // the PTX ISA "tcgen05 matrix descriptors" (cross-checked against cute/arch/mma_sm100_desc.hpp).
 //
 // Operand layout used everywhere in this library: K-major, SWIZZLE_NONE ("interleaved"):
@@ -167,16 +167,5 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
 }  // namespace tc
 }  // namespace enerf

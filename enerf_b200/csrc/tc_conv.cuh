@@ -37,11 +37,21 @@ struct TcConvLayer {
   int stride = 1;    // 1 | 2 (kind 0 only).  Dn,Hn,Wn passed to tc_conv_launch are ALWAYS the output grid.
 };
 
+// FeatureNet's lateral fused into the following smooth convolution (tc_conv2.cu, PROD = 1): the convolution's 32-channel
+// input  bilinear_x2(up_in) + (lat_b + lat_w^T lat_in)  is computed tile by tile in shared memory and never written to HBM.
+struct TcLateral {
+  const float* lat_in;   // (S,H,W,8) channels-last
+  const float* lat_w;    // [8][32]
+  const float* lat_b;    // [32]
+  const float* up_in;    // (S,H/2,W/2,32)
+};
+
 // tc_conv2.cu: the persistent TMA-fed kernel.  Returns ENERF_OK when it launched the layer, 1 when the layer is
 // not eligible (stride 2, weights beyond shared memory, ...) -- the caller then uses tc_conv.cu's kernel -- or an error.
 int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias, const float* skip,
-                        float* out, float* out2, int out_cstride, int out_coff, bool fold, cudaStream_t stream);
-int tc_conv2_impl();   // 0 auto, 1 tc_conv.cu only, 2 tc_conv2.cu where eligible
+                        float* out, float* out2, int out_cstride, int out_coff, bool fold, cudaStream_t stream, const TcLateral* lat = nullptr);
+int tc_conv2_impl();   // 0 auto, 1 tc_conv.cu only, 2 auto + stride-2 layers
+bool tc_conv2_fuse_lateral();
 
 int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias,
                    const float* skip, float* out, float* out2, int out_cstride, int out_coff, cudaStream_t stream);

@@ -17,6 +17,8 @@
 //                                    then hand the accumulator back
 //     The accumulators are double buffered in TMEM (2 x n_mt x N columns), so the epilogue of tile i runs under the
 //     MMAs of tile i+1, and the ring keeps 2-4 boxes in flight.  The layer's weights are loaded once per CTA.
+#include <string.h>
+
 #include <algorithm>
 
 #include "tc_conv.cuh"
@@ -30,7 +32,10 @@ struct TcConv2Params {
   int IZ, IY, IX;        // tile + halo
   int oz, oy, ox;        // halo origin = tile origin - (oz,oy,ox)
   int nx, ny, nz, n_tiles;
-  int tap_off[27];       // operand start offsets of the taps in 16-byte units (rows * row_bytes / 16)
+  int sz, sy, sx;        // stride per dimension (1|2): a stride-2 halo is staged as sz*sy*sx PHASE tiles X_r[q] = in[2q + r], each one
+  int n_phases;          //   TMA box with element stride 2 starting at 2*(tile origin - o) + r; a tap k - pad = 2d + r reads phase r at offset d
+  uint32_t phase_bytes;  // distance between phase tiles inside a slot (1024-aligned)
+  int tap_off[27];       // operand start offsets of the taps in 16-byte units (phase * phase_bytes + rows * row_bytes) / 16
   int kbc, n_kb;         // channels per K-block (box channel extent: 8 | 16 | 32), K-blocks per tile (cin / kbc)
   int n_slots;           // ring depth
   uint32_t slot_bytes, box_bytes, w_bytes, xch_bytes;
@@ -43,6 +48,12 @@ struct TcConv2Params {
   const float* skip;
   float* out;
   float* out2;
+  // PROD = 1 (FeatureNet smooth0 with the lateral fused in): the 32-channel input tile is COMPUTED by four producer
+  // warps instead of loaded: in[n,y,x,:] = bilinear_x2(up_in)[n,y,x,:] + (lat_b + lat_w^T lat_in[n,y,x,:]), zero outside the image
+  const float* lat_in;   // (S,H,W,8) channels-last
+  const float* lat_w;    // [8][32]
+  const float* lat_b;    // [32]
+  const float* up_in;    // (S,H/2,W/2,32)
 };
 
 __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
@@ -55,8 +66,9 @@ __device__ __forceinline__ bool elect_one() {
   return p != 0;
 }
 
-template <int NTAPS, int MODE, int FOLD, int NMMA>
-__global__ void __launch_bounds__(32 * (5 + NMMA)) tc_conv2_kernel(const __grid_constant__ CUtensorMap map, const TcConv2Params P) {
+template <int NTAPS, int MODE, int FOLD, int NMMA, int PROD = 0>
+__global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_kernel(const __grid_constant__ CUtensorMap map, const TcConv2Params P) {
+  constexpr int NP = PROD ? 4 : 1;      // producer warps
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], accf_bar[2], acce_bar[2], w_bar;
   __shared__ uint32_t tmem_base_s;
@@ -68,7 +80,7 @@ __global__ void __launch_bounds__(32 * (5 + NMMA)) tc_conv2_kernel(const __grid_
 
   if (t == 0) {
     for (int i = 0; i < 8; ++i) {
-      tc::mbar_init(&full_bar[i], 1);        // the producer's expect_tx arrival (+ the box's bytes)
+      tc::mbar_init(&full_bar[i], PROD ? 128 : 1);   // the producer's expect_tx arrival (+ the box's bytes) | every computing producer thread
       tc::mbar_init(&empty_bar[i], NMMA);    // one tcgen05.commit per MMA warp
     }
     for (int i = 0; i < 2; ++i) {
@@ -78,14 +90,89 @@ __global__ void __launch_bounds__(32 * (5 + NMMA)) tc_conv2_kernel(const __grid_
     tc::mbar_init(&w_bar, 1);
     tc::fence_mbar_init();
   }
-  if (warp == 1) tc::tmem_alloc(&tmem_base_s, P.tmem_cols);
+  if (warp == NP) tc::tmem_alloc(&tmem_base_s, P.tmem_cols);
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   const uint32_t row_bytes = (uint32_t)P.kbc * 4u;
 
-  if (warp == 0) {
+  if (PROD == 1 && warp < NP) {
+    // ============================== computing producer (lateral 1x1 conv + bilinear x2 + add) ==============================
+    // thread = (halo pixel, g): channels [4g, 4g+4) and [16+4g, 16+4g+4) -- 16-byte chunks g and 4+g of the pixel's 128-byte
+    // row, written at their SWIZZLE_128B position (chunk ^ (row & 7)); same arithmetic and order as lateral_upadd_kernel
+    if (lane == 0 && warp == 0) {
+      tc::mbar_expect_tx(&w_bar, P.w_bytes);
+      tc::tma_load_1d(w_s, P.wpack, P.w_bytes, &w_bar);
+    }
+    const int g = t & 3;
+    float4 wreg[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      wreg[2 * k] = ldg4(P.lat_w + k * 32 + g * 4);
+      wreg[2 * k + 1] = ldg4(P.lat_w + k * 32 + 16 + g * 4);
+    }
+    const float4 bias0 = ldg4(P.lat_b + g * 4), bias1 = ldg4(P.lat_b + 16 + g * 4);
+    const int H = P.Hn, W = P.Wn, hi = H / 2, wi = W / 2;
+    const float rh = (H > 1) ? (float)(hi - 1) / (float)(H - 1) : 0.f;
+    const float rw = (W > 1) ? (float)(wi - 1) / (float)(W - 1) : 0.f;
+    const int npix = P.IY * P.IX;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+      const int bx = tile % P.nx, by = (tile / P.nx) % P.ny, n = tile / (P.nx * P.ny);
+      const int x0 = bx * P.TX - P.ox, y0 = by * P.TY - P.oy;
+      const int slot = it % P.n_slots;
+      tc::mbar_wait(&empty_bar[slot], (uint32_t)(((it / P.n_slots) & 1) ^ 1));
+      unsigned char* dst = ring + (size_t)slot * P.slot_bytes;
+      for (int i = t; i < npix * 4; i += 128) {
+        const int pp = i >> 2;
+        const int yy = pp / P.IX, xx = pp - yy * P.IX;
+        const int y = y0 + yy, x = x0 + xx;
+        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+          const size_t pix = ((size_t)n * H + y) * W + x;
+          float acc[8] = {bias0.x, bias0.y, bias0.z, bias0.w, bias1.x, bias1.y, bias1.z, bias1.w};
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float4 v = ldg4(P.lat_in + pix * 8 + 4 * q);
+            const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 w0 = wreg[2 * (4 * q + j)], w1 = wreg[2 * (4 * q + j) + 1];
+              acc[0] = fmaf(xv[j], w0.x, acc[0]), acc[1] = fmaf(xv[j], w0.y, acc[1]), acc[2] = fmaf(xv[j], w0.z, acc[2]), acc[3] = fmaf(xv[j], w0.w, acc[3]);
+              acc[4] = fmaf(xv[j], w1.x, acc[4]), acc[5] = fmaf(xv[j], w1.y, acc[5]), acc[6] = fmaf(xv[j], w1.z, acc[6]), acc[7] = fmaf(xv[j], w1.w, acc[7]);
+            }
+          }
+          // bilinear x2 with align_corners=True (ATen upsample_bilinear2d lambdas)
+          const float h1r = rh * (float)y, w1r = rw * (float)x;
+          const int h1 = (int)h1r, w1 = (int)w1r;
+          const int h1p = (h1 < hi - 1) ? 1 : 0, w1p = (w1 < wi - 1) ? 1 : 0;
+          const float h1l = h1r - (float)h1, h0l = 1.f - h1l, w1l = w1r - (float)w1, w0l = 1.f - w1l;
+          const float* u00 = P.up_in + (((size_t)n * hi + h1) * wi + w1) * 32 + g * 4;
+          const float* u01 = u00 + (size_t)w1p * 32;
+          const float* u10 = u00 + (size_t)h1p * wi * 32;
+          const float* u11 = u10 + (size_t)w1p * 32;
+          float up[8];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float4 a = ldg4(u00 + 16 * q), b = ldg4(u01 + 16 * q), c = ldg4(u10 + 16 * q), dd = ldg4(u11 + 16 * q);
+            up[4 * q + 0] = h0l * (w0l * a.x + w1l * b.x) + h1l * (w0l * c.x + w1l * dd.x);
+            up[4 * q + 1] = h0l * (w0l * a.y + w1l * b.y) + h1l * (w0l * c.y + w1l * dd.y);
+            up[4 * q + 2] = h0l * (w0l * a.z + w1l * b.z) + h1l * (w0l * c.z + w1l * dd.z);
+            up[4 * q + 3] = h0l * (w0l * a.w + w1l * b.w) + h1l * (w0l * c.w + w1l * dd.w);
+          }
+          // reference order: interpolate(x) + lateral(y)   (feature_net.py:25)
+          o0 = make_float4(up[0] + acc[0], up[1] + acc[1], up[2] + acc[2], up[3] + acc[3]);
+          o1 = make_float4(up[4] + acc[4], up[5] + acc[5], up[6] + acc[6], up[7] + acc[7]);
+        }
+        unsigned char* rowp = dst + (size_t)pp * 128;
+        *reinterpret_cast<float4*>(rowp + ((g ^ (pp & 7)) << 4)) = o0;
+        *reinterpret_cast<float4*>(rowp + (((4 + g) ^ (pp & 7)) << 4)) = o1;
+      }
+      tc::fence_proxy_async();                 // my part of the tile -> visible to the tensor core
+      mbar_arrive1(&full_bar[slot]);
+    }
+  } else if (warp == 0) {
     // ============================== producer ==============================
     if (lane == 0) {
       tma::prefetch_desc(&map);
@@ -100,15 +187,19 @@ __global__ void __launch_bounds__(32 * (5 + NMMA)) tc_conv2_kernel(const __grid_
         const int slot = it % P.n_slots;
         tc::mbar_wait(&empty_bar[slot], (uint32_t)(((it / P.n_slots) & 1) ^ 1));
         if (lane == 0) {
-          tc::mbar_expect_tx(&full_bar[slot], P.box_bytes);
-          tma::load_4d(tc::smem_u32(ring + (size_t)slot * P.slot_bytes), &map, kb * P.kbc, x0, y0, z0, &full_bar[slot]);
+          tc::mbar_expect_tx(&full_bar[slot], P.box_bytes * (uint32_t)P.n_phases);
+          const uint32_t dst = tc::smem_u32(ring + (size_t)slot * P.slot_bytes);
+          for (int ph = 0; ph < P.n_phases; ++ph) {
+            const int rx = ph % P.sx, ry = (ph / P.sx) % P.sy, rz = ph / (P.sx * P.sy);
+            tma::load_4d(dst + (uint32_t)ph * P.phase_bytes, &map, kb * P.kbc, P.sx * x0 + rx, P.sy * y0 + ry, P.sz * z0 + rz, &full_bar[slot]);
+          }
         }
         __syncwarp();
       }
     }
-  } else if (warp <= NMMA) {
+  } else if (warp < NP + NMMA) {
     // ============================== MMA issue (converged warp, one elected lane issues) ==============================
-    const int mw = warp - 1;
+    const int mw = warp - NP;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t idesc = tc::idesc_tf32(128, P.N);
     const uint64_t a_hi = tma::smem_desc_swz(0, row_bytes, 0), b_hi = tc::smem_desc(0, (uint32_t)P.N * 16u, 128u);
@@ -296,28 +387,35 @@ __global__ void __launch_bounds__(32 * (5 + NMMA)) tc_conv2_kernel(const __grid_
   }
   tc::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem, P.tmem_cols);
+  if (warp == NP) tc::tmem_dealloc(tmem, P.tmem_cols);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-static int g_impl = 0;          // 0 auto, 1 force tc_conv.cu's kernel, 2 force this kernel where eligible
+static int g_fuse_lateral = 1;  // FeatureNet: lat0 (1x1 conv + bilinear x2 + add) computed inside smooth0's producer warps
+static int g_impl = 0;          // 0 auto, 1 force tc_conv.cu's kernel, 2 auto + the stride-2 layers as well
+static bool stride2_enabled() { return g_impl == 2; }
 static int g_nmma = 1;          // MMA-issuing warps per CTA (1 | 2)
 static int g_ctas_per_sm = 1;   // persistent CTAs per SM (1 | 2)
 static int g_tune2_tz = 0, g_tune2_ty = 0, g_tune2_fold = -1, g_tune2_kbc = 0, g_tune2_slots = 0;
 
 int tc_conv2_impl() { return g_impl; }
+bool tc_conv2_fuse_lateral() { return g_impl != 1 && g_fuse_lateral != 0; }
 
 // returns ENERF_OK when launched, 1 when the layer is not eligible (caller falls back to tc_conv_launch)
 int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias, const float* skip,
-                        float* out, float* out2, int out_cstride, int out_coff, bool fold_default, cudaStream_t stream) {
+                        float* out, float* out2, int out_cstride, int out_coff, bool fold_default, cudaStream_t stream, const TcLateral* lat) {
   const int stride = (L.kind == 0) ? L.stride : 1;
-  if (L.cin % 8 != 0 || L.cin > 64 || stride != 1) return 1;
+  if (lat != nullptr && !(L.kind == 0 && L.KD == 1 && L.KH == 3 && L.cin == 32 && stride == 1 && L.mode == TC_PLAIN && !fold_default && Hn % 2 == 0 && Wn % 2 == 0))
+    return 1;
+  if (L.cin % 8 != 0 || L.cin > 64 || (stride != 1 && stride != 2)) return 1;
+  if (stride == 2 && (fold_default || !stride2_enabled())) return 1;
   if (tma::encode_fn() == nullptr) return 1;
   TcConv2Params P;
   P.Dn = Dn, P.Hn = Hn, P.Wn = Wn;
   P.cout = L.cout, P.relu = L.relu, P.mode = L.mode;
   P.out_cstride = out_cstride, P.out_coff = out_coff;
   P.wpack = wpack, P.bias = bias, P.skip = skip, P.out = out, P.out2 = out2;
+  P.lat_in = lat ? lat->lat_in : nullptr, P.lat_w = lat ? lat->lat_w : nullptr, P.lat_b = lat ? lat->lat_b : nullptr, P.up_in = lat ? lat->up_in : nullptr;
   bool fold = fold_default;      // the weights are packed for the default rule (packing.tc_fold_kx): keep it
   const int n_real = (L.kind == 1) ? 8 * L.cout : fold ? 3 * L.cout : L.cout;
   P.N = (n_real + 15) / 16 * 16;
@@ -328,9 +426,20 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
   if (L.mode == TC_DECONV && !(L.cout % 8 == 0 && skip && bias)) return 1;
   if (L.mode == TC_PLAIN && !(L.cout % 8 == 0 && bias)) return 1;
 
+  P.sz = (stride == 2 && L.KD > 1) ? 2 : 1, P.sy = stride, P.sx = stride;
+  P.n_phases = P.sz * P.sy * P.sx;
+  // per-dimension tap decomposition  k - pad = s*d + r :  halo extent E = dmax - dmin, origin shift o = -dmin
+  auto dim_geom = [](int K, int s, int kind, int& E, int& o) {
+    if (kind == 1) { E = 1, o = 0; return; }
+    const int pad = K / 2;
+    if (s == 1) { E = K - 1, o = pad; return; }
+    const int dmin = -((pad + 1) / 2), dmax = (K - 1 - pad) / 2;
+    E = dmax - dmin, o = -dmin;
+  };
   int hz, hy, hx;
-  if (L.kind == 1) hz = hy = hx = 1, P.oz = P.oy = P.ox = 0;
-  else hz = L.KD - 1, hy = L.KH - 1, hx = L.KH - 1, P.oz = L.KD / 2, P.oy = L.KH / 2, P.ox = L.KH / 2;
+  dim_geom(L.KD, P.sz, L.kind, hz, P.oz);
+  dim_geom(L.KH, P.sy, L.kind, hy, P.oy);
+  dim_geom(L.KH, P.sx, L.kind, hx, P.ox);
   const bool is2d = (L.kind == 0 && L.KD == 1);
   P.TX = 32;
   P.TY = is2d ? 16 : 8;
@@ -341,6 +450,10 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
   }
   if (L.kind == 0 && L.KH == 1) P.TY = 8;
   if (L.kind == 1) P.TZ = 2, P.TY = (P.N <= 64) ? 3 : 4;
+  if (stride == 2) {
+    if (is2d) P.TY = 7;
+    else P.TZ = 2, P.TY = 3;
+  }
   if (g_tune2_tz > 0) P.TZ = g_tune2_tz;
   if (g_tune2_ty > 0) P.TY = g_tune2_ty;
   P.TZ = std::min(P.TZ, Dn), P.TY = std::min(P.TY, Hn);
@@ -350,11 +463,30 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
   for (;;) {
     P.IZ = P.TZ + hz, P.IY = P.TY + hy, P.IX = P.TX + hx;
     const int npix = P.IZ * P.IY * P.IX;
-    if (P.IZ > 256 || P.IY > 256 || P.IX > 256) return 1;
+    if (P.IZ * P.sz > 256 || P.IY * P.sy > 256 || P.IX * P.sx > 256) return 1;
     const int pmax = ((P.TZ - 1) * P.IY + (P.TY - 1)) * P.IX + P.TX - 1;
     P.n_mt = (pmax + (fold ? 2 : 0)) / 128 + 1;
-    int max_tap_rows = 0, tap_rows[27];
-    if (L.kind == 1) {
+    int max_tap_rows = 0, tap_rows[27], tap_phase[27];
+    for (int i = 0; i < 27; ++i) tap_phase[i] = 0;
+    if (stride == 2) {
+      auto split = [](int k, int K, int o, int& d, int& r) {   // k - pad = 2*d + r, returns d' = d + o
+        const int tt = k - K / 2;
+        const int fl = (tt >= 0) ? tt / 2 : -((-tt + 1) / 2);
+        r = tt - 2 * fl, d = fl + o;
+      };
+      int i = 0;
+      for (int kz = 0; kz < L.KD; ++kz)
+        for (int ky = 0; ky < L.KH; ++ky)
+          for (int kx = 0; kx < L.KH; ++kx) {
+            int dz = 0, rz = 0, dy, ry, dx, rx;
+            if (P.sz == 2) split(kz, L.KD, P.oz, dz, rz);
+            else dz = kz - L.KD / 2 + P.oz;
+            split(ky, L.KH, P.oy, dy, ry);
+            split(kx, L.KH, P.ox, dx, rx);
+            tap_phase[i] = (rz * P.sy + ry) * P.sx + rx;
+            tap_rows[i++] = (dz * P.IY + dy) * P.IX + dx;
+          }
+    } else if (L.kind == 1) {
       for (int d = 0; d < 8; ++d) tap_rows[d] = (((d >> 2) & 1) * P.IY + ((d >> 1) & 1)) * P.IX + (d & 1);
     } else if (fold) {
       for (int kz = 0, i = 0; kz < L.KD; ++kz)
@@ -373,7 +505,7 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
     bool placed = false;
     const int cands[3] = {32, 16, 8};
     for (int ci = 0; ci < 3 && !placed && tmem_ok; ++ci) {
-      const int kbc = g_tune2_kbc > 0 ? g_tune2_kbc : cands[ci];
+      const int kbc = lat ? 32 : g_tune2_kbc > 0 ? g_tune2_kbc : cands[ci];
       if (kbc > L.cin || L.cin % kbc) {
         if (g_tune2_kbc > 0) break;
         continue;
@@ -381,7 +513,8 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
       const uint32_t rb = (uint32_t)kbc * 4u;
       // garbage rows of the last M-tile read past the box: keep them inside the slot
       const uint32_t rows_alloc = (uint32_t)std::max(npix, P.n_mt * 128 + max_tap_rows + 2);
-      const uint32_t slot = (uint32_t)align_up((size_t)rows_alloc * rb, 1024);
+      const uint32_t phase_stride = (uint32_t)align_up((size_t)npix * rb, 1024);
+      const uint32_t slot = (uint32_t)align_up((size_t)(P.n_phases - 1) * phase_stride + (size_t)rows_alloc * rb, 1024);
       const size_t fixed = 1024 + align_up(P.w_bytes, 128) + P.xch_bytes + 256;
       int slots = (int)((budget - std::min(budget, fixed)) / slot);
       slots = std::min(slots, 4);
@@ -389,10 +522,11 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
       const int want = (ci == 2 || g_tune2_kbc > 0) ? 2 : 3;      // fall to narrower K-blocks rather than a 2-deep ring
       if (slots >= want || (slots >= 2 && kbc == 8)) {
         P.kbc = kbc, P.n_kb = L.cin / kbc, P.n_slots = slots, P.slot_bytes = slot, P.box_bytes = (uint32_t)npix * rb;
-        for (int i = 0; i < n_taps; ++i) P.tap_off[i] = tap_rows[i] * (int)(rb / 16);
+        P.phase_bytes = phase_stride;
+        for (int i = 0; i < n_taps; ++i) P.tap_off[i] = (int)((tap_phase[i] * phase_stride + (uint32_t)tap_rows[i] * rb) / 16);
         placed = true;
       }
-      if (g_tune2_kbc > 0) break;
+      if (g_tune2_kbc > 0 || lat) break;
     }
     P.nx = ceil_div(Wn, P.TX), P.ny = ceil_div(Hn, P.TY), P.nz = ceil_div(Dn, P.TZ);
     P.n_tiles = P.nx * P.ny * P.nz;
@@ -410,11 +544,15 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
 
   // tensor map of the input: channels-last (D,H,W,C) fp32 -> dims {C, W, H, D}, box {kbc, IX, IY, IZ}
   CUtensorMap map;
-  {
-    const uint64_t dims[4] = {(uint64_t)L.cin, (uint64_t)Wn, (uint64_t)Hn, (uint64_t)Dn};
-    const uint64_t strides[3] = {(uint64_t)L.cin * 4, (uint64_t)Wn * L.cin * 4, (uint64_t)Hn * Wn * L.cin * 4};
-    const uint32_t box[4] = {(uint32_t)P.kbc, (uint32_t)P.IX, (uint32_t)P.IY, (uint32_t)P.IZ};
-    const int rc = tma::encode_f32(&map, in, 4, dims, strides, box, nullptr, tma::swizzle_for_bytes(P.kbc * 4));
+  memset(&map, 0, sizeof(map));
+  if (lat == nullptr) {
+    // stride 2: the row grid is the OUTPUT grid, the tensor is the (even) input; a box traverses s*I elements with element stride s
+    const uint64_t Wi = (uint64_t)Wn * P.sx, Hi = (uint64_t)Hn * P.sy, Di = (uint64_t)Dn * P.sz;
+    const uint64_t dims[4] = {(uint64_t)L.cin, Wi, Hi, Di};
+    const uint64_t strides[3] = {(uint64_t)L.cin * 4, Wi * L.cin * 4, Hi * Wi * L.cin * 4};
+    const uint32_t box[4] = {(uint32_t)P.kbc, (uint32_t)(P.IX * P.sx), (uint32_t)(P.IY * P.sy), (uint32_t)(P.IZ * P.sz)};
+    const uint32_t estr[4] = {1u, (uint32_t)P.sx, (uint32_t)P.sy, (uint32_t)P.sz};
+    const int rc = tma::encode_f32(&map, in, 4, dims, strides, box, estr, tma::swizzle_for_bytes(P.kbc * 4));
     ENERF_REQUIRE(rc == 0, ENERF_ECUDA, "tc_conv2: cuTensorMapEncodeTiled failed (%d) for a (%d,%d,%d,%d) tensor, box (%d,%d,%d,%d)", rc, Dn, Hn, Wn, L.cin,
                   P.kbc, P.IX, P.IY, P.IZ);
   }
@@ -429,13 +567,35 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
       ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv2: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));               \
       smem_set = smem;                                                                                                                    \
     }                                                                                                                                     \
-    tc_conv2_kernel<NT, MD, FD, NM><<<grid, 32 * (5 + NM), smem, stream>>>(map, P);                                                       \
+    tc_conv2_kernel<NT, MD, FD, NM><<<grid, 32 * (4 + NM + 1), smem, stream>>>(map, P);                                                       \
   } while (0)
 #define TC2_DISPATCH(NT, MD, FD)             \
   do {                                       \
     if (g_nmma >= 2) TC2_LAUNCH(NT, MD, FD, 2); \
     else TC2_LAUNCH(NT, MD, FD, 1);          \
   } while (0)
+  if (lat != nullptr) {
+    const size_t smem_l = smem;
+    static PerDeviceSize lat_set_pd[2];
+    size_t& lat_set = lat_set_pd[g_nmma >= 2 ? 1 : 0].cur();
+    if (g_nmma >= 2) {
+      if (smem_l > lat_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv2_kernel<9, TC_PLAIN, 0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
+        ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv2(lateral): cudaFuncSetAttribute(%zu): %s", smem_l, cudaGetErrorString(e));
+        lat_set = smem_l;
+      }
+      tc_conv2_kernel<9, TC_PLAIN, 0, 2, 1><<<grid, 32 * (4 + 2 + 4), smem_l, stream>>>(map, P);
+    } else {
+      if (smem_l > lat_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv2_kernel<9, TC_PLAIN, 0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
+        ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv2(lateral): cudaFuncSetAttribute(%zu): %s", smem_l, cudaGetErrorString(e));
+        lat_set = smem_l;
+      }
+      tc_conv2_kernel<9, TC_PLAIN, 0, 1, 1><<<grid, 32 * (4 + 1 + 4), smem_l, stream>>>(map, P);
+    }
+    ENERF_CHECK_LAUNCH("tc_conv2(lateral)");
+    return ENERF_OK;
+  }
   if (L.kind == 1) TC2_DISPATCH(8, TC_DECONV, 0);
   else if (fold && n_taps == 9 && L.mode == TC_PLAIN) TC2_DISPATCH(9, TC_PLAIN, 1);
   else if (fold && n_taps == 9 && L.mode == TC_HEAD) TC2_DISPATCH(9, TC_HEAD, 1);
@@ -445,6 +605,7 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
   else if (!fold && n_taps == 27 && L.mode == TC_HEAD) TC2_DISPATCH(27, TC_HEAD, 0);
   else if (!fold && n_taps == 27 && L.mode == TC_SINGLE) TC2_DISPATCH(27, TC_SINGLE, 0);
   else if (!fold && n_taps == 9 && L.mode == TC_PLAIN) TC2_DISPATCH(9, TC_PLAIN, 0);
+  else if (!fold && n_taps == 25 && L.mode == TC_PLAIN) TC2_DISPATCH(25, TC_PLAIN, 0);
   else if (!fold && n_taps == 1 && L.mode == TC_PLAIN) TC2_DISPATCH(1, TC_PLAIN, 0);
   else return 1;
 #undef TC2_DISPATCH
@@ -457,6 +618,11 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
 
 // Diagnostic / tuning of the TMA-fed kernel: impl 0 auto | 1 tc_conv.cu only | 2 this kernel where eligible;
 // nmma = MMA-issuing warps (1|2); ctas_per_sm (1|2); tz/ty/kbc/slots = forced tile / K-block / ring depth (0 = built-in).
+extern "C" int enerf_tc_conv2_fuse_lateral(int on) {
+  enerf::g_fuse_lateral = on;
+  return ENERF_OK;
+}
+
 extern "C" int enerf_tc_conv2_tune(int impl, int nmma, int ctas_per_sm, int tz, int ty, int kbc, int slots) {
   using namespace enerf;
   ENERF_REQUIRE(impl >= 0 && impl <= 2 && nmma >= 1 && nmma <= 2 && ctas_per_sm >= 1 && ctas_per_sm <= 2 && (kbc == 0 || kbc == 8 || kbc == 16 || kbc == 32),

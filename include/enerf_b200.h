@@ -275,6 +275,9 @@ ENERF_API int enerf_render_rays_tc_select(int impl);
  * 1 = csrc/tc_conv.cu's kernel only, 2 = same as 0; nmma = MMA-issuing warps per CTA (1|2); ctas_per_sm (1|2);
  * tz, ty, kbc (8|16|32), slots: forced tile / K-block width / ring depth, 0 = built-in choice. */
 ENERF_API int enerf_tc_conv2_tune(int impl, int nmma, int ctas_per_sm, int tz, int ty, int kbc, int slots);
+/* Diagnostic: 1 (default) = enerf_feature_net computes lat0 (1x1 lateral + bilinear x2 + add, feature_net.py:31-35) inside
+ * smooth0's producer warps on the tensor-core path; 0 = separate lateral kernel + plain smooth0 (bit-identical features). */
+ENERF_API int enerf_tc_conv2_fuse_lateral(int on);
 
 /* Diagnostic: when buf != NULL, CTA (0,0,0) of every later enerf_tc_conv-family launch writes 64
  * %globaltimer phase stamps (ns) into buf (device memory, 64 x u64).  NULL switches it off. */

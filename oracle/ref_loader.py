@@ -2,8 +2,8 @@
 
 Only usable where a reference tree exists ($ENERF_REF or /root/reference); the GPU box has none,
 so nothing in the `-m gpu` tests, smoke() or bench.py calls this.  It is used by
-`oracle/make_golden.py` (to mint tests/golden/*.pt) and by the optional
-`tests/test_oracle_vs_reference.py`, which skips when the tree is absent.
+`oracle/make_golden.py` (to mint tests/golden/*.pt) and by `tests/test_reference_boundary.py` (the reference's own
+`make_network(cfg)` loading the drop-in modules), which skips when the tree is absent.
 
 What it does: puts two shims on sys.path (kornia.utils.create_meshgrid,
 imp.load_source), sets $workspace (lib/config/config.py:10), fakes argv before `import lib.config`

@@ -196,11 +196,14 @@ TC_CONV_CASES = [
     (0, 3, 3, 32, 8, 0, 1, (16, 64, 80)),    # MinCostRegNet conv0: 32 channels = two 16-channel K-blocks
     (0, 3, 3, 8, 9, 1, 0, (8, 128, 160)),    # head
     (1, 3, 3, 16, 8, 2, 0, (4, 64, 80)),     # conv11 (transposed), many tiles
+    (0, 3, 3, 8, 16, 0, 1, (8, 128, 160), 2),   # conv1 (stride 2) with many tiles
+    (0, 1, 5, 8, 16, 0, 1, (3, 256, 320), 2),   # FeatureNet conv1.0 (5x5 stride 2) with many tiles
 ]
 
 # which kernel runs the layer: csrc/tc_conv.cu ("v1"), or the persistent TMA-fed csrc/tc_conv2.cu where it is eligible
 # (auto = the shipped policy; + 2 MMA-issuing warps; + 2 persistent CTAs per SM)
-TC_CONV_IMPLS = {"v1": dict(impl=1), "auto": dict(impl=0), "nmma2": dict(impl=0, nmma=2), "2cta": dict(impl=0, ctas_per_sm=2)}
+TC_CONV_IMPLS = {"v1": dict(impl=1), "auto": dict(impl=0), "nmma2": dict(impl=0, nmma=2), "2cta": dict(impl=0, ctas_per_sm=2),
+                 "s2": dict(impl=2)}      # impl 2: the stride-2 layers on tc_conv2 as well (phase tiles = TMA boxes with element stride 2)
 
 
 @pytest.mark.parametrize("impl", list(TC_CONV_IMPLS))
@@ -208,8 +211,8 @@ TC_CONV_IMPLS = {"v1": dict(impl=1), "auto": dict(impl=0), "nmma2": dict(impl=0,
 def test_tc_conv_layer(case, impl):
     kind, KD, KH, cin, cout, mode, relu, dims = case[:8]
     stride = case[8] if len(case) > 8 else 1
-    if impl != "v1" and stride != 1:
-        pytest.skip("stride-2 layers always run on csrc/tc_conv.cu")
+    if (stride != 1) != (impl == "s2") and impl != "v1":
+        pytest.skip("stride-2 layers run on csrc/tc_conv.cu unless impl 2 is selected; impl 2 is exercised on them only")
     if impl in ("nmma2", "2cta") and dims[1] * dims[2] < 64 * 80:
         pytest.skip("variant exercised on the larger cases")
     """tcgen05 implicit-GEMM convolution vs torch's fp32 conv on the same (TF32-rounded) operands.
@@ -263,6 +266,42 @@ def test_tc_conv_layer(case, impl):
     err = (got - refc).abs().max().item()
     assert not torch.isnan(got).any()
     assert err < 2e-3 * max(1.0, refc.abs().max().item()), f"max abs err {err} (ref max {refc.abs().max().item()})"
+
+
+@pytest.mark.parametrize("H,W,S", [(64, 96, 2), (512, 640, 3)])
+def test_feature_net_fused_lateral_is_bit_identical(H, W, S):
+    """FeatureNet on the tensor-core path: lat0 computed inside smooth0's producer warps (tc_conv2.cu, PROD = 1) against the
+    separate lateral kernel + smooth0, and both tcgen05 convolution kernels against each other: identical arithmetic in
+    identical order, so level_2 / level_1 / level_0 features must be EQUAL."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from enerf_b200 import capi, packing
+    from enerf_b200 import config as bcfg
+    import stage_harness
+    cfg = bcfg.make_cfg(volume_planes=[8, 8], render_if=[False, True])
+    sd, _ = stage_harness.make_case(64, 96, 2, cfg, seed=5)
+    g = torch.Generator().manual_seed(H + S)
+    src = (2 * torch.rand(S, 3, H, W, generator=g) - 1).cuda()
+    pk = packing.pack_feature_net(sd, torch.device("cuda"), tensor_cores=True)
+    ws = torch.empty(capi.feature_net_workspace_bytes(S, H, W) // 4, device="cuda")
+    outs = {}
+    try:
+        for name, impl, fuse in (("v1", 1, False), ("v2", 0, False), ("v2_fused", 0, True)):
+            capi.tc_conv2_tune(impl=impl)
+            capi.tc_conv2_fuse_lateral(fuse)
+            f0 = torch.full((S, H // 4, W // 4, 32), float("nan"), device="cuda")
+            f1 = torch.full((S, H // 2, W // 2, 16), float("nan"), device="cuda")
+            f2 = torch.full((S, H, W, 8), float("nan"), device="cuda")
+            capi.feature_net(pk, src, f0, f1, f2, ws, tensor_cores=True)
+            torch.cuda.synchronize()
+            outs[name] = (f0, f1, f2)
+    finally:
+        capi.tc_conv2_tune()
+        capi.tc_conv2_fuse_lateral(True)
+    for name in ("v2", "v2_fused"):
+        for lvl in range(3):
+            assert not torch.isnan(outs[name][lvl]).any(), (name, lvl)
+            assert torch.equal(outs[name][lvl], outs["v1"][lvl]), (name, lvl, (outs[name][lvl] - outs["v1"][lvl]).abs().max().item())
 
 
 def test_device_ray_generation_matches_data_layer(harness):
