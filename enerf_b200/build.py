@@ -30,6 +30,8 @@ def units():
     u = [(n, n + ".cu", []) for n in ("camera", "feature_net", "cost_volume", "cost_reg", "render_rays", "render_rays_tc", "render_rays_ws", "tc_selftest", "tc_probe", "tc_conv", "tc_conv2", "mask_rays", "eval_ops", "composite")]
     for fc, s, st in RAY_INSTANCES:
         u.append((f"rr_{fc}_{s}_{st}", "render_rays_inst.cu", [f"-DRR_FC={fc}", f"-DRR_S={s}", f"-DRR_STATIC={st}"]))
+    for sv in range(2, 9):
+        u.append((f"rtc_{sv}", "render_rays_tc_inst.cu", [f"-DRTC_S={sv}"]))
     extra = os.path.join(CSRC, "units.txt")  # optional additional units: "<name> <source> [-Dflags...]"
     if os.path.exists(extra):
         for line in open(extra):

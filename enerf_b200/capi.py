@@ -313,7 +313,7 @@ def render_rays_tc_select(impl=0):
 
 
 def tc_ray_kernel_supports(feat_ch, n_views, num_samples):
-    return feat_ch == 8 and 2 <= n_views <= 4 and num_samples in (1, 2, 4, 8)
+    return feat_ch == 8 and 2 <= n_views <= MAX_VIEWS and num_samples in (1, 2, 4, 8)
 
 
 def tc_conv(kind, KD, KH, cout, mode, relu, x, wpack, bias, skip, out, out2=None, out_cstride=None, out_coff=0, stride=1):

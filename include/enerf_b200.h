@@ -220,7 +220,7 @@ ENERF_API int enerf_render_rays_raw(const EnerfCam* cam, int level, const float*
                                     int depth_inv, int viewdir_agg, float* out_raw, float* out_z, int out_stride, int out_off,
                                     void* stream);
 /* enerf_render_rays_raw with the MLP on the tensor cores (wblob: packing.pack_nerf_tc_novox); same
- * support matrix as enerf_render_rays_tc (feat_ch 8, n_views 2..4, num_samples in {1,2,4,8}). */
+ * support matrix as enerf_render_rays_tc (feat_ch 8, n_views 2..8, num_samples in {1,2,4,8}). */
 ENERF_API int enerf_render_rays_raw_tc(const EnerfCam* cam, int level, const float* wblob, const float* rays, const int* window,
                                        const float* depth, const float* std, const float* near_far, int hv, int wv,
                                        const float* img_feat_rgb, int n_views, int Hr, int Wr, int feat_ch, int num_samples,
@@ -242,7 +242,7 @@ ENERF_API int enerf_pack_rgb8(const float* rgb, int H, int W, int flip_vertical,
 
 /* Tensor-core variant of enerf_render_rays (same stage, same arguments, same outputs): the MLP
  * contractions run as tcgen05.mma kind::tf32 with accumulators in TMEM, 128 sample points per CTA.
- * feat_ch == 8, n_views in [2,4], num_samples in {1,2,4,8}.  wblob = one packed device buffer of
+ * feat_ch == 8, n_views in [2,8], num_samples in {1,2,4,8}.  wblob = one packed device buffer of
  * 10,392 floats (enerf_b200/packing.py::pack_nerf_tc: TF32-rounded B operands in the K-major
  * 16-byte-chunk layout of csrc/tc.cuh, followed by the fp32 bias / 1-wide vectors). */
 ENERF_API int enerf_render_rays_tc(const EnerfCam* cam, int level, const float* wblob, const float* rays, int n_rays,
