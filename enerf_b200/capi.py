@@ -60,6 +60,7 @@ _SIGS = {
     "enerf_tc_conv_tune": (_i, [_i, _i, _i]),
     "enerf_tc_conv2_tune": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "enerf_tc_conv2_fuse_lateral": (_i, [_i]),
+    "enerf_tc_conv2_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_i)]),
     "enerf_tc_mma_bench": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "enerf_render_rays_debug": (_i, [_vp]),
     "enerf_tc_selftest": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
@@ -264,6 +265,19 @@ def tc_conv2_tune(impl=0, nmma=1, ctas_per_sm=1, tz=0, ty=0, kbc=0, slots=0):
     global _CONV_IMPL
     _CONV_IMPL = int(impl)
     _check(lib().enerf_tc_conv2_tune(int(impl), int(nmma), int(ctas_per_sm), int(tz), int(ty), int(kbc), int(slots)), "enerf_tc_conv2_tune", launches=0)
+
+
+PLAN_FIELDS = ("TZ TY TX IZ IY IX oz oy ox nx ny nz n_tiles sz sy sx n_phases phase_bytes kbc n_kb n_slots slot_bytes box_bytes "
+               "N n_mt n_acc n_taps fold tmem_cols w_bytes xch_bytes").split()
+
+
+def tc_conv2_plan(kind, KD, KH, stride, cin, cout, mode, D, H, W, fold, lateral=False, n_sm=148):
+    """Launch geometry of csrc/tc_conv2.cu for a layer (no GPU needed); dict of PLAN_FIELDS + 'tap_off' (16-byte units)."""
+    out = (ctypes.c_int * 67)()
+    _check(lib().enerf_tc_conv2_plan(kind, KD, KH, stride, cin, cout, mode, D, H, W, int(fold), int(lateral), n_sm, out), "enerf_tc_conv2_plan", launches=0)
+    plan = {k: out[i] for i, k in enumerate(PLAN_FIELDS)}
+    plan["tap_off"] = [out[40 + i] for i in range(plan["n_taps"])]
+    return plan
 
 
 def tc_conv2_fuse_lateral(on=True):

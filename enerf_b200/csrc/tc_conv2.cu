@@ -402,20 +402,18 @@ int tc_conv2_impl() { return g_impl; }
 bool tc_conv2_fuse_lateral() { return g_impl != 1 && g_fuse_lateral != 0; }
 
 // returns ENERF_OK when launched, 1 when the layer is not eligible (caller falls back to tc_conv_launch)
-int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias, const float* skip,
-                        float* out, float* out2, int out_cstride, int out_coff, bool fold_default, cudaStream_t stream, const TcLateral* lat) {
+// Host geometry of a launch, free of CUDA calls (so tests/test_host_cpu.py can emulate the kernel from it on a CPU-only
+// box through enerf_tc_conv2_plan): tile, halo, taps, K-block, ring, accumulators.  Returns 0, or 1 = not eligible.
+static int tc_conv2_plan(const TcConvLayer& L, int Dn, int Hn, int Wn, bool fold_default, bool lat, bool has_bias, bool has_skip, int n_sm,
+                         TcConv2Params& P, int& n_taps_out, bool& fold_out) {
   const int stride = (L.kind == 0) ? L.stride : 1;
-  if (lat != nullptr && !(L.kind == 0 && L.KD == 1 && L.KH == 3 && L.cin == 32 && stride == 1 && L.mode == TC_PLAIN && !fold_default && Hn % 2 == 0 && Wn % 2 == 0))
+  if (lat && !(L.kind == 0 && L.KD == 1 && L.KH == 3 && L.cin == 32 && stride == 1 && L.mode == TC_PLAIN && !fold_default && Hn % 2 == 0 && Wn % 2 == 0))
     return 1;
   if (L.cin % 8 != 0 || L.cin > 64 || (stride != 1 && stride != 2)) return 1;
   if (stride == 2 && (fold_default || !stride2_enabled())) return 1;
-  if (tma::encode_fn() == nullptr) return 1;
-  TcConv2Params P;
   P.Dn = Dn, P.Hn = Hn, P.Wn = Wn;
   P.cout = L.cout, P.relu = L.relu, P.mode = L.mode;
-  P.out_cstride = out_cstride, P.out_coff = out_coff;
-  P.wpack = wpack, P.bias = bias, P.skip = skip, P.out = out, P.out2 = out2;
-  P.lat_in = lat ? lat->lat_in : nullptr, P.lat_w = lat ? lat->lat_w : nullptr, P.lat_b = lat ? lat->lat_b : nullptr, P.up_in = lat ? lat->up_in : nullptr;
+  const bool skip = has_skip, bias = has_bias;
   bool fold = fold_default;      // the weights are packed for the default rule (packing.tc_fold_kx): keep it
   const int n_real = (L.kind == 1) ? 8 * L.cout : fold ? 3 * L.cout : L.cout;
   P.N = (n_real + 15) / 16 * 16;
@@ -458,7 +456,6 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
   if (g_tune2_ty > 0) P.TY = g_tune2_ty;
   P.TZ = std::min(P.TZ, Dn), P.TY = std::min(P.TY, Hn);
 
-  const int n_sm = device_sm_count();
   const size_t budget = (g_ctas_per_sm >= 2 ? 110 : 216) * 1024;
   for (;;) {
     P.IZ = P.TZ + hz, P.IY = P.TY + hy, P.IX = P.TX + hx;
@@ -541,6 +538,21 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
   uint32_t cols = 32;
   while ((int)cols < P.n_acc * P.n_mt * P.N) cols <<= 1;
   P.tmem_cols = cols;
+  n_taps_out = n_taps, fold_out = fold;
+  return 0;
+}
+
+int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias, const float* skip,
+                        float* out, float* out2, int out_cstride, int out_coff, bool fold_default, cudaStream_t stream, const TcLateral* lat) {
+  if (tma::encode_fn() == nullptr) return 1;
+  TcConv2Params P;
+  int n_taps = 0;
+  bool fold = false;
+  const int n_sm = device_sm_count();
+  if (tc_conv2_plan(L, Dn, Hn, Wn, fold_default, lat != nullptr, bias != nullptr, skip != nullptr, n_sm, P, n_taps, fold) != 0) return 1;
+  P.out_cstride = out_cstride, P.out_coff = out_coff;
+  P.wpack = wpack, P.bias = bias, P.skip = skip, P.out = out, P.out2 = out2;
+  P.lat_in = lat ? lat->lat_in : nullptr, P.lat_w = lat ? lat->lat_w : nullptr, P.lat_b = lat ? lat->lat_b : nullptr, P.up_in = lat ? lat->up_in : nullptr;
 
   // tensor map of the input: channels-last (D,H,W,C) fp32 -> dims {C, W, H, D}, box {kbc, IX, IY, IZ}
   CUtensorMap map;
@@ -618,6 +630,30 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
 
 // Diagnostic / tuning of the TMA-fed kernel: impl 0 auto | 1 tc_conv.cu only | 2 this kernel where eligible;
 // nmma = MMA-issuing warps (1|2); ctas_per_sm (1|2); tz/ty/kbc/slots = forced tile / K-block / ring depth (0 = built-in).
+// The launch geometry tc_conv2 would use for a layer on a device with n_sm SMs, without touching a GPU (CPU-testable):
+// out[0..39] = TZ TY TX IZ IY IX oz oy ox nx ny nz n_tiles sz sy sx n_phases phase_bytes kbc n_kb n_slots slot_bytes box_bytes
+//              N n_mt n_acc n_taps fold tmem_cols w_bytes xch_bytes, out[40..66] = tap_off (16-byte units).  (D,H,W) = row grid.
+extern "C" int enerf_tc_conv2_plan(int kind, int KD, int KH, int stride, int cin, int cout, int mode, int D, int H, int W, int fold, int lateral, int n_sm,
+                                   int* out) {
+  using namespace enerf;
+  ENERF_REQUIRE(out && n_sm > 0, ENERF_EINVAL, "tc_conv2_plan: bad arguments");
+  TcConvLayer L{kind, KD, KH, cin, cout, mode, 0, stride};
+  TcConv2Params P;
+  int n_taps = 0;
+  bool f = false;
+  const int rc = tc_conv2_plan(L, D, H, W, fold != 0, lateral != 0, true, true, n_sm, P, n_taps, f);
+  if (rc != 0) {
+    set_error("tc_conv2_plan: layer not eligible for the TMA-fed kernel");
+    return ENERF_EUNSUPPORTED;
+  }
+  const int v[40] = {P.TZ, P.TY, P.TX, P.IZ, P.IY, P.IX, P.oz, P.oy, P.ox, P.nx, P.ny, P.nz, P.n_tiles, P.sz, P.sy, P.sx, P.n_phases, (int)P.phase_bytes,
+                     P.kbc, P.n_kb, P.n_slots, (int)P.slot_bytes, (int)P.box_bytes, P.N, P.n_mt, P.n_acc, n_taps, f ? 1 : 0, (int)P.tmem_cols,
+                     (int)P.w_bytes, (int)P.xch_bytes, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 40; ++i) out[i] = v[i];
+  for (int i = 0; i < 27; ++i) out[40 + i] = i < n_taps ? P.tap_off[i] : 0;
+  return ENERF_OK;
+}
+
 extern "C" int enerf_tc_conv2_fuse_lateral(int on) {
   enerf::g_fuse_lateral = on;
   return ENERF_OK;

@@ -275,6 +275,11 @@ ENERF_API int enerf_render_rays_tc_select(int impl);
  * 1 = csrc/tc_conv.cu's kernel only, 2 = same as 0; nmma = MMA-issuing warps per CTA (1|2); ctas_per_sm (1|2);
  * tz, ty, kbc (8|16|32), slots: forced tile / K-block width / ring depth, 0 = built-in choice. */
 ENERF_API int enerf_tc_conv2_tune(int impl, int nmma, int ctas_per_sm, int tz, int ty, int kbc, int slots);
+/* The launch geometry csrc/tc_conv2.cu would use for a layer ((D,H,W) = its row grid) on a device with n_sm SMs, computed
+ * without touching a GPU, so the CPU test suite can emulate the kernel from it (tests/test_host_cpu.py).  out: 67 ints,
+ * layout documented at the definition.  Returns ENERF_EUNSUPPORTED when the layer stays on csrc/tc_conv.cu. */
+ENERF_API int enerf_tc_conv2_plan(int kind, int KD, int KH, int stride, int cin, int cout, int mode, int D, int H, int W, int fold, int lateral,
+                                  int n_sm, int* out);
 /* Diagnostic: 1 (default) = enerf_feature_net computes lat0 (1x1 lateral + bilinear x2 + add, feature_net.py:31-35) inside
  * smooth0's producer warps on the tensor-core path; 0 = separate lateral kernel + plain smooth0 (bit-identical features). */
 ENERF_API int enerf_tc_conv2_fuse_lateral(int on);
