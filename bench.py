@@ -438,7 +438,9 @@ def main():
     # ---- N > 1, c2: the north-star intra-frame layout in the same run (row bands + halo, one all-gather) ----
     intra = None
     if world > 1 and kind == "plain" and not args.no_extras:
-        intra = edist.measure_intra_frame(net, gbatch, rank, world, dev, steps=min(args.steps, 20), warmup=args.warmup,
+        _, _, batch0, _ = build_problem(args.workload, seed=2)       # every rank renders ITS BAND OF THE SAME frame (rank 0's)
+        gb0 = to_dev({k: v for k, v in batch0.items() if not k.startswith("rays_")}, dev)
+        intra = edist.measure_intra_frame(net, gb0, rank, world, dev, steps=min(args.steps, 20), warmup=args.warmup,
                                           flush_buf=flush_buf, single_frame_ms=lat_ms)
 
     if rank != 0:

@@ -166,3 +166,28 @@ def test_folded_tc_conv_packing_is_a_shifted_sum_of_partial_convolutions():
     out = sum(P[:, :, kx:kx + W, kx] for kx in range(3))               # out[x] = sum_kx P[x+kx][kx]
     ref = F.conv3d(x, packing.tf32_round(w), None, 1, 1)[0].permute(1, 2, 3, 0)
     assert (out - ref).abs().max().item() < 1e-4
+
+
+def test_band_rows_cover_the_receptive_field():
+    """Network._band_rows: the volume rows a rank regularises = its rows + the regulariser's halo, clamped to the grid and
+    aligned to the U-Net's stride; misaligned bands are refused (the bit-identity argument needs aligned crops)."""
+    import pytest
+    from enerf_b200 import config as bcfg
+    from enerf_b200.config import snapshot
+    from enerf_b200.network import Network
+    cfg = bcfg.set_cfg(bcfg.make_cfg(volume_planes=[48, 8], render_if=[False, True]))
+    net = Network()
+    lv = snapshot(cfg)[1]
+    H, h = 512, 256
+    for world in (2, 4, 8):
+        rows = H // world
+        for rank in range(world):
+            net.ray_rows = (rank * rows, (rank + 1) * rows)
+            y0, y1 = net._band_rows(lv, H, h, True)
+            v0, v1 = rank * rows // 2, (rank + 1) * rows // 2
+            assert y0 == max(0, v0 - 32) and y1 == min(h, v1 + 32) and y0 % 8 == 0 and y1 % 8 == 0
+            assert (v0 - y0 >= 31 or y0 == 0) and (y1 - v1 >= 31 or y1 == h)      # RF 30 rows + 1 for the bilinear / trilinear taps
+    net.ray_rows = (0, 40)      # 20 volume rows: not a multiple of the 3-level U-Net's stride 8
+    with pytest.raises(ValueError):
+        net._band_rows(lv, H, h, True)
+    net.ray_rows = None

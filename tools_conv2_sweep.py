@@ -72,23 +72,35 @@ def main(quick):
         out = torch.empty((Do, Ho, Wo) if mode == 3 else (Do, Ho, Wo, 8 if mode == 1 else cout)).cuda()
         out2 = torch.empty(Do, Ho, Wo).cuda() if mode == 1 else None
         ref = None
-        for vname, kw in variants:
+        layer_variants = list(variants)
+        if kind == 0 and KD == 1 and KH == 3 and cout in (8, 16):       # kx folding for 2-D layers (off in the shipped rule): A/B it on v2
+            layer_variants += [("v2.fold2d", dict(impl=0, _fold=True)), ("v2.fold2d.nmma2", dict(impl=0, nmma=2, _fold=True)), ("v1.fold2d", dict(impl=1, _fold=True))]
+        for vname, kw in layer_variants:
             is3d = KD == 3 or kind == 1
             if "t1x" in vname and is3d or (".t2x" in vname or ".t4x" in vname) and not is3d:
                 continue
+            kw = dict(kw)
+            fold2d = kw.pop("_fold", False)
             capi.tc_conv2_tune(**kw)
+            wp_v = wp
+            if fold2d:
+                wp_v = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=True).cuda()
+                capi.tc_conv_tune(0, 0, 1)
             try:
                 out.fill_(float("nan"))
-                fn = lambda: capi.tc_conv(kind, KD, KH, cout, mode, relu, x, wp, bias, skip, out, out2, out_cstride=(8 if mode == 1 else cout))  # noqa: E731
+                fn = lambda: capi.tc_conv(kind, KD, KH, cout, mode, relu, x, wp_v, bias, skip, out, out2, out_cstride=(8 if mode == 1 else cout))  # noqa: E731
                 us = time_launch(fn)
                 if ref is None:
                     ref = out.clone()
                     same = True
                 else:
-                    same = bool(torch.equal(out, ref))
+                    same = bool(torch.equal(out, ref)) if not fold2d else float((out - ref).abs().max())
             except Exception as e:  # noqa: BLE001
                 us, same = None, str(e)[:120]
                 torch.cuda.synchronize()
+            finally:
+                if fold2d:
+                    capi.tc_conv_tune(0, 0, -1)
             results.append({"layer": name, "variant": vname, "us": us, "equal_to_v1": same})
             if us and vname in ("v1", "v2", "v2.nmma2", "v2.2cta", "v2.2cta.nmma2"):
                 totals[vname] = totals.get(vname, 0.0) + us
