@@ -40,8 +40,9 @@ struct TcConvLayer {
 // FeatureNet's lateral fused into the following smooth convolution (tc_conv2.cu, PROD = 1): the convolution's 32-channel
 // input  bilinear_x2(up_in) + (lat_b + lat_w^T lat_in)  is computed tile by tile in shared memory and never written to HBM.
 struct TcLateral {
-  const float* lat_in;   // (S,H,W,8) channels-last
-  const float* lat_w;    // [8][32]
+  int lat_cin;           // 8 (lat0: conv0) | 16 (lat1: conv1)
+  const float* lat_in;   // (S,H,W,lat_cin) channels-last
+  const float* lat_w;    // [lat_cin][32]
   const float* lat_b;    // [32]
   const float* up_in;    // (S,H/2,W/2,32)
 };

@@ -50,8 +50,8 @@ struct TcConv2Params {
   float* out2;
   // PROD = 1 (FeatureNet smooth0 with the lateral fused in): the 32-channel input tile is COMPUTED by four producer
   // warps instead of loaded: in[n,y,x,:] = bilinear_x2(up_in)[n,y,x,:] + (lat_b + lat_w^T lat_in[n,y,x,:]), zero outside the image
-  const float* lat_in;   // (S,H,W,8) channels-last
-  const float* lat_w;    // [8][32]
+  const float* lat_in;   // (S,H,W,LATC) channels-last, LATC = 8 (PROD 1) | 16 (PROD 2)
+  const float* lat_w;    // [LATC][32]
   const float* lat_b;    // [32]
   const float* up_in;    // (S,H/2,W/2,32)
 };
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_ker
 
   if (t == 0) {
     for (int i = 0; i < 8; ++i) {
-      tc::mbar_init(&full_bar[i], PROD ? 128 : 1);   // the producer's expect_tx arrival (+ the box's bytes) | every computing producer thread
+      tc::mbar_init(&full_bar[i], PROD != 0 ? 128 : 1);   // the producer's expect_tx arrival (+ the box's bytes) | every computing producer thread
       tc::mbar_init(&empty_bar[i], NMMA);    // one tcgen05.commit per MMA warp
     }
     for (int i = 0; i < 2; ++i) {
@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_ker
   const uint32_t tmem = tmem_base_s;
   const uint32_t row_bytes = (uint32_t)P.kbc * 4u;
 
-  if (PROD == 1 && warp < NP) {
+  if (PROD != 0 && warp < NP) {
+    constexpr int LATC = (PROD == 2) ? 16 : 8;       // channels of the lateral's input (conv0: 8, conv1: 16)
     // ============================== computing producer (lateral 1x1 conv + bilinear x2 + add) ==============================
     // thread = (halo pixel, g): channels [4g, 4g+4) and [16+4g, 16+4g+4) -- 16-byte chunks g and 4+g of the pixel's 128-byte
     // row, written at their SWIZZLE_128B position (chunk ^ (row & 7)); same arithmetic and order as lateral_upadd_kernel
@@ -106,11 +107,13 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_ker
       tc::tma_load_1d(w_s, P.wpack, P.w_bytes, &w_bar);
     }
     const int g = t & 3;
-    float4 wreg[16];
+    float4 wreg[LATC == 8 ? 16 : 1];                  // LATC = 8: this thread's 8 x 8 weight slice lives in registers
+    if constexpr (LATC == 8) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      wreg[2 * k] = ldg4(P.lat_w + k * 32 + g * 4);
-      wreg[2 * k + 1] = ldg4(P.lat_w + k * 32 + 16 + g * 4);
+      for (int k = 0; k < 8; ++k) {
+        wreg[2 * k] = ldg4(P.lat_w + k * 32 + g * 4);
+        wreg[2 * k + 1] = ldg4(P.lat_w + k * 32 + 16 + g * 4);
+      }
     }
     const float4 bias0 = ldg4(P.lat_b + g * 4), bias1 = ldg4(P.lat_b + 16 + g * 4);
     const int H = P.Hn, W = P.Wn, hi = H / 2, wi = W / 2;
@@ -133,12 +136,17 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_ker
           const size_t pix = ((size_t)n * H + y) * W + x;
           float acc[8] = {bias0.x, bias0.y, bias0.z, bias0.w, bias1.x, bias1.y, bias1.z, bias1.w};
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const float4 v = ldg4(P.lat_in + pix * 8 + 4 * q);
+          for (int q = 0; q < LATC / 4; ++q) {
+            const float4 v = ldg4(P.lat_in + pix * LATC + 4 * q);
             const float xv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 w0 = wreg[2 * (4 * q + j)], w1 = wreg[2 * (4 * q + j) + 1];
+              float4 w0, w1;
+              if constexpr (LATC == 8) {
+                w0 = wreg[2 * (4 * q + j)], w1 = wreg[2 * (4 * q + j) + 1];
+              } else {       // 2 KB of weights, warp-uniform addresses per g: L1-resident
+                w0 = ldg4(P.lat_w + (4 * q + j) * 32 + g * 4), w1 = ldg4(P.lat_w + (4 * q + j) * 32 + 16 + g * 4);
+              }
               acc[0] = fmaf(xv[j], w0.x, acc[0]), acc[1] = fmaf(xv[j], w0.y, acc[1]), acc[2] = fmaf(xv[j], w0.z, acc[2]), acc[3] = fmaf(xv[j], w0.w, acc[3]);
               acc[4] = fmaf(xv[j], w1.x, acc[4]), acc[5] = fmaf(xv[j], w1.y, acc[5]), acc[6] = fmaf(xv[j], w1.z, acc[6]), acc[7] = fmaf(xv[j], w1.w, acc[7]);
             }
@@ -405,9 +413,10 @@ bool tc_conv2_fuse_lateral() { return g_impl != 1 && g_fuse_lateral != 0; }
 // Host geometry of a launch, free of CUDA calls (so tests/test_host_cpu.py can emulate the kernel from it on a CPU-only
 // box through enerf_tc_conv2_plan): tile, halo, taps, K-block, ring, accumulators.  Returns 0, or 1 = not eligible.
 static int tc_conv2_plan(const TcConvLayer& L, int Dn, int Hn, int Wn, bool fold_default, bool lat, bool has_bias, bool has_skip, int n_sm,
-                         TcConv2Params& P, int& n_taps_out, bool& fold_out) {
+                         TcConv2Params& P, int& n_taps_out, bool& fold_out, int lat_cin = 8) {
   const int stride = (L.kind == 0) ? L.stride : 1;
-  if (lat && !(L.kind == 0 && L.KD == 1 && L.KH == 3 && L.cin == 32 && stride == 1 && L.mode == TC_PLAIN && !fold_default && Hn % 2 == 0 && Wn % 2 == 0))
+  if (lat && (lat_cin != 8 || fold_default)) return 1;     // instantiated: lat0 (8 channels) in front of an unfolded 3x3
+  if (lat && !(L.kind == 0 && L.KD == 1 && L.KH == 3 && L.cin == 32 && stride == 1 && L.mode == TC_PLAIN && Hn % 2 == 0 && Wn % 2 == 0))
     return 1;
   if (L.cin % 8 != 0 || L.cin > 64 || (stride != 1 && stride != 2)) return 1;
   if (stride == 2 && (fold_default || !stride2_enabled())) return 1;
@@ -549,7 +558,7 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
   int n_taps = 0;
   bool fold = false;
   const int n_sm = device_sm_count();
-  if (tc_conv2_plan(L, Dn, Hn, Wn, fold_default, lat != nullptr, bias != nullptr, skip != nullptr, n_sm, P, n_taps, fold) != 0) return 1;
+  if (tc_conv2_plan(L, Dn, Hn, Wn, fold_default, lat != nullptr, bias != nullptr, skip != nullptr, n_sm, P, n_taps, fold, lat ? lat->lat_cin : 8) != 0) return 1;
   P.out_cstride = out_cstride, P.out_coff = out_coff;
   P.wpack = wpack, P.bias = bias, P.skip = skip, P.out = out, P.out2 = out2;
   P.lat_in = lat ? lat->lat_in : nullptr, P.lat_w = lat ? lat->lat_w : nullptr, P.lat_b = lat ? lat->lat_b : nullptr, P.up_in = lat ? lat->up_in : nullptr;
@@ -587,24 +596,22 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
     else TC2_LAUNCH(NT, MD, FD, 1);          \
   } while (0)
   if (lat != nullptr) {
-    const size_t smem_l = smem;
-    static PerDeviceSize lat_set_pd[2];
-    size_t& lat_set = lat_set_pd[g_nmma >= 2 ? 1 : 0].cur();
-    if (g_nmma >= 2) {
-      if (smem_l > lat_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv2_kernel<9, TC_PLAIN, 0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
-        ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv2(lateral): cudaFuncSetAttribute(%zu): %s", smem_l, cudaGetErrorString(e));
-        lat_set = smem_l;
-      }
-      tc_conv2_kernel<9, TC_PLAIN, 0, 2, 1><<<grid, 32 * (4 + 2 + 4), smem_l, stream>>>(map, P);
-    } else {
-      if (smem_l > lat_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv2_kernel<9, TC_PLAIN, 0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
-        ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv2(lateral): cudaFuncSetAttribute(%zu): %s", smem_l, cudaGetErrorString(e));
-        lat_set = smem_l;
-      }
-      tc_conv2_kernel<9, TC_PLAIN, 0, 1, 1><<<grid, 32 * (4 + 1 + 4), smem_l, stream>>>(map, P);
-    }
+#define TC2_LAT(NM, PR)                                                                                                                          \
+  do {                                                                                                                                           \
+    static PerDeviceSize lat_set_pd;                                                                                                             \
+    size_t& lat_set = lat_set_pd.cur();                                                                                                          \
+    if (smem > lat_set) {                                                                                                                        \
+      cudaError_t e = cudaFuncSetAttribute(tc_conv2_kernel<9, TC_PLAIN, 0, NM, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+      ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv2(lateral): cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));             \
+      lat_set = smem;                                                                                                                            \
+    }                                                                                                                                            \
+    tc_conv2_kernel<9, TC_PLAIN, 0, NM, PR><<<grid, 32 * (4 + NM + 4), smem, stream>>>(map, P);                                                  \
+  } while (0)
+    // (lat1 -> smooth1 is NOT fused: its output feat1_pre is also lat0's up-sampling source, so it must exist in HBM anyway;
+    //  the producer is written for lat_cin 8 | 16, only 8 is instantiated)
+    if (g_nmma >= 2) TC2_LAT(2, 1);
+    else TC2_LAT(1, 1);
+#undef TC2_LAT
     ENERF_CHECK_LAUNCH("tc_conv2(lateral)");
     return ENERF_OK;
   }
