@@ -125,7 +125,7 @@ def proj_mats(batch, src_scale, tar_scale):
     k_t = batch["tar_ixt"].clone()
     k_t[:, :2] *= tar_scale
     p_t = k_t @ batch["tar_ext"][:, :3]
-    last = torch.zeros(B, 1, 4, dtype=p_t.dtype)
+    last = torch.zeros(B, 1, 4, dtype=p_t.dtype, device=p_t.device)
     last[:, :, 3] = 1
     p_t_inv = torch.inverse(torch.cat([p_t, last], dim=1))
     return p_s @ p_t_inv[:, None]
@@ -136,8 +136,9 @@ def homo_warp(src_feat, proj, depth_values):
     -> (B,C,D,h,w).  Samples the source at pixel coord xy (align_corners=True, zeros padding)."""
     B, D, h, w = depth_values.shape
     C, Hs, Ws = src_feat.shape[1:]
-    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
-    pix = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(h * w)], 0)[None].expand(B, -1, -1)  # (B,3,hw)
+    dev = src_feat.device     # (device-agnostic: bench.py also runs this port on cuda:0 as the library-kernel baseline)
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=dev), torch.arange(w, dtype=torch.float32, device=dev), indexing="ij")
+    pix = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(h * w, device=dev)], 0)[None].expand(B, -1, -1)  # (B,3,hw)
     pix = pix.repeat(1, 1, D)
     q = proj[:, :, :3] @ pix + proj[:, :, 3:] / depth_values.reshape(B, 1, D * h * w)
     xy = q[:, :2] / torch.clamp_min(q[:, 2:], 1e-6)
@@ -154,7 +155,7 @@ def depth_values_for_level(batch, cfg, level, D, depth, std, near_far):
     B = batch["src_inps"].shape[0]
     H, W = batch["src_inps"].shape[-2:]
     h, w = int(H * c.volume_scale[level]), int(W * c.volume_scale[level])
-    lin = torch.linspace(0.0, 1.0, steps=D, dtype=torch.float32)
+    lin = torch.linspace(0.0, 1.0, steps=D, dtype=torch.float32, device=batch["src_inps"].device)
     if depth is None:
         nf = batch["near_far"]
         if c.depth_inv[level]:
@@ -242,7 +243,7 @@ def sample_along_depth(rays, n_samples, depth_inv):
     if n_samples == 1:
         z = rn + (rf - rn) * 0.5
     else:
-        z = rn + (rf - rn) * torch.linspace(0.0, 1.0, n_samples)[None, None]
+        z = rn + (rf - rn) * torch.linspace(0.0, 1.0, n_samples, device=rays.device)[None, None]
     if depth_inv:
         xyz = o[..., None, :] + d[..., None, :] * (1 / torch.clamp_min(z[..., None], 1e-6))
         dn = (vn - z) / torch.clamp_min(vn - vf, 1e-6)
@@ -375,7 +376,7 @@ def forward(sd, cfg, batch, intermediates=False, human=False):
         if stash:
             mid.update({f"{k}_{i}": v for k, v in stash.items()})
         if masked:
-            rgb = torch.zeros(1, mask.shape[1], 3)
+            rgb = torch.zeros(1, mask.shape[1], 3, device=out["rgb"].device)
             if mask.sum() > 1:
                 rgb[mask] = out["rgb"][0]
             out["rgb"] = rgb

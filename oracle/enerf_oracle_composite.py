@@ -52,9 +52,10 @@ def homo_warp_crop(src_feat, proj, depth_values, xywh):
     x, y, w, h = xywh
     B, D, Ht, Wt = depth_values.shape
     C, Hs, Ws = src_feat.shape[1:]
-    ys, xs = torch.meshgrid(torch.arange(Ht, dtype=torch.float32), torch.arange(Wt, dtype=torch.float32), indexing="ij")
+    dev = src_feat.device
+    ys, xs = torch.meshgrid(torch.arange(Ht, dtype=torch.float32, device=dev), torch.arange(Wt, dtype=torch.float32, device=dev), indexing="ij")
     ys, xs = ys[y:y + h, x:x + w], xs[y:y + h, x:x + w]
-    pix = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(h * w)], 0)[None].expand(B, -1, -1).repeat(1, 1, D)
+    pix = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(h * w, device=dev)], 0)[None].expand(B, -1, -1).repeat(1, 1, D)
     q = proj[:, :, :3] @ pix + proj[:, :, 3:] / depth_values[:, :, y:y + h, x:x + w].reshape(B, 1, D * h * w)
     xy = q[:, :2] / torch.clamp_min(q[:, 2:], 1e-6)
     gx = xy[:, 0] / ((Ws - 1) / 2) - 1
@@ -122,8 +123,9 @@ def parse_layer(layer, box, Hr, Wr, render_scale):
     """parse_layer, utils.py:875-887: the layer's samples placed into a zero full-frame canvas."""
     B, _, ns, _ = layer["net_output"].shape
     x, y, w, h = _int_box(box, render_scale)
-    raw = torch.zeros(B, Hr, Wr, ns, 4)
-    z = torch.zeros(B, Hr, Wr, ns)
+    dev = layer["net_output"].device
+    raw = torch.zeros(B, Hr, Wr, ns, 4, device=dev)
+    z = torch.zeros(B, Hr, Wr, ns, device=dev)
     raw[:, y:y + h, x:x + w] = layer["net_output"].reshape(B, h, w, ns, 4)
     z[:, y:y + h, x:x + w] = layer["z_vals"].reshape(B, h, w, ns)
     return raw.reshape(B, -1, ns, 4), z.reshape(B, -1, ns)

@@ -7,10 +7,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -
   python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extras --graph 0 --inflight 1 > gpurun_out/r2_launches_bench.json 2> gpurun_out/r2_launches_bench.err
 echo "launch list rc=$?"
 timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-  -k regex:"render_rays_ws|render_rays_tc|tc_conv2_kernel|tc_conv_kernel|cost_volume_kernel|lateral_upadd" -s $SKIP -c 40 -o gpurun_out/r2_prof \
+  -k regex:"render_rays_ws|render_rays_tc|tc_conv2_kernel|tc_conv_kernel|cost_volume_kernel|lateral_upadd" -s $SKIP -c 36 -o gpurun_out/r2_prof \
   python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extras --graph 0 --inflight 1 > gpurun_out/r2_prof_bench.json 2> gpurun_out/r2_prof_bench.err
 echo "full capture rc=$?"
-ENERF_B200_OVERLAP=0 timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_sanitizer_memcheck.log 2>&1
+ENERF_B200_OVERLAP=0 timeout 500 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_sanitizer_memcheck.log 2>&1
 echo "memcheck rc=$?"; tail -4 gpurun_out/r2_sanitizer_memcheck.log
-ENERF_B200_OVERLAP=0 timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_sanitizer_racecheck.log 2>&1
+ENERF_B200_OVERLAP=0 timeout 500 compute-sanitizer --tool racecheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_sanitizer_racecheck.log 2>&1
 echo "racecheck rc=$?"; tail -4 gpurun_out/r2_sanitizer_racecheck.log
