@@ -6,7 +6,7 @@
 namespace enerf {
 
 // render_rays_ws.cu: the warp-specialised kernel (2-3 views); returns 1 when it does not take the configuration
-int render_rays_ws_try_launch(const RayParams& r, const float* wblob, int n_tiles, cudaStream_t stream);
+int render_rays_ws_try_launch(const RayParams& r, const float* wblob, int n_tiles, cudaStream_t stream, unsigned long long* dbg);
 
 extern template int launch_rays_tc<2>(const RayTcParams&, cudaStream_t);
 extern template int launch_rays_tc<3>(const RayTcParams&, cudaStream_t);
@@ -62,7 +62,7 @@ extern "C" int enerf_render_rays_tc(const EnerfCam* cam, int level, const float*
   P.wblob = wblob, P.dbg = g_ray_dbg_host;
   P.n_tiles = (int)(((long long)n_rays * num_samples + 127) / 128);
   {
-    const int rc = render_rays_ws_try_launch(P.r, wblob, P.n_tiles, stream);
+    const int rc = render_rays_ws_try_launch(P.r, wblob, P.n_tiles, stream, g_ray_dbg_host);
     if (rc != 1) return rc;
   }
   return dispatch_rays_tc(P, n_views, stream);
@@ -101,7 +101,7 @@ extern "C" int enerf_render_rays_raw_tc(const EnerfCam* cam, int level, const fl
   P.wblob = wblob, P.dbg = g_ray_dbg_host;
   P.n_tiles = (int)(((long long)p.n_rays * num_samples + 127) / 128);
   {
-    const int rc = render_rays_ws_try_launch(P.r, wblob, P.n_tiles, stream);
+    const int rc = render_rays_ws_try_launch(P.r, wblob, P.n_tiles, stream, g_ray_dbg_host);
     if (rc != 1) return rc;
   }
   return dispatch_rays_tc(P, n_views, stream);

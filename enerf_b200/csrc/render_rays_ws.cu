@@ -101,7 +101,19 @@ struct Params {
   RayParams r;
   const float* wblob;
   int n_tiles;
+  unsigned long long* dbg;    // optional %globaltimer stamps of CTA 0 (enerf_render_rays_debug): [role 0..2][tile 0..7][16]
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// role 0 = consumer (thread 0), 1 / 2 = gather group 0 / 1 (their row 0); tile = the role's own tile counter
+#define WS_STAMP(role_, tile_, i_)                                                                   \
+  do {                                                                                               \
+    if (dbg && (tile_) < 8) dbg[((role_) * 8 + (tile_)) * 16 + (i_)] = gtime();                      \
+  } while (0)
 
 template <int S>
 __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) {
@@ -155,7 +167,9 @@ __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) 
     float* gb = smem + SM::o_g + grp * SM::g_floats;
     float* scal = gb + SM::G_CHUNKS * CHUNK;
     int j = 0;                                       // this group's tile counter
+    unsigned long long* dbg = (P.dbg && blockIdx.x == 0 && row == 0) ? P.dbg : nullptr;
     for (int k = grp, tile = blockIdx.x + grp * gridDim.x; tile < n_tiles; k += 2, tile += 2 * gridDim.x, ++j) {
+      WS_STAMP(1 + grp, j, 0);
       const long long pt = (long long)tile * 128 + row;
       const bool valid = pt < (long long)n_rays * Ns;
       int ray = valid ? (int)(pt / Ns) : n_rays - 1;
@@ -272,7 +286,9 @@ __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) 
       }
 
       // ---- the buffer is free once the consumer's first MMA batch of this group's previous tile has read it ----
+      WS_STAMP(1 + grp, j, 1);     // gathers done (in registers)
       tc::mbar_wait(&free_bar[grp], (uint32_t)((j & 1) ^ 1));
+      WS_STAMP(1 + grp, j, 2);     // buffer free
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         const int cf = SM::c_fd + 4 * s;
@@ -324,6 +340,7 @@ __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) 
       scal[(3 * S) * 128 + row] = z;
       tc::fence_proxy_async();             // my rows -> visible to the tensor core (async proxy)
       mbar_arrive(&full_bar[grp]);
+      WS_STAMP(1 + grp, j, 3);     // rows stored
     }
   } else {
     // ======================================= consumer =======================================
@@ -347,8 +364,10 @@ __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) 
       tc::tc_fence_after_sync();
     };
     int k = 0;
+    unsigned long long* dbg = (P.dbg && blockIdx.x == 0 && t == 0) ? P.dbg : nullptr;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
       const int b = k & 1;
+      WS_STAMP(0, k, 0);
       const uint32_t g_addr = tc::smem_u32(smem + SM::o_g + b * SM::g_floats);
       const float* scal = smem + SM::o_g + b * SM::g_floats + SM::G_CHUNKS * CHUNK;
       const long long pt = (long long)tile * 128 + t;
@@ -358,6 +377,7 @@ __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) 
       const int ks = (int)(pt % Ns);
 
       tc::mbar_wait(&full_bar[b], (uint32_t)((k >> 1) & 1));
+      WS_STAMP(0, k, 1);           // gathered tile available
       float rgb_s[S][3];
 #pragma unroll
       for (int s = 0; s < S; ++s)
@@ -393,7 +413,9 @@ __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) 
         tc::mma_commit_elect(&mma_bar);
         __syncwarp();
       }
+      WS_STAMP(0, k, 2);           // batch 1 issued
       wait_mma();
+      WS_STAMP(0, k, 3);           // batch 1 complete
       // ---- E1: global_fc = shared + view, ReLU, agg_w_fc logits, softmax over views, weighted pooling (nerf.py:85-88) ----
       {
         float sh[32], im[32];
@@ -425,6 +447,7 @@ __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) 
 #pragma unroll
         for (int q = 0; q < 8; ++q) store_chunk(p_s, SM::p_x + q, t, im[4 * q] * inv, im[4 * q + 1] * inv, im[4 * q + 2] * inv, im[4 * q + 3] * inv);
       }
+      WS_STAMP(0, k, 4);           // E1 done
       publish();
       // ===== G2: fc 32 -> 16 =====
       if (warp == 0) {
@@ -435,6 +458,7 @@ __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) 
         __syncwarp();
       }
       wait_mma();
+      WS_STAMP(0, k, 5);           // G2 complete
       {
         float o[16];
         tc::tmem_ld16(tmem_row + SM::t_g1s, o);
@@ -444,6 +468,7 @@ __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) 
 #pragma unroll
         for (int q = 0; q < 4; ++q) store_chunk(p_s, SM::p_img + q, t, o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
       }
+      WS_STAMP(0, k, 6);           // E2 done
       publish();
       // ===== G3: the img columns of lr0 (rows 8..23) and of color.0's shared part (rows 72..87) =====
       if (warp == 0) {
@@ -457,6 +482,7 @@ __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) 
         __syncwarp();
       }
       wait_mma();
+      WS_STAMP(0, k, 7);           // G3 complete
       float sigma;
       {
         float sg = sw[W::v_bs];
@@ -475,6 +501,7 @@ __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) 
         }
         sigma = (sg > 20.f) ? sg : log1pf(expf(sg));
       }
+      WS_STAMP(0, k, 8);           // E3 done
       publish();
       // ===== G5: the x columns of color.0's shared part (rows 0..63) =====
       if (warp == 0) {
@@ -485,6 +512,7 @@ __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) 
         __syncwarp();
       }
       wait_mma();
+      WS_STAMP(0, k, 9);           // G5 complete
       // ---- E5: color.0 = ReLU(shared + view), color.2 logits, softmax over views, blend of the SOURCE colours (nerf.py:38-43) ----
       float cr = 0.f, cg = 0.f, cb = 0.f;
       {
@@ -524,6 +552,7 @@ __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) 
         }
       }
 
+      WS_STAMP(0, k, 10);          // E5 done
       // ================= raw2outputs: prefix product / sums over the Ns lanes of a ray =================
       if (p.out_raw) {   // layered mode: samples are merged across layers by enerf_composite_layers
         if (valid) {
@@ -598,6 +627,7 @@ __global__ void __launch_bounds__(384, 1) render_rays_ws_kernel(const Params P) 
           }
         }
       }
+      WS_STAMP(0, k, 11);          // composited + stored
       // the next tile's first batch overwrites the accumulators: its issue is ordered behind the consumer barrier at the top
     }
   }
@@ -631,10 +661,10 @@ static int g_ray_impl = 0;     // 0 auto (warp-specialised kernel for 2-3 views)
 
 // Called by enerf_render_rays_tc / enerf_render_rays_raw_tc (render_rays_tc.cu).  Returns 1 when this kernel does not
 // take the configuration (the caller then launches render_rays_tc_kernel).
-int render_rays_ws_try_launch(const RayParams& r, const float* wblob, int n_tiles, cudaStream_t stream) {
+int render_rays_ws_try_launch(const RayParams& r, const float* wblob, int n_tiles, cudaStream_t stream, unsigned long long* dbg) {
   if (g_ray_impl == 1 || r.S < 2 || r.S > 3) return 1;
   ws::Params P;
-  P.r = r, P.wblob = wblob, P.n_tiles = n_tiles;
+  P.r = r, P.wblob = wblob, P.n_tiles = n_tiles, P.dbg = dbg;
   return r.S == 2 ? ws::launch<2>(P, stream) : ws::launch<3>(P, stream);
 }
 
