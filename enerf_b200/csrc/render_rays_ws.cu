@@ -657,12 +657,14 @@ static int launch(const Params& P, cudaStream_t stream) {
 
 }  // namespace ws
 
-static int g_ray_impl = 0;     // 0 auto (warp-specialised kernel for 2-3 views), 1 render_rays_tc.cu only
+// 0 auto, 1 the single-role kernel (render_rays_tc.cuh), 2 this kernel for 2-3 views.  auto = 1: measured on the B200 at the
+// headline workload the two kernels are on par (0.316 vs 0.305 ms, profiles/r2_frame_ab.md), so the simpler one stays the default.
+static int g_ray_impl = 0;
 
 // Called by enerf_render_rays_tc / enerf_render_rays_raw_tc (render_rays_tc.cu).  Returns 1 when this kernel does not
 // take the configuration (the caller then launches render_rays_tc_kernel).
 int render_rays_ws_try_launch(const RayParams& r, const float* wblob, int n_tiles, cudaStream_t stream, unsigned long long* dbg) {
-  if (g_ray_impl == 1 || r.S < 2 || r.S > 3) return 1;
+  if (g_ray_impl != 2 || r.S < 2 || r.S > 3) return 1;
   ws::Params P;
   P.r = r, P.wblob = wblob, P.n_tiles = n_tiles, P.dbg = dbg;
   return r.S == 2 ? ws::launch<2>(P, stream) : ws::launch<3>(P, stream);
@@ -670,7 +672,7 @@ int render_rays_ws_try_launch(const RayParams& r, const float* wblob, int n_tile
 
 }  // namespace enerf
 
-// Diagnostic: impl 0 = auto, 1 = force render_rays_tc.cu's kernel (the single-role round-1 kernel) for every configuration.
+// Diagnostic: impl 0 = auto (the single-role kernel), 1 = the single-role kernel, 2 = the warp-specialised kernel for 2-3 views.
 extern "C" int enerf_render_rays_tc_select(int impl) {
   enerf::g_ray_impl = impl;
   return ENERF_OK;

@@ -257,140 +257,192 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_ker
       tc::tc_fence_after_sync();
       const uint32_t trow = trow0 + (uint32_t)(acc * P.n_mt * P.N);
       float* xch = xch0 + (size_t)(ti & 1) * (P.xch_bytes / 8);      // [n_mt*4 + 1][2 rows][N], double buffered
-      if constexpr (FOLD) {
-        // rows 0 and 1 of every 32-row group, for the two last lanes of the group before it
-        for (int m = 0; m < P.n_mt; ++m)
-          for (int c = 0; c < P.N; c += 8) {
-            float v[8];
-            tc::tmem_ld8(trow + (uint32_t)(m * P.N + c), v);
-            tc::tmem_ld_wait();
-            if (lane < 2) {
-              float4* d = reinterpret_cast<float4*>(xch + ((size_t)((m * 4 + g) * 2 + lane)) * P.N + c);
-              d[0] = make_float4(v[0], v[1], v[2], v[3]);
-              d[1] = make_float4(v[4], v[5], v[6], v[7]);
-            }
-          }
-        epi_bar_sync();
-      }
-      for (int m = 0; m < P.n_mt; ++m) {
+      // Measured (profiles/r2_conv2_sweep.md): a tcgen05.ld + wait::ld issued while the MMA warps keep the tensor pipe busy
+      // with the NEXT tile costs hundreds of cycles, so every M-tile is read with ONE load (as wide as its columns) and ONE wait.
+      auto position = [&](int m, size_t& pix, int& gz, int& gy, int& gx) -> bool {
         const int q = m * 128 + r;                              // linear halo position of this thread's row
         const int z = q / plane, rem = q - z * plane, y = rem / P.IX, x = rem - y * P.IX;
-        const int gz = z0 + z, gy = y0 + y, gx = x0 + x;
-        const bool valid = (z < P.TZ) && (y < P.TY) && (x < P.TX) && (gz < P.Dn) && (gy < P.Hn) && (gx < P.Wn);
-        const size_t pix = ((size_t)gz * P.Hn + gy) * P.Wn + gx;
-        const float* nxr = xch + (size_t)((m * 4 + g + 1) * 2) * P.N;   // rows 0,1 of the next 32-row group
-        auto shifted = [&](float b, float c, int colb, int colc, float& b1, float& c2) {
-          b1 = __shfl_down_sync(0xffffffffu, b, 1);
-          c2 = __shfl_down_sync(0xffffffffu, c, 2);
-          if (lane == 31) b1 = nxr[colb];
-          if (lane >= 30) c2 = nxr[(lane - 30) * P.N + colc];
-        };
-        if constexpr (FOLD && MODE == TC_PLAIN) {
-          const int C = P.cout;
-          for (int c0 = 0; c0 < C; c0 += 8) {
-            float a[8], b[8], c[8];
-            tc::tmem_ld8(trow + (uint32_t)(m * P.N + c0), a);
-            tc::tmem_ld8(trow + (uint32_t)(m * P.N + C + c0), b);
-            tc::tmem_ld8(trow + (uint32_t)(m * P.N + 2 * C + c0), c);
+        gz = z0 + z, gy = y0 + y, gx = x0 + x;
+        pix = ((size_t)gz * P.Hn + gy) * P.Wn + gx;
+        return (z < P.TZ) && (y < P.TY) && (x < P.TX) && (gz < P.Dn) && (gy < P.Hn) && (gx < P.Wn);
+      };
+      if constexpr (FOLD) {
+        // columns kx*C + co (C = cout | 9 | 1): out[q] = P[q][0:C] + P[q+1][C:2C] + P[q+2][2C:3C].  Rows q+1, q+2 sit in the next
+        // lanes (shuffles); the two last lanes of a 32-row group need rows 0, 1 of the next group: those go through `xch`.
+        // The M-tiles are pipelined by one: iteration m loads tile m and publishes its rows 0, 1; after the barrier the outputs
+        // of tile m-1 are formed from the registers of iteration m-1.
+        constexpr int NF = (MODE == TC_SINGLE) ? 16 : 32;        // columns held per row (3C padded: 24 / 27 / 3)
+        const int C = (MODE == TC_PLAIN) ? P.cout : (MODE == TC_HEAD) ? 9 : 1;
+        float vp[NF];
+        for (int m = 0; m <= P.n_mt; ++m) {
+          float vc[NF];
+          if (m < P.n_mt) {
+            if constexpr (NF == 32) tc::tmem_ld32(trow + (uint32_t)(m * P.N), vc);
+            else tc::tmem_ld16(trow + (uint32_t)(m * P.N), vc);
             tc::tmem_ld_wait();
+            if (m + 1 == P.n_mt) {       // the last TMEM read of this accumulator: hand it back to the MMA warps
+              tc::tc_fence_before_sync();
+              mbar_arrive1(&acce_bar[acc]);
+            }
+            if (lane < 2) {
+              float4* d = reinterpret_cast<float4*>(xch + ((size_t)((m * 4 + g) * 2 + lane)) * NF);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+              for (int c4 = 0; c4 < NF / 4; ++c4) d[c4] = make_float4(vc[4 * c4], vc[4 * c4 + 1], vc[4 * c4 + 2], vc[4 * c4 + 3]);
+            }
+          }
+          epi_bar_sync();
+          if (m >= 1) {
+            const int mo = m - 1;
+            size_t pix;
+            int gz, gy, gx;
+            const bool valid = position(mo, pix, gz, gy, gx);
+            const float* nxr = xch + (size_t)((mo * 4 + g + 1) * 2) * NF;   // rows 0, 1 of the next 32-row group
+            auto shifted = [&](int colb, int colc, float& b1, float& c2) {
+              b1 = __shfl_down_sync(0xffffffffu, vp[colb], 1);
+              c2 = __shfl_down_sync(0xffffffffu, vp[colc], 2);
+              if (lane == 31) b1 = nxr[colb];
+              if (lane >= 30) c2 = nxr[(lane - 30) * NF + colc];
+            };
+            if constexpr (MODE == TC_PLAIN) {      // C = 8 (the rule folds 8-channel layers only): columns [0,8) [8,16) [16,24)
+              float a[8];
+#pragma unroll
+              for (int jx = 0; jx < 8; ++jx) {
+                float b1, c2;
+                shifted(8 + jx, 16 + jx, b1, c2);
+                a[jx] = (vp[jx] + b1) + c2;
+              }
+              if (valid) {
+                const float4 b0v = ldg4(P.bias), b1v = ldg4(P.bias + 4);
+                float4 o0 = make_float4(a[0] + b0v.x, a[1] + b0v.y, a[2] + b0v.z, a[3] + b0v.w);
+                float4 o1 = make_float4(a[4] + b1v.x, a[5] + b1v.y, a[6] + b1v.z, a[7] + b1v.w);
+                if (P.relu) {
+                  o0 = make_float4(fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f));
+                  o1 = make_float4(fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f));
+                }
+                float4* o = reinterpret_cast<float4*>(P.out + pix * P.out_cstride + P.out_coff);
+                o[0] = o0;
+                o[1] = o1;
+              }
+            } else if constexpr (MODE == TC_HEAD) {   // columns kx*9 + co: 8 feat + 1 prob per kx
+              float rr[9];
+#pragma unroll
+              for (int jx = 0; jx < 9; ++jx) {
+                float b1, c2;
+                shifted(9 + jx, 18 + jx, b1, c2);
+                rr[jx] = (vp[jx] + b1) + c2;
+              }
+              if (valid) {
+                float4* o = reinterpret_cast<float4*>(P.out + pix * 8);
+                o[0] = make_float4(rr[0], rr[1], rr[2], rr[3]);
+                o[1] = make_float4(rr[4], rr[5], rr[6], rr[7]);
+                P.out2[pix] = rr[8];
+              }
+            } else {                                  // TC_SINGLE
               float b1, c2;
-              shifted(b[j], c[j], C + c0 + j, 2 * C + c0 + j, b1, c2);
-              a[j] = (a[j] + b1) + c2;
+              shifted(1, 2, b1, c2);
+              if (valid) P.out[pix] = (vp[0] + b1) + c2;
             }
-            if (valid) {
-              const float4 b0v = ldg4(P.bias + c0), b1v = ldg4(P.bias + c0 + 4);
-              float4 o0 = make_float4(a[0] + b0v.x, a[1] + b0v.y, a[2] + b0v.z, a[3] + b0v.w);
-              float4 o1 = make_float4(a[4] + b1v.x, a[5] + b1v.y, a[6] + b1v.z, a[7] + b1v.w);
-              if (P.relu) {
-                o0 = make_float4(fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f));
-                o1 = make_float4(fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f));
-              }
-              float4* o = reinterpret_cast<float4*>(P.out + pix * P.out_cstride + P.out_coff + c0);
-              o[0] = o0;
-              o[1] = o1;
-            }
+            (void)C;
           }
-        } else if constexpr (FOLD && MODE == TC_HEAD) {   // columns kx*9 + co: 8 feat + 1 prob per kx
-          float v[32];
-          tc::tmem_ld32(trow + (uint32_t)(m * P.N), v);
-          tc::tmem_ld_wait();
-          float rr[9];
 #pragma unroll
-          for (int j = 0; j < 9; ++j) {
-            float b1, c2;
-            shifted(v[9 + j], v[18 + j], 9 + j, 18 + j, b1, c2);
-            rr[j] = (v[j] + b1) + c2;
-          }
-          if (valid) {
-            float4* o = reinterpret_cast<float4*>(P.out + pix * 8);
-            o[0] = make_float4(rr[0], rr[1], rr[2], rr[3]);
-            o[1] = make_float4(rr[4], rr[5], rr[6], rr[7]);
-            P.out2[pix] = rr[8];
-          }
-        } else if constexpr (FOLD && MODE == TC_SINGLE) {
-          float v[8];
-          tc::tmem_ld8(trow + (uint32_t)(m * P.N), v);
-          tc::tmem_ld_wait();
-          float b1, c2;
-          shifted(v[1], v[2], 1, 2, b1, c2);
-          if (valid) P.out[pix] = (v[0] + b1) + c2;
-        } else if constexpr (MODE == TC_PLAIN) {
-          for (int c0 = 0; c0 < P.cout; c0 += 8) {       // cout is a multiple of 8
-            float v[8];
-            tc::tmem_ld8(trow + (uint32_t)(m * P.N + c0), v);
-            tc::tmem_ld_wait();
-            if (valid) {
-              const float4 b0v = ldg4(P.bias + c0), b1v = ldg4(P.bias + c0 + 4);
-              float4 o0 = make_float4(v[0] + b0v.x, v[1] + b0v.y, v[2] + b0v.z, v[3] + b0v.w);
-              float4 o1 = make_float4(v[4] + b1v.x, v[5] + b1v.y, v[6] + b1v.z, v[7] + b1v.w);
-              if (P.relu) {
-                o0 = make_float4(fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f));
-                o1 = make_float4(fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f));
-              }
-              float4* o = reinterpret_cast<float4*>(P.out + pix * P.out_cstride + P.out_coff + c0);
-              o[0] = o0;
-              o[1] = o1;
+          for (int c = 0; c < NF; ++c) vp[c] = vc[c];
+        }
+      } else {
+        for (int m = 0; m < P.n_mt; ++m) {
+          size_t pix;
+          int gz, gy, gx;
+          const bool valid = position(m, pix, gz, gy, gx);
+          const bool last = (m + 1 == P.n_mt);
+          auto release = [&]() {           // after the last TMEM read of this accumulator: hand it back to the MMA warps
+            if (last) {
+              tc::tc_fence_before_sync();
+              mbar_arrive1(&acce_bar[acc]);
             }
-          }
-        } else if constexpr (MODE == TC_HEAD) {          // feat_conv (8) + depth_conv (1), no bias
-          float v[16];
-          tc::tmem_ld16(trow + (uint32_t)(m * P.N), v);
-          tc::tmem_ld_wait();
-          if (valid) {
-            float4* o = reinterpret_cast<float4*>(P.out + pix * 8);
-            o[0] = make_float4(v[0], v[1], v[2], v[3]);
-            o[1] = make_float4(v[4], v[5], v[6], v[7]);
-            P.out2[pix] = v[8];
-          }
-        } else if constexpr (MODE == TC_SINGLE) {
-          float v[8];
-          tc::tmem_ld8(trow + (uint32_t)(m * P.N), v);
-          tc::tmem_ld_wait();
-          if (valid) P.out[pix] = v[0];
-        } else {  // TC_DECONV: columns = parity * cout + co ; out[2b+e] = skip + (acc + bias)
-          const int Ho = 2 * P.Hn, Wo = 2 * P.Wn;
-          for (int c = 0; c < P.N; c += 8) {
-            float v[8];
-            tc::tmem_ld8(trow + (uint32_t)(m * P.N + c), v);
+          };
+          auto store8 = [&](const float* v, float* dst, const float* bias8) {
+            const float4 b0v = ldg4(bias8), b1v = ldg4(bias8 + 4);
+            float4 o0 = make_float4(v[0] + b0v.x, v[1] + b0v.y, v[2] + b0v.z, v[3] + b0v.w);
+            float4 o1 = make_float4(v[4] + b1v.x, v[5] + b1v.y, v[6] + b1v.z, v[7] + b1v.w);
+            if (P.relu) {
+              o0 = make_float4(fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f));
+              o1 = make_float4(fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f));
+            }
+            reinterpret_cast<float4*>(dst)[0] = o0;
+            reinterpret_cast<float4*>(dst)[1] = o1;
+          };
+          if constexpr (MODE == TC_PLAIN) {
+            float* dst = P.out + pix * P.out_cstride + P.out_coff;
+            const uint32_t tcol = trow + (uint32_t)(m * P.N);
+            if (P.cout == 8) {
+              float v[8];
+              tc::tmem_ld8(tcol, v);
+              tc::tmem_ld_wait();
+              release();
+              if (valid) store8(v, dst, P.bias);
+            } else if (P.cout == 16) {
+              float v[16];
+              tc::tmem_ld16(tcol, v);
+              tc::tmem_ld_wait();
+              release();
+              if (valid) {
+                store8(v, dst, P.bias);
+                store8(v + 8, dst + 8, P.bias + 8);
+              }
+            } else {                       // 32 | 64 output channels: 32 columns per load, one wait for all of them
+              float v[64];
+              tc::tmem_ld32(tcol, v);
+              if (P.cout == 64) tc::tmem_ld32(tcol + 32, v + 32);
+              tc::tmem_ld_wait();
+              release();
+              if (valid) {
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 8)
+                  if (c0 < P.cout) store8(v + c0, dst + c0, P.bias + c0);
+              }
+            }
+          } else if constexpr (MODE == TC_HEAD) {          // feat_conv (8) + depth_conv (1), no bias
+            float v[16];
+            tc::tmem_ld16(trow + (uint32_t)(m * P.N), v);
             tc::tmem_ld_wait();
+            release();
             if (valid) {
-              const int e = c / P.cout, co = c - e * P.cout;
-              const size_t opix = ((size_t)(2 * gz + (e >> 2)) * Ho + (2 * gy + ((e >> 1) & 1))) * Wo + (2 * gx + (e & 1));
-              const float* sk = P.skip + opix * P.cout + co;
-              const float4 s0 = ldg4(sk), s1 = ldg4(sk + 4);
-              const float4 b0v = ldg4(P.bias + co), b1v = ldg4(P.bias + co + 4);
-              float4* o = reinterpret_cast<float4*>(P.out + opix * P.cout + co);
-              o[0] = make_float4(s0.x + (v[0] + b0v.x), s0.y + (v[1] + b0v.y), s0.z + (v[2] + b0v.z), s0.w + (v[3] + b0v.w));
-              o[1] = make_float4(s1.x + (v[4] + b1v.x), s1.y + (v[5] + b1v.y), s1.z + (v[6] + b1v.z), s1.w + (v[7] + b1v.w));
+              float4* o = reinterpret_cast<float4*>(P.out + pix * 8);
+              o[0] = make_float4(v[0], v[1], v[2], v[3]);
+              o[1] = make_float4(v[4], v[5], v[6], v[7]);
+              P.out2[pix] = v[8];
+            }
+          } else if constexpr (MODE == TC_SINGLE) {
+            float v[8];
+            tc::tmem_ld8(trow + (uint32_t)(m * P.N), v);
+            tc::tmem_ld_wait();
+            release();
+            if (valid) P.out[pix] = v[0];
+          } else {  // TC_DECONV: columns = parity * cout + co ; out[2b+e] = skip + (acc + bias); 64 columns per wait
+            const int Ho = 2 * P.Hn, Wo = 2 * P.Wn;
+            for (int cb = 0; cb < P.N; cb += 64) {
+              float v[64];
+              tc::tmem_ld32(trow + (uint32_t)(m * P.N + cb), v);
+              tc::tmem_ld32(trow + (uint32_t)(m * P.N + cb + 32), v + 32);       // N = 8 * cout is a multiple of 64
+              tc::tmem_ld_wait();
+              if (cb + 64 >= P.N) release();
+              if (valid) {
+#pragma unroll
+                for (int c8 = 0; c8 < 64; c8 += 8) {
+                  const int c = cb + c8;
+                  const int e = c / P.cout, co = c - e * P.cout;
+                  const size_t opix = ((size_t)(2 * gz + (e >> 2)) * Ho + (2 * gy + ((e >> 1) & 1))) * Wo + (2 * gx + (e & 1));
+                  const float* sk = P.skip + opix * P.cout + co;
+                  const float4 s0 = ldg4(sk), s1 = ldg4(sk + 4);
+                  const float4 b0v = ldg4(P.bias + co), b1v = ldg4(P.bias + co + 4);
+                  float4* o = reinterpret_cast<float4*>(P.out + opix * P.cout + co);
+                  o[0] = make_float4(s0.x + (v[c8 + 0] + b0v.x), s0.y + (v[c8 + 1] + b0v.y), s0.z + (v[c8 + 2] + b0v.z), s0.w + (v[c8 + 3] + b0v.w));
+                  o[1] = make_float4(s1.x + (v[c8 + 4] + b1v.x), s1.y + (v[c8 + 5] + b1v.y), s1.z + (v[c8 + 6] + b1v.z), s1.w + (v[c8 + 7] + b1v.w));
+                }
+              }
             }
           }
         }
       }
-      // every TMEM read of this accumulator is complete (tcgen05.wait::ld above): hand it back to the MMA warps
-      tc::tc_fence_before_sync();
-      mbar_arrive1(&acce_bar[acc]);
     }
   }
   tc::tc_fence_before_sync();
@@ -399,11 +451,15 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_ker
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-static int g_fuse_lateral = 1;  // FeatureNet: lat0 (1x1 conv + bilinear x2 + add) computed inside smooth0's producer warps
+// FeatureNet: lat0 (1x1 conv + bilinear x2 + add) computed inside smooth0's producer warps.  OFF by default: measured on the
+// B200 the computing producer is the bottleneck (smooth0 304 us fused vs 84 + 58 us for the two kernels, profiles/r2_frame_ab.md)
+static int g_fuse_lateral = 0;
 static int g_impl = 0;          // 0 auto, 1 force tc_conv.cu's kernel, 2 auto + the stride-2 layers as well
 static bool stride2_enabled() { return g_impl == 2; }
-static int g_nmma = 1;          // MMA-issuing warps per CTA (1 | 2)
-static int g_ctas_per_sm = 1;   // persistent CTAs per SM (1 | 2)
+// One issuing warp sustains one M=128,K=8 MMA per ~91 cycles, the tensor pipe takes one per ~46 (profiles/r2_mma_bench2.md):
+// two issuing warps x two persistent CTAs per SM keep it fed (per-layer A/B: profiles/r2_conv2_sweep.md).
+static int g_nmma = 2;          // MMA-issuing warps per CTA (1 | 2)
+static int g_ctas_per_sm = 2;   // persistent CTAs per SM (1 | 2)
 static int g_tune2_tz = 0, g_tune2_ty = 0, g_tune2_fold = -1, g_tune2_kbc = 0, g_tune2_slots = 0;
 
 int tc_conv2_impl() { return g_impl; }
@@ -432,6 +488,9 @@ static int tc_conv2_plan(const TcConvLayer& L, int Dn, int Hn, int Wn, bool fold
   if (P.w_bytes > 72 * 1024) return 1;
   if (L.mode == TC_DECONV && !(L.cout % 8 == 0 && skip && bias)) return 1;
   if (L.mode == TC_PLAIN && !(L.cout % 8 == 0 && bias)) return 1;
+  // epilogue shapes the kernel is written for: one TMEM load per M-tile of 8 / 16 / 32 / 64 channels; kx-folded PLAIN layers have 8
+  if (L.mode == TC_PLAIN && L.kind == 0 && !(fold ? L.cout == 8 : (L.cout == 8 || L.cout == 16 || L.cout == 32 || L.cout == 64))) return 1;
+  if (L.kind == 1 && P.N % 64 != 0) return 1;
 
   P.sz = (stride == 2 && L.KD > 1) ? 2 : 1, P.sy = stride, P.sx = stride;
   P.n_phases = P.sz * P.sy * P.sx;
@@ -668,8 +727,10 @@ extern "C" int enerf_tc_conv2_fuse_lateral(int on) {
 
 extern "C" int enerf_tc_conv2_tune(int impl, int nmma, int ctas_per_sm, int tz, int ty, int kbc, int slots) {
   using namespace enerf;
-  ENERF_REQUIRE(impl >= 0 && impl <= 2 && nmma >= 1 && nmma <= 2 && ctas_per_sm >= 1 && ctas_per_sm <= 2 && (kbc == 0 || kbc == 8 || kbc == 16 || kbc == 32),
+  ENERF_REQUIRE(impl >= 0 && impl <= 2 && nmma >= 0 && nmma <= 2 && ctas_per_sm >= 0 && ctas_per_sm <= 2 && (kbc == 0 || kbc == 8 || kbc == 16 || kbc == 32),
                 ENERF_EINVAL, "tc_conv2_tune: bad arguments");
+  if (nmma == 0) nmma = 2;                    // 0 = the shipped default
+  if (ctas_per_sm == 0) ctas_per_sm = 2;
   g_impl = impl, g_nmma = nmma, g_ctas_per_sm = ctas_per_sm, g_tune2_tz = tz, g_tune2_ty = ty, g_tune2_kbc = kbc, g_tune2_slots = slots;
   return ENERF_OK;
 }

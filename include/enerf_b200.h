@@ -265,14 +265,15 @@ ENERF_API int enerf_tc_conv(int kind, int KD, int KH, int stride, int cin, int c
                             int W, const float* wpack, const float* bias, const float* skip, float* out, float* out2,
                             int out_cstride, int out_coff, void* stream);
 
-/* Diagnostic: which kernel serves enerf_render_rays_tc / enerf_render_rays_raw_tc.  0 = auto: the warp-specialised
- * kernel (csrc/render_rays_ws.cu: gather warpgroups + a consumer warpgroup, factored MLP) for 2-3 source views, the
- * single-role kernel (csrc/render_rays_tc.cu) for 4; 1 = the single-role kernel always. */
+/* Diagnostic: which kernel serves enerf_render_rays_tc / enerf_render_rays_raw_tc.  0 = auto (currently the single-role
+ * kernel, csrc/render_rays_tc.cuh, 2-8 views), 1 = the single-role kernel, 2 = the warp-specialised kernel
+ * (csrc/render_rays_ws.cu: two gather warpgroups + a consumer warpgroup, factored MLP) for 2-3 source views. */
 ENERF_API int enerf_render_rays_tc_select(int impl);
 
 /* Diagnostic / tuning of the persistent TMA-fed convolution kernel (csrc/tc_conv2.cu) behind enerf_tc_conv and the
  * conv stacks: impl 0 = auto (it takes every stride-1 / transposed layer whose weights fit in shared memory),
- * 1 = csrc/tc_conv.cu's kernel only, 2 = same as 0; nmma = MMA-issuing warps per CTA (1|2); ctas_per_sm (1|2);
+ * 1 = csrc/tc_conv.cu's kernel only, 2 = auto + the stride-2 layers (phase tiles = TMA boxes with element stride 2);
+ * nmma = MMA-issuing warps per CTA (1|2, 0 = default 2); ctas_per_sm (1|2, 0 = default 2);
  * tz, ty, kbc (8|16|32), slots: forced tile / K-block width / ring depth, 0 = built-in choice. */
 ENERF_API int enerf_tc_conv2_tune(int impl, int nmma, int ctas_per_sm, int tz, int ty, int kbc, int slots);
 /* The launch geometry csrc/tc_conv2.cu would use for a layer ((D,H,W) = its row grid) on a device with n_sm SMs, computed
@@ -280,8 +281,9 @@ ENERF_API int enerf_tc_conv2_tune(int impl, int nmma, int ctas_per_sm, int tz, i
  * layout documented at the definition.  Returns ENERF_EUNSUPPORTED when the layer stays on csrc/tc_conv.cu. */
 ENERF_API int enerf_tc_conv2_plan(int kind, int KD, int KH, int stride, int cin, int cout, int mode, int D, int H, int W, int fold, int lateral,
                                   int n_sm, int* out);
-/* Diagnostic: 1 (default) = enerf_feature_net computes lat0 (1x1 lateral + bilinear x2 + add, feature_net.py:31-35) inside
- * smooth0's producer warps on the tensor-core path; 0 = separate lateral kernel + plain smooth0 (bit-identical features). */
+/* Diagnostic: 1 = enerf_feature_net computes lat0 (1x1 lateral + bilinear x2 + add, feature_net.py:31-35) inside
+ * smooth0's producer warps on the tensor-core path; 0 (default: the computing producer measured slower) = separate lateral
+ * kernel + plain smooth0 (bit-identical features). */
 ENERF_API int enerf_tc_conv2_fuse_lateral(int on);
 
 /* Diagnostic: when buf != NULL, CTA (0,0,0) of every later enerf_tc_conv-family launch writes 64

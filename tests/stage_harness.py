@@ -160,8 +160,8 @@ def stage_report(sd, cfg, batch, oracle_out=None, oracle_mid=None, precision="fp
             rep[f"render_rays_tc.rgb_{i}"] = err(rgb2, oracle_out[f"rgb_level{i}"][0])
             rep[f"render_rays_tc.depth_{i}"] = err(d2, oracle_out[f"depth_level{i}"][0])
             rep[f"render_rays_tc.weights_{i}"] = err(w2, oracle_out[f"weights_level{i}"][0])
-            if S <= 3:   # 2-3 views default to the warp-specialised kernel (render_rays_ws.cu): check the single-role kernel as well
-                capi.render_rays_tc_select(1)
+            if S <= 3:   # 2-3 views: the warp-specialised kernel (render_rays_ws.cu, opt-in) must agree as well
+                capi.render_rays_tc_select(2)
                 try:
                     rgb3, d3, w3 = torch.full_like(rgb, float("nan")), torch.full_like(dmap, float("nan")), torch.full_like(wts, float("nan"))
                     capi.render_rays_tc(cam, i, blob, rays, o_depth, o_std, o_nf, ndhwc(mid[f"feat_volume_{i}"][0]), img, lv.feat_ch,
@@ -169,9 +169,9 @@ def stage_report(sd, cfg, batch, oracle_out=None, oracle_mid=None, precision="fp
                     torch.cuda.synchronize()
                 finally:
                     capi.render_rays_tc_select(0)
-                rep[f"render_rays_tc.v1_rgb_{i}"] = err(rgb3, oracle_out[f"rgb_level{i}"][0])
-                rep[f"render_rays_tc.v1_depth_{i}"] = err(d3, oracle_out[f"depth_level{i}"][0])
-                rep[f"render_rays_tc.v1_weights_{i}"] = err(w3, oracle_out[f"weights_level{i}"][0])
+                rep[f"render_rays_tc.ws_rgb_{i}"] = err(rgb3, oracle_out[f"rgb_level{i}"][0])
+                rep[f"render_rays_tc.ws_depth_{i}"] = err(d3, oracle_out[f"depth_level{i}"][0])
+                rep[f"render_rays_tc.ws_weights_{i}"] = err(w3, oracle_out[f"weights_level{i}"][0])
 
     # end to end through the drop-in Network
     if human:

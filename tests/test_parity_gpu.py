@@ -201,8 +201,8 @@ TC_CONV_CASES = [
 ]
 
 # which kernel runs the layer: csrc/tc_conv.cu ("v1"), or the persistent TMA-fed csrc/tc_conv2.cu where it is eligible
-# (auto = the shipped policy; + 2 MMA-issuing warps; + 2 persistent CTAs per SM)
-TC_CONV_IMPLS = {"v1": dict(impl=1), "auto": dict(impl=0), "nmma2": dict(impl=0, nmma=2), "2cta": dict(impl=0, ctas_per_sm=2),
+# (auto = the shipped policy: 2 persistent CTAs per SM x 2 MMA-issuing warps; the 1-CTA variants)
+TC_CONV_IMPLS = {"v1": dict(impl=1), "auto": dict(impl=0), "1cta1mma": dict(impl=0, nmma=1, ctas_per_sm=1), "1cta2mma": dict(impl=0, nmma=2, ctas_per_sm=1),
                  "s2": dict(impl=2)}      # impl 2: the stride-2 layers on tc_conv2 as well (phase tiles = TMA boxes with element stride 2)
 
 
@@ -213,7 +213,7 @@ def test_tc_conv_layer(case, impl):
     stride = case[8] if len(case) > 8 else 1
     if (stride != 1) != (impl == "s2") and impl != "v1":
         pytest.skip("stride-2 layers run on csrc/tc_conv.cu unless impl 2 is selected; impl 2 is exercised on them only")
-    if impl in ("nmma2", "2cta") and dims[1] * dims[2] < 64 * 80:
+    if impl in ("1cta1mma", "1cta2mma") and dims[1] * dims[2] < 64 * 80:
         pytest.skip("variant exercised on the larger cases")
     """tcgen05 implicit-GEMM convolution vs torch's fp32 conv on the same (TF32-rounded) operands.
     Bound: 2e-3 * max|ref| (TF32 operand rounding of activations; weights are pre-rounded)."""
@@ -297,7 +297,7 @@ def test_feature_net_fused_lateral_is_bit_identical(H, W, S):
             outs[name] = (f0, f1, f2)
     finally:
         capi.tc_conv2_tune()
-        capi.tc_conv2_fuse_lateral(True)
+        capi.tc_conv2_fuse_lateral(False)
     for name in ("v2", "v2_fused"):
         for lvl in range(3):
             assert not torch.isnan(outs[name][lvl]).any(), (name, lvl)

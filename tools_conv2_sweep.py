@@ -46,14 +46,14 @@ def time_launch(fn, reps=20):
 
 
 def main(quick):
-    variants = [("v1", dict(impl=1)), ("v2", dict(impl=0)), ("v2.nmma2", dict(impl=0, nmma=2)), ("v2.2cta", dict(impl=0, ctas_per_sm=2)),
-                ("v2.2cta.nmma2", dict(impl=0, ctas_per_sm=2, nmma=2))]
+    variants = [("v1", dict(impl=1)), ("v2", dict(impl=0, nmma=1, ctas_per_sm=1)), ("v2.nmma2", dict(impl=0, nmma=2, ctas_per_sm=1)),
+                ("v2.2cta", dict(impl=0, ctas_per_sm=2, nmma=1)), ("v2.2cta.nmma2", dict(impl=0, ctas_per_sm=2, nmma=2))]
     if not quick:
         for kbc in (8, 16, 32):
-            variants.append((f"v2.kbc{kbc}", dict(impl=0, kbc=kbc)))
+            variants.append((f"v2.2cta.nmma2.kbc{kbc}", dict(impl=0, kbc=kbc)))
         for tz, ty in ((1, 7), (1, 11), (1, 15), (2, 4), (2, 8), (4, 4), (4, 8), (2, 3)):
-            variants.append((f"v2.t{tz}x{ty}", dict(impl=0, tz=tz, ty=ty)))
-            variants.append((f"v2.nmma2.t{tz}x{ty}", dict(impl=0, nmma=2, tz=tz, ty=ty)))
+            variants.append((f"v2.2cta.nmma2.t{tz}x{ty}", dict(impl=0, tz=tz, ty=ty)))
+            variants.append((f"v2.1cta.nmma2.t{tz}x{ty}", dict(impl=0, ctas_per_sm=1, tz=tz, ty=ty)))
     results, totals = [], {}
     for name, kind, KD, KH, cin, cout, mode, relu, (D, H, W) in LAYERS:
         g = torch.Generator().manual_seed(1)
@@ -74,10 +74,11 @@ def main(quick):
         ref = None
         layer_variants = list(variants)
         if kind == 0 and KD == 1 and KH == 3 and cout in (8, 16):       # kx folding for 2-D layers (off in the shipped rule): A/B it on v2
-            layer_variants += [("v2.fold2d", dict(impl=0, _fold=True)), ("v2.fold2d.nmma2", dict(impl=0, nmma=2, _fold=True)), ("v1.fold2d", dict(impl=1, _fold=True))]
+            layer_variants += [("v2.2cta.nmma2.fold2d", dict(impl=0, _fold=True)), ("v2.1cta.nmma2.fold2d", dict(impl=0, ctas_per_sm=1, _fold=True)),
+                               ("v1.fold2d", dict(impl=1, _fold=True))]
         for vname, kw in layer_variants:
             is3d = KD == 3 or kind == 1
-            if "t1x" in vname and is3d or (".t2x" in vname or ".t4x" in vname) and not is3d:
+            if ".t1x" in vname and is3d or (".t2x" in vname or ".t4x" in vname) and not is3d:
                 continue
             kw = dict(kw)
             fold2d = kw.pop("_fold", False)

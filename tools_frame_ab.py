@@ -16,12 +16,11 @@ from enerf_b200.pipeline import GraphedNetwork  # noqa: E402
 
 CONFIGS = [
     ("conv v1 | rays v1 (round-1 kernels)", dict(impl=1), False, 1),
-    ("conv v2 1cta nmma1 fused | rays ws", dict(impl=0), True, 0),
-    ("conv v2 2cta nmma2 fused | rays ws", dict(impl=0, nmma=2, ctas_per_sm=2), True, 0),
-    ("conv v2 2cta nmma2 fused | rays v1", dict(impl=0, nmma=2, ctas_per_sm=2), True, 1),
-    ("conv v2 2cta nmma2 unfused | rays v1", dict(impl=0, nmma=2, ctas_per_sm=2), False, 1),
-    ("conv v2 2cta nmma2 + stride2 fused | rays v1", dict(impl=2, nmma=2, ctas_per_sm=2), True, 1),
-    ("conv v2 1cta nmma2 fused | rays v1", dict(impl=0, nmma=2, ctas_per_sm=1), True, 1),
+    ("conv v2 2cta nmma2 | rays v1 (shipped default)", dict(impl=0, nmma=2, ctas_per_sm=2), False, 1),
+    ("conv v2 2cta nmma2 + stride2 | rays v1", dict(impl=2, nmma=2, ctas_per_sm=2), False, 1),
+    ("conv v2 2cta nmma2 + stride2 | rays ws", dict(impl=2, nmma=2, ctas_per_sm=2), False, 2),
+    ("conv v2 1cta nmma2 | rays v1", dict(impl=0, nmma=2, ctas_per_sm=1), False, 1),
+    ("conv v2 2cta nmma2 fused lat0 | rays v1", dict(impl=0, nmma=2, ctas_per_sm=2), True, 1),
 ]
 
 
@@ -93,7 +92,7 @@ def main():
         out.append(rec)
         print(json.dumps(rec), flush=True)
     capi.tc_conv2_tune()
-    capi.tc_conv2_fuse_lateral(True)
+    capi.tc_conv2_fuse_lateral(False)
     capi.render_rays_tc_select(0)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/frame_ab.json", "w"), indent=1)

@@ -18,7 +18,7 @@ for k in [k for k in batch if k.startswith("rays_")]:
     batch.pop(k)
 gb = bench.to_dev(batch, torch.device("cuda"))
 out = {}
-for impl, name in ((0, "ws"), (1, "single_role")):
+for impl, name in ((2, "ws"), (1, "single_role")):
     capi.render_rays_tc_select(impl)
     buf = torch.zeros(3 * 8 * 16, dtype=torch.int64, device="cuda")
     with torch.no_grad():
@@ -28,7 +28,7 @@ for impl, name in ((0, "ws"), (1, "single_role")):
             torch.cuda.synchronize()
     capi.render_rays_debug(None)
     t = buf.cpu().view(3, 8, 16)
-    if impl == 0:
+    if impl == 2:
         t0 = int(t[t > 0].min())
         cons = ["tile start", "gather ready", "batch1 issued", "batch1 done", "E1 done", "G2 done", "E2 done", "G3 done", "E3 done", "G5 done", "E5 done", "tile end"]
         gath = ["start", "gathered (regs)", "buffer free", "rows stored"]
