@@ -347,6 +347,64 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_ker
 #pragma unroll
           for (int c = 0; c < NF; ++c) vp[c] = vc[c];
         }
+      } else if (MODE == TC_PLAIN && (P.cout == 8 || P.cout == 16)) {
+        // narrow layers: the TMEM read latency is amortised over several M-tiles per wait (4 x 8 or 2 x 16 columns)
+        auto emit8 = [&](const float* vv, float* dst, const float* bias8) {
+          const float4 b0v = ldg4(bias8), b1v = ldg4(bias8 + 4);
+          float4 o0 = make_float4(vv[0] + b0v.x, vv[1] + b0v.y, vv[2] + b0v.z, vv[3] + b0v.w);
+          float4 o1 = make_float4(vv[4] + b1v.x, vv[5] + b1v.y, vv[6] + b1v.z, vv[7] + b1v.w);
+          if (P.relu) {
+            o0 = make_float4(fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f));
+            o1 = make_float4(fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f));
+          }
+          reinterpret_cast<float4*>(dst)[0] = o0;
+          reinterpret_cast<float4*>(dst)[1] = o1;
+        };
+        auto release_if = [&](bool last) {           // after the last TMEM read of this accumulator: hand it back to the MMA warps
+          if (last) {
+            tc::tc_fence_before_sync();
+            mbar_arrive1(&acce_bar[acc]);
+          }
+        };
+        if (P.cout == 8) {
+          for (int m0 = 0; m0 < P.n_mt; m0 += 4) {
+            float v0[8], v1[8], v2[8], v3[8];
+            const int nb = min(4, P.n_mt - m0);
+            tc::tmem_ld8(trow + (uint32_t)(m0 * P.N), v0);
+            if (nb > 1) tc::tmem_ld8(trow + (uint32_t)((m0 + 1) * P.N), v1);
+            if (nb > 2) tc::tmem_ld8(trow + (uint32_t)((m0 + 2) * P.N), v2);
+            if (nb > 3) tc::tmem_ld8(trow + (uint32_t)((m0 + 3) * P.N), v3);
+            tc::tmem_ld_wait();
+            release_if(m0 + nb == P.n_mt);
+            size_t pix;
+            int gz, gy, gx;
+            if (position(m0, pix, gz, gy, gx)) emit8(v0, P.out + pix * P.out_cstride + P.out_coff, P.bias);
+            if (nb > 1 && position(m0 + 1, pix, gz, gy, gx)) emit8(v1, P.out + pix * P.out_cstride + P.out_coff, P.bias);
+            if (nb > 2 && position(m0 + 2, pix, gz, gy, gx)) emit8(v2, P.out + pix * P.out_cstride + P.out_coff, P.bias);
+            if (nb > 3 && position(m0 + 3, pix, gz, gy, gx)) emit8(v3, P.out + pix * P.out_cstride + P.out_coff, P.bias);
+          }
+        } else {
+          for (int m0 = 0; m0 < P.n_mt; m0 += 2) {
+            float v0[16], v1[16];
+            const int nb = min(2, P.n_mt - m0);
+            tc::tmem_ld16(trow + (uint32_t)(m0 * P.N), v0);
+            if (nb > 1) tc::tmem_ld16(trow + (uint32_t)((m0 + 1) * P.N), v1);
+            tc::tmem_ld_wait();
+            release_if(m0 + nb == P.n_mt);
+            size_t pix;
+            int gz, gy, gx;
+            if (position(m0, pix, gz, gy, gx)) {
+              float* dst = P.out + pix * P.out_cstride + P.out_coff;
+              emit8(v0, dst, P.bias);
+              emit8(v0 + 8, dst + 8, P.bias + 8);
+            }
+            if (nb > 1 && position(m0 + 1, pix, gz, gy, gx)) {
+              float* dst = P.out + pix * P.out_cstride + P.out_coff;
+              emit8(v1, dst, P.bias);
+              emit8(v1 + 8, dst + 8, P.bias + 8);
+            }
+          }
+        }
       } else {
         for (int m = 0; m < P.n_mt; ++m) {
           size_t pix;
@@ -454,8 +512,8 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_ker
 // FeatureNet: lat0 (1x1 conv + bilinear x2 + add) computed inside smooth0's producer warps.  OFF by default: measured on the
 // B200 the computing producer is the bottleneck (smooth0 304 us fused vs 84 + 58 us for the two kernels, profiles/r2_frame_ab.md)
 static int g_fuse_lateral = 0;
-static int g_impl = 0;          // 0 auto, 1 force tc_conv.cu's kernel, 2 auto + the stride-2 layers as well
-static bool stride2_enabled() { return g_impl == 2; }
+static int g_impl = 0;          // 0 auto (every eligible layer incl. stride 2), 1 force tc_conv.cu's kernel, 2 = 0, 3 auto without the stride-2 layers
+static bool stride2_enabled() { return g_impl != 3; }
 // One issuing warp sustains one M=128,K=8 MMA per ~91 cycles, the tensor pipe takes one per ~46 (profiles/r2_mma_bench2.md):
 // two issuing warps x two persistent CTAs per SM keep it fed (per-layer A/B: profiles/r2_conv2_sweep.md).
 static int g_nmma = 2;          // MMA-issuing warps per CTA (1 | 2)
@@ -512,7 +570,7 @@ static int tc_conv2_plan(const TcConvLayer& L, int Dn, int Hn, int Wn, bool fold
   P.TZ = is2d ? 1 : 2;
   if (L.kind == 0 && L.KH == 3) {
     if (is2d) P.TY = (L.cin == 8) ? 15 : 7;
-    else if (fold) P.TZ = 4, P.TY = 4;
+    else if (fold) P.TZ = (g_ctas_per_sm >= 2) ? 2 : 4, P.TY = 4;      // sweep: 2 x 4 x 32 with two CTAs per SM (reg0.conv0 42 -> 35 us, reg1.conv0 65 -> 60)
   }
   if (L.kind == 0 && L.KH == 1) P.TY = 8;
   if (L.kind == 1) P.TZ = 2, P.TY = (P.N <= 64) ? 3 : 4;
@@ -584,7 +642,9 @@ static int tc_conv2_plan(const TcConvLayer& L, int Dn, int Hn, int Wn, bool fold
       int slots = (int)((budget - std::min(budget, fixed)) / slot);
       slots = std::min(slots, 4);
       if (g_tune2_slots > 0) slots = std::min(slots, g_tune2_slots);
-      const int want = (ci == 2 || g_tune2_kbc > 0) ? 2 : 3;      // fall to narrower K-blocks rather than a 2-deep ring
+      // one CTA per SM: fall to narrower K-blocks rather than a 2-deep ring; two CTAs per SM overlap each other, the widest
+      // K-block with two slots wins (sweep: smooth0 59.9 -> 55.8 us, reg1.conv2 20.9 -> 19.4)
+      const int want = (ci == 2 || g_tune2_kbc > 0 || g_ctas_per_sm >= 2) ? 2 : 3;
       if (slots >= want || (slots >= 2 && kbc == 8)) {
         P.kbc = kbc, P.n_kb = L.cin / kbc, P.n_slots = slots, P.slot_bytes = slot, P.box_bytes = (uint32_t)npix * rb;
         P.phase_bytes = phase_stride;
@@ -727,7 +787,7 @@ extern "C" int enerf_tc_conv2_fuse_lateral(int on) {
 
 extern "C" int enerf_tc_conv2_tune(int impl, int nmma, int ctas_per_sm, int tz, int ty, int kbc, int slots) {
   using namespace enerf;
-  ENERF_REQUIRE(impl >= 0 && impl <= 2 && nmma >= 0 && nmma <= 2 && ctas_per_sm >= 0 && ctas_per_sm <= 2 && (kbc == 0 || kbc == 8 || kbc == 16 || kbc == 32),
+  ENERF_REQUIRE(impl >= 0 && impl <= 3 && nmma >= 0 && nmma <= 2 && ctas_per_sm >= 0 && ctas_per_sm <= 2 && (kbc == 0 || kbc == 8 || kbc == 16 || kbc == 32),
                 ENERF_EINVAL, "tc_conv2_tune: bad arguments");
   if (nmma == 0) nmma = 2;                    // 0 = the shipped default
   if (ctas_per_sm == 0) ctas_per_sm = 2;

@@ -271,8 +271,9 @@ ENERF_API int enerf_tc_conv(int kind, int KD, int KH, int stride, int cin, int c
 ENERF_API int enerf_render_rays_tc_select(int impl);
 
 /* Diagnostic / tuning of the persistent TMA-fed convolution kernel (csrc/tc_conv2.cu) behind enerf_tc_conv and the
- * conv stacks: impl 0 = auto (it takes every stride-1 / transposed layer whose weights fit in shared memory),
- * 1 = csrc/tc_conv.cu's kernel only, 2 = auto + the stride-2 layers (phase tiles = TMA boxes with element stride 2);
+ * conv stacks: impl 0 = auto (it takes every layer whose weights fit in shared memory),
+ * 1 = csrc/tc_conv.cu's kernel only, 2 = same as 0, 3 = auto without the stride-2 layers (their phase tiles are TMA boxes
+ * with element stride 2);
  * nmma = MMA-issuing warps per CTA (1|2, 0 = default 2); ctas_per_sm (1|2, 0 = default 2);
  * tz, ty, kbc (8|16|32), slots: forced tile / K-block width / ring depth, 0 = built-in choice. */
 ENERF_API int enerf_tc_conv2_tune(int impl, int nmma, int ctas_per_sm, int tz, int ty, int kbc, int slots);

@@ -203,7 +203,7 @@ TC_CONV_CASES = [
 # which kernel runs the layer: csrc/tc_conv.cu ("v1"), or the persistent TMA-fed csrc/tc_conv2.cu where it is eligible
 # (auto = the shipped policy: 2 persistent CTAs per SM x 2 MMA-issuing warps; the 1-CTA variants)
 TC_CONV_IMPLS = {"v1": dict(impl=1), "auto": dict(impl=0), "1cta1mma": dict(impl=0, nmma=1, ctas_per_sm=1), "1cta2mma": dict(impl=0, nmma=2, ctas_per_sm=1),
-                 "s2": dict(impl=2)}      # impl 2: the stride-2 layers on tc_conv2 as well (phase tiles = TMA boxes with element stride 2)
+                 "nos2": dict(impl=3)}    # impl 3: the stride-2 layers stay on csrc/tc_conv.cu (default: TMA boxes with element stride 2)
 
 
 @pytest.mark.parametrize("impl", list(TC_CONV_IMPLS))
@@ -211,8 +211,8 @@ TC_CONV_IMPLS = {"v1": dict(impl=1), "auto": dict(impl=0), "1cta1mma": dict(impl
 def test_tc_conv_layer(case, impl):
     kind, KD, KH, cin, cout, mode, relu, dims = case[:8]
     stride = case[8] if len(case) > 8 else 1
-    if (stride != 1) != (impl == "s2") and impl != "v1":
-        pytest.skip("stride-2 layers run on csrc/tc_conv.cu unless impl 2 is selected; impl 2 is exercised on them only")
+    if impl == "nos2" and stride == 1:
+        pytest.skip("impl 3 differs from auto on the stride-2 layers only")
     if impl in ("1cta1mma", "1cta2mma") and dims[1] * dims[2] < 64 * 80:
         pytest.skip("variant exercised on the larger cases")
     """tcgen05 implicit-GEMM convolution vs torch's fp32 conv on the same (TF32-rounded) operands.

@@ -126,11 +126,7 @@ def test_tc_conv2_geometry_emulated_on_cpu(case):
     kind, KD, KH, stride, cin, cout, mode, relu, (D, H, W), n_sm = case
     g = torch.Generator().manual_seed(cin * 31 + cout + KD)
     fold = packing.tc_fold_kx(KD, KH, stride, cout, single=(mode == TC_SINGLE)) if kind == 0 else False
-    capi.tc_conv2_tune(impl=2)      # impl 2 also plans the stride-2 layers (no CUDA call involved)
-    try:
-        plan = capi.tc_conv2_plan(kind, KD, KH, stride, cin, cout, mode, D, H, W, fold, n_sm=n_sm)
-    finally:
-        capi.tc_conv2_tune()
+    plan = capi.tc_conv2_plan(kind, KD, KH, stride, cin, cout, mode, D, H, W, fold, n_sm=n_sm)
     assert plan["fold"] == int(fold)
     sz = stride if (KD > 1 and kind == 0) else 1
     xin = torch.randn(1, cin, D * sz, H * (stride if kind == 0 else 1), W * (stride if kind == 0 else 1), generator=g)

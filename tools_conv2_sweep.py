@@ -76,17 +76,23 @@ def main(quick):
         if kind == 0 and KD == 1 and KH == 3 and cout in (8, 16):       # kx folding for 2-D layers (off in the shipped rule): A/B it on v2
             layer_variants += [("v2.2cta.nmma2.fold2d", dict(impl=0, _fold=True)), ("v2.1cta.nmma2.fold2d", dict(impl=0, ctas_per_sm=1, _fold=True)),
                                ("v1.fold2d", dict(impl=1, _fold=True))]
+        if kind == 0 and packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3)):       # the folded 3-D layers, unfolded (27 taps of N = C)
+            layer_variants += [("v2.2cta.nmma2.nofold", dict(impl=0, _nofold=True)), ("v1.nofold", dict(impl=1, _nofold=True))]
         for vname, kw in layer_variants:
             is3d = KD == 3 or kind == 1
             if ".t1x" in vname and is3d or (".t2x" in vname or ".t4x" in vname) and not is3d:
                 continue
             kw = dict(kw)
             fold2d = kw.pop("_fold", False)
+            nofold = kw.pop("_nofold", False)
             capi.tc_conv2_tune(**kw)
             wp_v = wp
             if fold2d:
                 wp_v = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=True).cuda()
                 capi.tc_conv_tune(0, 0, 1)
+            if nofold:
+                wp_v = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=False).cuda()
+                capi.tc_conv_tune(0, 0, 0)
             try:
                 out.fill_(float("nan"))
                 fn = lambda: capi.tc_conv(kind, KD, KH, cout, mode, relu, x, wp_v, bias, skip, out, out2, out_cstride=(8 if mode == 1 else cout))  # noqa: E731
@@ -95,12 +101,12 @@ def main(quick):
                     ref = out.clone()
                     same = True
                 else:
-                    same = bool(torch.equal(out, ref)) if not fold2d else float((out - ref).abs().max())
+                    same = bool(torch.equal(out, ref)) if not (fold2d or nofold) else float((out - ref).abs().max())
             except Exception as e:  # noqa: BLE001
                 us, same = None, str(e)[:120]
                 torch.cuda.synchronize()
             finally:
-                if fold2d:
+                if fold2d or nofold:
                     capi.tc_conv_tune(0, 0, -1)
             results.append({"layer": name, "variant": vname, "us": us, "equal_to_v1": same})
             if us and vname in ("v1", "v2", "v2.nmma2", "v2.2cta", "v2.2cta.nmma2"):

@@ -17,8 +17,8 @@ from enerf_b200.pipeline import GraphedNetwork  # noqa: E402
 CONFIGS = [
     ("conv v1 | rays v1 (round-1 kernels)", dict(impl=1), False, 1),
     ("conv v2 2cta nmma2 | rays v1 (shipped default)", dict(impl=0, nmma=2, ctas_per_sm=2), False, 1),
-    ("conv v2 2cta nmma2 + stride2 | rays v1", dict(impl=2, nmma=2, ctas_per_sm=2), False, 1),
-    ("conv v2 2cta nmma2 + stride2 | rays ws", dict(impl=2, nmma=2, ctas_per_sm=2), False, 2),
+    ("conv v2 2cta nmma2, stride-2 layers on v1 | rays v1", dict(impl=3, nmma=2, ctas_per_sm=2), False, 1),
+    ("conv v2 2cta nmma2 | rays ws", dict(impl=0, nmma=2, ctas_per_sm=2), False, 2),
     ("conv v2 1cta nmma2 | rays v1", dict(impl=0, nmma=2, ctas_per_sm=1), False, 1),
     ("conv v2 2cta nmma2 fused lat0 | rays v1", dict(impl=0, nmma=2, ctas_per_sm=2), True, 1),
 ]
