@@ -50,10 +50,14 @@ struct TcConv2Params {
   float* out2;
   // PROD = 1 (FeatureNet smooth0 with the lateral fused in): the 32-channel input tile is COMPUTED by four producer
   // warps instead of loaded: in[n,y,x,:] = bilinear_x2(up_in)[n,y,x,:] + (lat_b + lat_w^T lat_in[n,y,x,:]), zero outside the image
-  const float* lat_in;   // (S,H,W,LATC) channels-last, LATC = 8 (PROD 1) | 16 (PROD 2)
-  const float* lat_w;    // [LATC][32]
+  const float* lat_in;   // (S,H,W,8) channels-last   (read through map_c0)
+  const float* lat_w;    // [8][32]
   const float* lat_b;    // [32]
-  const float* up_in;    // (S,H/2,W/2,32)
+  const float* up_in;    // (S,H/2,W/2,32)            (read through map_f1)
+  // the producer's SOURCE tiles arrive by TMA into a 2-deep ring behind the fold exchange: [c0 tile (IY x IX px x 32 B, SWIZZLE_32B)]
+  // [f1 tile (FH x FW px x 128 B, SWIZZLE_128B)]
+  int FW, FH;
+  uint32_t src_slot_bytes, src_f1_off, src_bytes;   // slot stride, offset of the f1 tile inside a slot, bytes per slot's two boxes
 };
 
 __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
@@ -67,10 +71,12 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 template <int NTAPS, int MODE, int FOLD, int NMMA, int PROD = 0>
-__global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_kernel(const __grid_constant__ CUtensorMap map, const TcConv2Params P) {
-  constexpr int NP = PROD ? 4 : 1;      // producer warps
+__global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
+    tc_conv2_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_c0, const __grid_constant__ CUtensorMap map_f1,
+                    const TcConv2Params P) {
+  constexpr int NP = PROD ? 5 : 1;      // producer warps: the TMA warp (+ 4 computing warps when the lateral is fused)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], accf_bar[2], acce_bar[2], w_bar;
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], accf_bar[2], acce_bar[2], w_bar, srcf_bar[2], srce_bar[2];
   __shared__ uint32_t tmem_base_s;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   // dynamic shared memory: [ring][weights][fold exchange x2]; the ring base is 1024-aligned (swizzle pattern phase)
@@ -88,6 +94,10 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_ker
       tc::mbar_init(&acce_bar[i], 128);      // every epilogue thread
     }
     tc::mbar_init(&w_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&srcf_bar[i], 1);        // source boxes landed (expect_tx)
+      tc::mbar_init(&srce_bar[i], 128);      // every computing producer thread has read them
+    }
     tc::fence_mbar_init();
   }
   if (warp == NP) tc::tmem_alloc(&tmem_base_s, P.tmem_cols);
@@ -97,23 +107,45 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_ker
   const uint32_t tmem = tmem_base_s;
   const uint32_t row_bytes = (uint32_t)P.kbc * 4u;
 
-  if (PROD != 0 && warp < NP) {
-    constexpr int LATC = (PROD == 2) ? 16 : 8;       // channels of the lateral's input (conv0: 8, conv1: 16)
-    // ============================== computing producer (lateral 1x1 conv + bilinear x2 + add) ==============================
-    // thread = (halo pixel, g): channels [4g, 4g+4) and [16+4g, 16+4g+4) -- 16-byte chunks g and 4+g of the pixel's 128-byte
-    // row, written at their SWIZZLE_128B position (chunk ^ (row & 7)); same arithmetic and order as lateral_upadd_kernel
-    if (lane == 0 && warp == 0) {
+  if (PROD != 0 && warp == 0) {
+    // ============================== source loader (fused lateral): conv0 tile + feat1_pre region of every tile, by TMA ==============================
+    unsigned char* src0 = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(xch0) + P.xch_bytes + 1023) & ~(uintptr_t)1023);
+    if (lane == 0) {
+      tma::prefetch_desc(&map_c0);
+      tma::prefetch_desc(&map_f1);
       tc::mbar_expect_tx(&w_bar, P.w_bytes);
       tc::tma_load_1d(w_s, P.wpack, P.w_bytes, &w_bar);
     }
-    const int g = t & 3;
-    float4 wreg[LATC == 8 ? 16 : 1];                  // LATC = 8: this thread's 8 x 8 weight slice lives in registers
-    if constexpr (LATC == 8) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        wreg[2 * k] = ldg4(P.lat_w + k * 32 + g * 4);
-        wreg[2 * k + 1] = ldg4(P.lat_w + k * 32 + 16 + g * 4);
+    const int H = P.Hn, W = P.Wn, hi = H / 2, wi = W / 2;
+    const float rh = (H > 1) ? (float)(hi - 1) / (float)(H - 1) : 0.f;
+    const float rw = (W > 1) ? (float)(wi - 1) / (float)(W - 1) : 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+      const int bx = tile % P.nx, by = (tile / P.nx) % P.ny, n = tile / (P.nx * P.ny);
+      const int x0 = bx * P.TX - P.ox, y0 = by * P.TY - P.oy;
+      const int fy0 = (int)(rh * (float)max(y0, 0)), fx0 = (int)(rw * (float)max(x0, 0));     // first source row / column any pixel of the tile taps
+      const int ss = it & 1;
+      tc::mbar_wait(&srce_bar[ss], (uint32_t)(((it >> 1) & 1) ^ 1));
+      if (lane == 0) {
+        tc::mbar_expect_tx(&srcf_bar[ss], P.src_bytes);
+        const uint32_t dst = tc::smem_u32(src0 + (size_t)ss * P.src_slot_bytes);
+        tma::load_4d(dst, &map_c0, 0, x0, y0, n, &srcf_bar[ss]);
+        tma::load_4d(dst + P.src_f1_off, &map_f1, 0, fx0, fy0, n, &srcf_bar[ss]);
       }
+      __syncwarp();
+    }
+  } else if (PROD != 0 && warp < NP) {
+    // ============================== computing producer (lateral 1x1 conv + bilinear x2 + add), sources in shared memory ==============================
+    // thread = (halo pixel, g): channels [4g, 4g+4) and [16+4g, 16+4g+4) -- 16-byte chunks g and 4+g of the pixel's 128-byte
+    // row, written at their SWIZZLE_128B position (chunk ^ (row & 7)); same arithmetic and order as lateral_upadd_kernel
+    unsigned char* src0 = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(xch0) + P.xch_bytes + 1023) & ~(uintptr_t)1023);
+    const int pt = t - 32;                              // 0..127
+    const int g = pt & 3;
+    float4 wreg[16];                                    // this thread's 8 x 8 slice of the lateral's weights
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      wreg[2 * k] = ldg4(P.lat_w + k * 32 + g * 4);
+      wreg[2 * k + 1] = ldg4(P.lat_w + k * 32 + 16 + g * 4);
     }
     const float4 bias0 = ldg4(P.lat_b + g * 4), bias1 = ldg4(P.lat_b + 16 + g * 4);
     const int H = P.Hn, W = P.Wn, hi = H / 2, wi = W / 2;
@@ -122,48 +154,47 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_ker
     const int npix = P.IY * P.IX;
     int it = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
-      const int bx = tile % P.nx, by = (tile / P.nx) % P.ny, n = tile / (P.nx * P.ny);
+      const int bx = tile % P.nx, by = (tile / P.nx) % P.ny;
       const int x0 = bx * P.TX - P.ox, y0 = by * P.TY - P.oy;
-      const int slot = it % P.n_slots;
-      tc::mbar_wait(&empty_bar[slot], (uint32_t)(((it / P.n_slots) & 1) ^ 1));
+      const int fy0 = (int)(rh * (float)max(y0, 0)), fx0 = (int)(rw * (float)max(x0, 0));
+      const int slot = it % P.n_slots, ss = it & 1;
+      tc::mbar_wait(&empty_bar[slot], (uint32_t)(((it / P.n_slots) & 1) ^ 1));       // operand slot free (its MMAs are done)
+      tc::mbar_wait(&srcf_bar[ss], (uint32_t)((it >> 1) & 1));                       // this tile's sources have landed
       unsigned char* dst = ring + (size_t)slot * P.slot_bytes;
-      for (int i = t; i < npix * 4; i += 128) {
+      const unsigned char* c0s = src0 + (size_t)ss * P.src_slot_bytes;
+      const unsigned char* f1s = c0s + P.src_f1_off;
+      for (int i = pt; i < npix * 4; i += 128) {
         const int pp = i >> 2;
         const int yy = pp / P.IX, xx = pp - yy * P.IX;
         const int y = y0 + yy, x = x0 + xx;
         float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
         if (y >= 0 && y < H && x >= 0 && x < W) {
-          const size_t pix = ((size_t)n * H + y) * W + x;
           float acc[8] = {bias0.x, bias0.y, bias0.z, bias0.w, bias1.x, bias1.y, bias1.z, bias1.w};
+          const unsigned char* crow = c0s + (size_t)pp * 32;           // SWIZZLE_32B: 16-byte chunk j of row pp sits at j ^ ((pp >> 2) & 1)
 #pragma unroll
-          for (int q = 0; q < LATC / 4; ++q) {
-            const float4 v = ldg4(P.lat_in + pix * LATC + 4 * q);
+          for (int q = 0; q < 2; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(crow + ((q ^ ((pp >> 2) & 1)) << 4));
             const float xv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 w0, w1;
-              if constexpr (LATC == 8) {
-                w0 = wreg[2 * (4 * q + j)], w1 = wreg[2 * (4 * q + j) + 1];
-              } else {       // 2 KB of weights, warp-uniform addresses per g: L1-resident
-                w0 = ldg4(P.lat_w + (4 * q + j) * 32 + g * 4), w1 = ldg4(P.lat_w + (4 * q + j) * 32 + 16 + g * 4);
-              }
-              acc[0] = fmaf(xv[j], w0.x, acc[0]), acc[1] = fmaf(xv[j], w0.y, acc[1]), acc[2] = fmaf(xv[j], w0.z, acc[2]), acc[3] = fmaf(xv[j], w0.w, acc[3]);
-              acc[4] = fmaf(xv[j], w1.x, acc[4]), acc[5] = fmaf(xv[j], w1.y, acc[5]), acc[6] = fmaf(xv[j], w1.z, acc[6]), acc[7] = fmaf(xv[j], w1.w, acc[7]);
+            for (int jx = 0; jx < 4; ++jx) {
+              const float4 w0 = wreg[2 * (4 * q + jx)], w1 = wreg[2 * (4 * q + jx) + 1];
+              acc[0] = fmaf(xv[jx], w0.x, acc[0]), acc[1] = fmaf(xv[jx], w0.y, acc[1]), acc[2] = fmaf(xv[jx], w0.z, acc[2]), acc[3] = fmaf(xv[jx], w0.w, acc[3]);
+              acc[4] = fmaf(xv[jx], w1.x, acc[4]), acc[5] = fmaf(xv[jx], w1.y, acc[5]), acc[6] = fmaf(xv[jx], w1.z, acc[6]), acc[7] = fmaf(xv[jx], w1.w, acc[7]);
             }
           }
-          // bilinear x2 with align_corners=True (ATen upsample_bilinear2d lambdas)
+          // bilinear x2 with align_corners=True (ATen upsample_bilinear2d lambdas); taps from the staged feat1_pre region
           const float h1r = rh * (float)y, w1r = rw * (float)x;
           const int h1 = (int)h1r, w1 = (int)w1r;
           const int h1p = (h1 < hi - 1) ? 1 : 0, w1p = (w1 < wi - 1) ? 1 : 0;
           const float h1l = h1r - (float)h1, h0l = 1.f - h1l, w1l = w1r - (float)w1, w0l = 1.f - w1l;
-          const float* u00 = P.up_in + (((size_t)n * hi + h1) * wi + w1) * 32 + g * 4;
-          const float* u01 = u00 + (size_t)w1p * 32;
-          const float* u10 = u00 + (size_t)h1p * wi * 32;
-          const float* u11 = u10 + (size_t)w1p * 32;
+          const int r00 = (h1 - fy0) * P.FW + (w1 - fx0), r01 = r00 + w1p, r10 = r00 + h1p * P.FW, r11 = r10 + w1p;
+          auto tap = [&](int rr, int chunk) {       // SWIZZLE_128B: chunk c of row rr sits at c ^ (rr & 7)
+            return *reinterpret_cast<const float4*>(f1s + (size_t)rr * 128 + ((chunk ^ (rr & 7)) << 4));
+          };
           float up[8];
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const float4 a = ldg4(u00 + 16 * q), b = ldg4(u01 + 16 * q), c = ldg4(u10 + 16 * q), dd = ldg4(u11 + 16 * q);
+            const float4 a = tap(r00, g + 4 * q), b = tap(r01, g + 4 * q), c = tap(r10, g + 4 * q), dd = tap(r11, g + 4 * q);
             up[4 * q + 0] = h0l * (w0l * a.x + w1l * b.x) + h1l * (w0l * c.x + w1l * dd.x);
             up[4 * q + 1] = h0l * (w0l * a.y + w1l * b.y) + h1l * (w0l * c.y + w1l * dd.y);
             up[4 * q + 2] = h0l * (w0l * a.z + w1l * b.z) + h1l * (w0l * c.z + w1l * dd.z);
@@ -177,6 +208,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_ker
         *reinterpret_cast<float4*>(rowp + ((g ^ (pp & 7)) << 4)) = o0;
         *reinterpret_cast<float4*>(rowp + (((4 + g) ^ (pp & 7)) << 4)) = o1;
       }
+      mbar_arrive1(&srce_bar[ss]);             // the source slot may be refilled
       tc::fence_proxy_async();                 // my part of the tile -> visible to the tensor core
       mbar_arrive1(&full_bar[slot]);
     }
@@ -511,7 +543,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 4 : 1))) tc_conv2_ker
 // ---- host side ------------------------------------------------------------------------------------
 // FeatureNet: lat0 (1x1 conv + bilinear x2 + add) computed inside smooth0's producer warps.  OFF by default: measured on the
 // B200 the computing producer is the bottleneck (smooth0 304 us fused vs 84 + 58 us for the two kernels, profiles/r2_frame_ab.md)
-static int g_fuse_lateral = 0;
+static int g_fuse_lateral = 0;   // (second version of the producer -- sources staged by TMA, taps from shared memory -- to be re-measured)
 static int g_impl = 0;          // 0 auto (every eligible layer incl. stride 2), 1 force tc_conv.cu's kernel, 2 = 0, 3 auto without the stride-2 layers
 static bool stride2_enabled() { return g_impl != 3; }
 // One issuing warp sustains one M=128,K=8 MMA per ~91 cycles, the tensor pipe takes one per ~46 (profiles/r2_mma_bench2.md):
@@ -574,6 +606,7 @@ static int tc_conv2_plan(const TcConvLayer& L, int Dn, int Hn, int Wn, bool fold
   }
   if (L.kind == 0 && L.KH == 1) P.TY = 8;
   if (L.kind == 1) P.TZ = 2, P.TY = (P.N <= 64) ? 3 : 4;
+  if (lat) P.TY = 7;
   if (stride == 2) {
     if (is2d) P.TY = 7;
     else P.TZ = 2, P.TY = 3;
@@ -582,7 +615,9 @@ static int tc_conv2_plan(const TcConvLayer& L, int Dn, int Hn, int Wn, bool fold
   if (g_tune2_ty > 0) P.TY = g_tune2_ty;
   P.TZ = std::min(P.TZ, Dn), P.TY = std::min(P.TY, Hn);
 
-  const size_t budget = (g_ctas_per_sm >= 2 ? 110 : 216) * 1024;
+  // the fused-lateral kernel (352 threads, ~140 registers) runs one CTA per SM whatever the setting
+  const bool two_ctas = g_ctas_per_sm >= 2 && !lat;
+  const size_t budget = (two_ctas ? 110 : 216) * 1024;
   for (;;) {
     P.IZ = P.TZ + hz, P.IY = P.TY + hy, P.IX = P.TX + hx;
     const int npix = P.IZ * P.IY * P.IX;
@@ -621,9 +656,17 @@ static int tc_conv2_plan(const TcConvLayer& L, int Dn, int Hn, int Wn, bool fold
           for (int kx = 0; kx < L.KH; ++kx) tap_rows[i++] = (kz * P.IY + ky) * P.IX + kx;
     }
     for (int i = 0; i < n_taps; ++i) max_tap_rows = std::max(max_tap_rows, tap_rows[i]);
-    P.n_acc = (2 * P.n_mt * P.N <= (g_ctas_per_sm >= 2 ? 256 : 512)) ? 2 : 1;
-    const bool tmem_ok = P.n_acc * P.n_mt * P.N <= (g_ctas_per_sm >= 2 ? 256 : 512);
+    P.n_acc = (2 * P.n_mt * P.N <= (two_ctas ? 256 : 512)) ? 2 : 1;
+    const bool tmem_ok = P.n_acc * P.n_mt * P.N <= (two_ctas ? 256 : 512);
     P.xch_bytes = fold ? (uint32_t)align_up((size_t)(P.n_mt * 4 + 1) * 2 * P.N * 4, 64) * 2u : 0u;
+    P.FW = P.FH = 0, P.src_slot_bytes = P.src_f1_off = P.src_bytes = 0;
+    if (lat) {   // source tiles of the fused lateral: conv0 halo tile (32-byte rows) + the feat1_pre rows / columns its bilinear taps reach
+      P.FW = P.IX / 2 + 3, P.FH = P.IY / 2 + 3;
+      const uint32_t c0b = (uint32_t)npix * 32u, f1b = (uint32_t)(P.FW * P.FH) * 128u;
+      P.src_f1_off = (uint32_t)align_up(c0b, 1024);
+      P.src_slot_bytes = P.src_f1_off + (uint32_t)align_up(f1b, 1024);
+      P.src_bytes = c0b + f1b;
+    }
     // K-block = the widest channel group whose ring still holds >= 2 slots (3-4 preferred)
     bool placed = false;
     const int cands[3] = {32, 16, 8};
@@ -638,13 +681,13 @@ static int tc_conv2_plan(const TcConvLayer& L, int Dn, int Hn, int Wn, bool fold
       const uint32_t rows_alloc = (uint32_t)std::max(npix, P.n_mt * 128 + max_tap_rows + 2);
       const uint32_t phase_stride = (uint32_t)align_up((size_t)npix * rb, 1024);
       const uint32_t slot = (uint32_t)align_up((size_t)(P.n_phases - 1) * phase_stride + (size_t)rows_alloc * rb, 1024);
-      const size_t fixed = 1024 + align_up(P.w_bytes, 128) + P.xch_bytes + 256;
+      const size_t fixed = 1024 + align_up(P.w_bytes, 128) + P.xch_bytes + 256 + (lat ? 1024 + 2 * (size_t)P.src_slot_bytes : 0);
       int slots = (int)((budget - std::min(budget, fixed)) / slot);
       slots = std::min(slots, 4);
       if (g_tune2_slots > 0) slots = std::min(slots, g_tune2_slots);
       // one CTA per SM: fall to narrower K-blocks rather than a 2-deep ring; two CTAs per SM overlap each other, the widest
       // K-block with two slots wins (sweep: smooth0 59.9 -> 55.8 us, reg1.conv2 20.9 -> 19.4)
-      const int want = (ci == 2 || g_tune2_kbc > 0 || g_ctas_per_sm >= 2) ? 2 : 3;
+      const int want = (ci == 2 || g_tune2_kbc > 0 || two_ctas || lat) ? 2 : 3;
       if (slots >= want || (slots >= 2 && kbc == 8)) {
         P.kbc = kbc, P.n_kb = L.cin / kbc, P.n_slots = slots, P.slot_bytes = slot, P.box_bytes = (uint32_t)npix * rb;
         P.phase_bytes = phase_stride;
@@ -696,8 +739,22 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
     ENERF_REQUIRE(rc == 0, ENERF_ECUDA, "tc_conv2: cuTensorMapEncodeTiled failed (%d) for a (%d,%d,%d,%d) tensor, box (%d,%d,%d,%d)", rc, Dn, Hn, Wn, L.cin,
                   P.kbc, P.IX, P.IY, P.IZ);
   }
-  const size_t smem = 1024 + (size_t)P.n_slots * P.slot_bytes + align_up(P.w_bytes, 128) + P.xch_bytes + 128;
-  const int grid = std::min(P.n_tiles, n_sm * g_ctas_per_sm);
+  CUtensorMap map_c0, map_f1;
+  memset(&map_c0, 0, sizeof(map_c0));
+  memset(&map_f1, 0, sizeof(map_f1));
+  if (lat != nullptr) {
+    const uint64_t hi = (uint64_t)Hn / 2, wi = (uint64_t)Wn / 2;
+    const uint64_t d0[4] = {8, (uint64_t)Wn, (uint64_t)Hn, (uint64_t)Dn}, s0[3] = {32, (uint64_t)Wn * 32, (uint64_t)Hn * Wn * 32};
+    const uint32_t b0[4] = {8, (uint32_t)P.IX, (uint32_t)P.IY, 1};
+    int rc = tma::encode_f32(&map_c0, lat->lat_in, 4, d0, s0, b0, nullptr, CU_TENSOR_MAP_SWIZZLE_32B);
+    ENERF_REQUIRE(rc == 0, ENERF_ECUDA, "tc_conv2(lateral): cuTensorMapEncodeTiled(conv0) failed (%d)", rc);
+    const uint64_t d1[4] = {32, wi, hi, (uint64_t)Dn}, s1[3] = {128, wi * 128, hi * wi * 128};
+    const uint32_t b1[4] = {32, (uint32_t)P.FW, (uint32_t)P.FH, 1};
+    rc = tma::encode_f32(&map_f1, lat->up_in, 4, d1, s1, b1, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    ENERF_REQUIRE(rc == 0, ENERF_ECUDA, "tc_conv2(lateral): cuTensorMapEncodeTiled(feat1_pre) failed (%d)", rc);
+  }
+  const size_t smem = 1024 + (size_t)P.n_slots * P.slot_bytes + align_up(P.w_bytes, 128) + P.xch_bytes + 128 + (lat ? 1024 + 2 * (size_t)P.src_slot_bytes : 0);
+  const int grid = std::min(P.n_tiles, n_sm * ((g_ctas_per_sm >= 2 && lat == nullptr) ? 2 : 1));
 #define TC2_LAUNCH(NT, MD, FD, NM)                                                                                                        \
   do {                                                                                                                                    \
     static PerDeviceSize smem_set_pd;                                                                                                     \
@@ -707,7 +764,7 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
       ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv2: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));               \
       smem_set = smem;                                                                                                                    \
     }                                                                                                                                     \
-    tc_conv2_kernel<NT, MD, FD, NM><<<grid, 32 * (4 + NM + 1), smem, stream>>>(map, P);                                                       \
+    tc_conv2_kernel<NT, MD, FD, NM><<<grid, 32 * (4 + NM + 1), smem, stream>>>(map, map_c0, map_f1, P);                                                       \
   } while (0)
 #define TC2_DISPATCH(NT, MD, FD)             \
   do {                                       \
@@ -724,7 +781,7 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
       ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv2(lateral): cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));             \
       lat_set = smem;                                                                                                                            \
     }                                                                                                                                            \
-    tc_conv2_kernel<9, TC_PLAIN, 0, NM, PR><<<grid, 32 * (4 + NM + 4), smem, stream>>>(map, P);                                                  \
+    tc_conv2_kernel<9, TC_PLAIN, 0, NM, PR><<<grid, 32 * (4 + NM + 5), smem, stream>>>(map, map_c0, map_f1, P);                                                  \
   } while (0)
     // (lat1 -> smooth1 is NOT fused: its output feat1_pre is also lat0's up-sampling source, so it must exist in HBM anyway;
     //  the producer is written for lat_cin 8 | 16, only 8 is instantiated)
