@@ -258,7 +258,7 @@ def tc_conv_tune(tz=0, ty=0, fold=-1):
     _check(lib().enerf_tc_conv_tune(int(tz), int(ty), int(fold)), "enerf_tc_conv_tune", launches=0)
 
 
-_FUSE_LAT, _CONV_IMPL = False, 0     # mirrors of the library's switches, for the launch count only
+_FUSE_LAT, _CONV_IMPL = True, 0     # mirrors of the library's switches, for the launch count only
 
 
 def tc_conv2_tune(impl=0, nmma=0, ctas_per_sm=0, tz=0, ty=0, kbc=0, slots=0):
@@ -280,7 +280,7 @@ def tc_conv2_plan(kind, KD, KH, stride, cin, cout, mode, D, H, W, fold, lateral=
     return plan
 
 
-def tc_conv2_fuse_lateral(on=False):
+def tc_conv2_fuse_lateral(on=True):
     global _FUSE_LAT
     _FUSE_LAT = bool(on)
     _check(lib().enerf_tc_conv2_fuse_lateral(int(bool(on))), "enerf_tc_conv2_fuse_lateral", launches=0)

@@ -541,9 +541,11 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
 }
 
 // ---- host side ------------------------------------------------------------------------------------
-// FeatureNet: lat0 (1x1 conv + bilinear x2 + add) computed inside smooth0's producer warps.  OFF by default: measured on the
-// B200 the computing producer is the bottleneck (smooth0 304 us fused vs 84 + 58 us for the two kernels, profiles/r2_frame_ab.md)
-static int g_fuse_lateral = 0;   // (second version of the producer -- sources staged by TMA, taps from shared memory -- to be re-measured)
+// FeatureNet: lat0 (1x1 conv + bilinear x2 + add) computed inside smooth0's producer warps.  First version (taps gathered from
+// global memory by the producer threads): the producer was the bottleneck, 304 us against 84 + 58 us for the two kernels.
+// Second version (conv0 / feat1_pre source tiles staged by TMA, taps and the 1x1 from shared memory): feature_net 0.361 -> 0.335 ms,
+// frame 1.130 -> 1.114 ms, bit-identical features (profiles/r2_frame_ab.md) -> on by default.
+static int g_fuse_lateral = 1;
 static int g_impl = 0;          // 0 auto (every eligible layer incl. stride 2), 1 force tc_conv.cu's kernel, 2 = 0, 3 auto without the stride-2 layers
 static bool stride2_enabled() { return g_impl != 3; }
 // One issuing warp sustains one M=128,K=8 MMA per ~91 cycles, the tensor pipe takes one per ~46 (profiles/r2_mma_bench2.md):

@@ -282,9 +282,9 @@ ENERF_API int enerf_tc_conv2_tune(int impl, int nmma, int ctas_per_sm, int tz, i
  * layout documented at the definition.  Returns ENERF_EUNSUPPORTED when the layer stays on csrc/tc_conv.cu. */
 ENERF_API int enerf_tc_conv2_plan(int kind, int KD, int KH, int stride, int cin, int cout, int mode, int D, int H, int W, int fold, int lateral,
                                   int n_sm, int* out);
-/* Diagnostic: 1 = enerf_feature_net computes lat0 (1x1 lateral + bilinear x2 + add, feature_net.py:31-35) inside
- * smooth0's producer warps on the tensor-core path; 0 (default: the computing producer measured slower) = separate lateral
- * kernel + plain smooth0 (bit-identical features). */
+/* Diagnostic: 1 (default) = enerf_feature_net computes lat0 (1x1 lateral + bilinear x2 + add, feature_net.py:31-35) inside
+ * smooth0's producer warps on the tensor-core path (source tiles staged by TMA; the 126 MB 32-channel map is never written);
+ * 0 = separate lateral kernel + plain smooth0 (bit-identical features). */
 ENERF_API int enerf_tc_conv2_fuse_lateral(int on);
 
 /* Diagnostic: when buf != NULL, CTA (0,0,0) of every later enerf_tc_conv-family launch writes 64

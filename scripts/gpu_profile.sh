@@ -3,11 +3,12 @@
 set +e
 L=${LAUNCHES_PER_FORWARD:-42}
 SKIP=$(( L * 5 ))     # launch-count probe + 3 warm-up steps + 1 step of slack (eager, one frame in flight)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c $(( L * 2 )) --csv --log-file gpurun_out/r2_launches.csv \
+# (only this library's kernels: the first forward also runs ~330 ATen launches of the one-off weight packing)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:"enerf::" -s $SKIP -c $(( L * 2 )) --csv --log-file gpurun_out/r2_launches.csv \
   python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extras --graph 0 --inflight 1 > gpurun_out/r2_launches_bench.json 2> gpurun_out/r2_launches_bench.err
 echo "launch list rc=$?"
 timeout 1500 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-  -k regex:"render_rays_ws|render_rays_tc|tc_conv2_kernel|tc_conv_kernel|cost_volume_kernel|lateral_upadd" -s $SKIP -c 36 -o gpurun_out/r2_prof \
+  -k regex:"enerf::" -s $SKIP -c $L -o gpurun_out/r2_prof \
   python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extras --graph 0 --inflight 1 > gpurun_out/r2_prof_bench.json 2> gpurun_out/r2_prof_bench.err
 echo "full capture rc=$?"
 ENERF_B200_OVERLAP=0 timeout 500 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_sanitizer_memcheck.log 2>&1

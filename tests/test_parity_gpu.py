@@ -297,7 +297,7 @@ def test_feature_net_fused_lateral_is_bit_identical(H, W, S):
             outs[name] = (f0, f1, f2)
     finally:
         capi.tc_conv2_tune()
-        capi.tc_conv2_fuse_lateral(False)
+        capi.tc_conv2_fuse_lateral(True)
     for name in ("v2", "v2_fused"):
         for lvl in range(3):
             assert not torch.isnan(outs[name][lvl]).any(), (name, lvl)

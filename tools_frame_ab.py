@@ -16,11 +16,11 @@ from enerf_b200.pipeline import GraphedNetwork  # noqa: E402
 
 CONFIGS = [
     ("conv v1 | rays v1 (round-1 kernels)", dict(impl=1), False, 1),
-    ("conv v2 2cta nmma2 | rays v1 (shipped default)", dict(impl=0, nmma=2, ctas_per_sm=2), False, 1),
+    ("conv v2 2cta nmma2, lat0 fused | rays v1 (shipped default)", dict(impl=0, nmma=2, ctas_per_sm=2), True, 1),
+    ("conv v2 2cta nmma2, lat0 separate | rays v1", dict(impl=0, nmma=2, ctas_per_sm=2), False, 1),
     ("conv v2 2cta nmma2, stride-2 layers on v1 | rays v1", dict(impl=3, nmma=2, ctas_per_sm=2), False, 1),
     ("conv v2 2cta nmma2 | rays ws", dict(impl=0, nmma=2, ctas_per_sm=2), False, 2),
     ("conv v2 1cta nmma2 | rays v1", dict(impl=0, nmma=2, ctas_per_sm=1), False, 1),
-    ("conv v2 2cta nmma2 fused lat0 | rays v1", dict(impl=0, nmma=2, ctas_per_sm=2), True, 1),
 ]
 
 
@@ -92,7 +92,7 @@ def main():
         out.append(rec)
         print(json.dumps(rec), flush=True)
     capi.tc_conv2_tune()
-    capi.tc_conv2_fuse_lateral(False)
+    capi.tc_conv2_fuse_lateral(True)
     capi.render_rays_tc_select(0)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/frame_ab.json", "w"), indent=1)
