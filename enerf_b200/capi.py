@@ -66,6 +66,7 @@ _SIGS = {
     "enerf_tc_selftest": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "enerf_tc_swz_selftest": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "enerf_tc_mma_bench2": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "enerf_tc_ldtm_bench": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp]),
     "enerf_tma_box_bench": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
@@ -300,6 +301,13 @@ def tc_mma_bench2(layout, N, n_mma, n_issuers, ksteps=1, grid=1, pad_bytes=0):
     """Returns the (grid, 4) int64 tensor of per-issuer elapsed ns."""
     out = torch.zeros(grid * 4, dtype=torch.int64, device="cuda")
     _check(lib().enerf_tc_mma_bench2(layout, N, n_mma, n_issuers, ksteps, grid, pad_bytes, out.data_ptr(), stream()), "enerf_tc_mma_bench2")
+    torch.cuda.synchronize()
+    return out.view(grid, 4).cpu()
+
+
+def tc_ldtm_bench(mode, N, n_mma, n_ld, cols, grid=148):
+    out = torch.zeros(grid * 4, dtype=torch.int64, device="cuda")
+    _check(lib().enerf_tc_ldtm_bench(mode, N, n_mma, n_ld, cols, grid, out.data_ptr(), stream()), "enerf_tc_ldtm_bench")
     torch.cuda.synchronize()
     return out.view(grid, 4).cpu()
 

@@ -212,3 +212,71 @@ extern "C" int enerf_tc_mma_bench2(int layout, int N, int n_mma, int n_issuers, 
   ENERF_CHECK_LAUNCH("tc_mma_bench2");
   return ENERF_OK;
 }
+
+// ---- enerf_tc_ldtm_bench: what does a TMEM read cost while the tensor pipe is busy? -----------------------------------------
+// One CTA per SM.  Warp 0 (optionally) issues `n_mma` MMAs back to back into accumulator columns [0, N); warps 4-7 meanwhile run
+// `n_ld` iterations of { tcgen05.ld.32x32b.x`cols` of columns [256, 256+cols) ; tcgen05.wait::ld } and report their elapsed ns.
+// mode 0: no MMA traffic; 1: MMA traffic from warp 0; 2: MMA traffic from warps 0 and 1 (two accumulators).
+namespace enerf {
+__global__ void __launch_bounds__(256) tc_ldtm_bench_kernel(int mode, int N, int n_mma, int n_ld, int cols, unsigned long long* out_ns) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int go;
+  const int t = threadIdx.x, warp = t >> 5;
+  for (int e = t; e < 64 * 1024 / 4; e += 256) reinterpret_cast<float*>(sm)[e] = 1.0f;
+  if (t == 0) {
+    tc::mbar_init(&bar[0], 1);
+    tc::mbar_init(&bar[1], 1);
+    tc::fence_mbar_init();
+    go = 0;
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::fence_proxy_async();
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (warp < 2 && mode >= 1 + warp) {
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t a = tc::smem_u32(sm) + (uint32_t)warp * 16384u, b = tc::smem_u32(sm) + 49152u + (uint32_t)warp * 4096u;
+    const uint64_t ad = tc::smem_desc(a, 2048u, 128u), bd = tc::smem_desc(b, (uint32_t)N * 16u, 128u);
+    const uint32_t idesc = tc::idesc_tf32(128, N);
+    for (int i = 0; i < n_mma; ++i) tc::mma_tf32_elect(tm + (uint32_t)(warp * 128), ad + (uint32_t)((i % 9) * 16), bd, idesc, 1u);
+    tc::mma_commit_elect(&bar[warp]);
+    tc::mbar_wait(&bar[warp], 0);
+    __syncwarp();
+  } else if (warp >= 4) {
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256u;
+    float acc = 0.f;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    for (int i = 0; i < n_ld; ++i) {
+      float v[32];
+      if (cols == 32) tc::tmem_ld32(trow, v);
+      else if (cols == 16) tc::tmem_ld16(trow, v);
+      else tc::tmem_ld8(trow, v);
+      tc::tmem_ld_wait();
+      acc += v[0];
+    }
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    if ((t & 31) == 0) out_ns[blockIdx.x * 4 + (warp & 3)] = t1 - t0;
+    if (acc == 123.f) out_ns[0] = 0;
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
+}
+}  // namespace enerf
+
+extern "C" int enerf_tc_ldtm_bench(int mode, int N, int n_mma, int n_ld, int cols, int grid, unsigned long long* out_ns, void* stream) {
+  using namespace enerf;
+  ENERF_REQUIRE(out_ns && mode >= 0 && mode <= 2 && N >= 16 && N <= 128 && N % 16 == 0 && (cols == 8 || cols == 16 || cols == 32) && grid >= 1, ENERF_EINVAL,
+                "tc_ldtm_bench: bad args");
+  const size_t smem = 64 * 1024 + 1024 + 120 * 1024;      // one CTA per SM
+  cudaError_t e = cudaFuncSetAttribute(tc_ldtm_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_ldtm_bench: %s", cudaGetErrorString(e));
+  tc_ldtm_bench_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(mode, N, n_mma, n_ld, cols, out_ns);
+  ENERF_CHECK_LAUNCH("tc_ldtm_bench");
+  return ENERF_OK;
+}

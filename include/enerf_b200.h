@@ -322,6 +322,9 @@ ENERF_API int enerf_tc_swz_selftest(const float* A, int rows, int Kf, const floa
  * dynamic shared memory set the co-residency); out_ns[cta*4 + warp] = that issuer's elapsed ns. */
 ENERF_API int enerf_tc_mma_bench2(int layout, int N, int n_mma, int n_issuers, int ksteps, int grid, int pad_bytes, unsigned long long* out_ns,
                                   void* stream);
+/* Diagnostic: cost of a TMEM read (tcgen05.ld.32x32b.x{8,16,32} + wait::ld, n_ld iterations by warps 4-7) while the tensor
+ * pipe is idle (mode 0) or fed with n_mma back-to-back MMAs by one (1) or two (2) issuing warps.  out_ns[cta*4 + warp]. */
+ENERF_API int enerf_tc_ldtm_bench(int mode, int N, int n_mma, int n_ld, int cols, int grid, unsigned long long* out_ns, void* stream);
 ENERF_API int enerf_tma_box_bench(const float* x, int D, int H, int W, int C, int tx, int ty, int tz, int depth, int iters, int grid,
                                   float* sink, void* stream);
 
