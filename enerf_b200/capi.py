@@ -60,6 +60,7 @@ _SIGS = {
     "enerf_tc_conv_tune": (_i, [_i, _i, _i]),
     "enerf_tc_conv2_tune": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "enerf_tc_conv2_fuse_lateral": (_i, [_i]),
+    "enerf_tc_conv2_debug": (_i, [_vp]),
     "enerf_tc_conv2_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_i)]),
     "enerf_tc_mma_bench": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "enerf_render_rays_debug": (_i, [_vp]),
@@ -279,6 +280,11 @@ def tc_conv2_plan(kind, KD, KH, stride, cin, cout, mode, D, H, W, fold, lateral=
     plan = {k: out[i] for i, k in enumerate(PLAN_FIELDS)}
     plan["tap_off"] = [out[40 + i] for i in range(plan["n_taps"])]
     return plan
+
+
+def tc_conv2_debug(buf):
+    """buf: int64 CUDA tensor of 3*16*8 elements (or None to switch the stamps off)."""
+    _check(lib().enerf_tc_conv2_debug(buf.data_ptr() if buf is not None else None), "enerf_tc_conv2_debug", launches=0)
 
 
 def tc_conv2_fuse_lateral(on=True):

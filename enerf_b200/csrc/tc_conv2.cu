@@ -58,7 +58,19 @@ struct TcConv2Params {
   // [f1 tile (FH x FW px x 128 B, SWIZZLE_128B)]
   int FW, FH;
   uint32_t src_slot_bytes, src_f1_off, src_bytes;   // slot stride, offset of the f1 tile inside a slot, bytes per slot's two boxes
+  unsigned long long* dbg;                           // optional %globaltimer stamps of CTA 0 (enerf_tc_conv2_debug): [role 0..2][tile 0..15][8]
 };
+
+__device__ __forceinline__ unsigned long long gtime2() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// role 0 = producer (lane 0), 1 = MMA warp 0 (lane 0), 2 = epilogue (row 0)
+#define C2_STAMP(role_, tile_, i_)                                                                  \
+  do {                                                                                              \
+    if (dbg && (tile_) < 16) dbg[((role_) * 16 + (tile_)) * 8 + (i_)] = gtime2();                   \
+  } while (0)
 
 __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
@@ -219,13 +231,16 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
       tc::mbar_expect_tx(&w_bar, P.w_bytes);
       tc::tma_load_1d(w_s, P.wpack, P.w_bytes, &w_bar);
     }
-    int it = 0;
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    int it = 0, tcount = 0;
+    unsigned long long* dbg = (P.dbg && blockIdx.x == 0 && lane == 0) ? P.dbg : nullptr;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tcount) {
       const int bx = tile % P.nx, by = (tile / P.nx) % P.ny, bz = tile / (P.nx * P.ny);
       const int x0 = bx * P.TX - P.ox, y0 = by * P.TY - P.oy, z0 = bz * P.TZ - P.oz;
+      C2_STAMP(0, tcount, 0);
       for (int kb = 0; kb < P.n_kb; ++kb, ++it) {
         const int slot = it % P.n_slots;
         tc::mbar_wait(&empty_bar[slot], (uint32_t)(((it / P.n_slots) & 1) ^ 1));
+        if (kb == 0) C2_STAMP(0, tcount, 1);       // first slot free
         if (lane == 0) {
           tc::mbar_expect_tx(&full_bar[slot], P.box_bytes * (uint32_t)P.n_phases);
           const uint32_t dst = tc::smem_u32(ring + (size_t)slot * P.slot_bytes);
@@ -236,6 +251,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
         }
         __syncwarp();
       }
+      C2_STAMP(0, tcount, 2);                       // boxes issued
     }
   } else if (warp < NP + NMMA) {
     // ============================== MMA issue (converged warp, one elected lane issues) ==============================
@@ -248,15 +264,19 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
     const int ksteps = P.kbc / 8;
     tc::mbar_wait(&w_bar, 0);
     int it = 0, ti = 0;
+    unsigned long long* dbg = (P.dbg && blockIdx.x == 0 && mw == 0 && lane == 0) ? P.dbg : nullptr;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++ti) {
       const int acc = ti % P.n_acc;
+      C2_STAMP(1, ti, 0);
       tc::mbar_wait(&acce_bar[acc], (uint32_t)(((ti / P.n_acc) & 1) ^ 1));      // the epilogue has drained this accumulator
       tc::tc_fence_after_sync();
+      C2_STAMP(1, ti, 1);                           // accumulator free
       const uint32_t td0 = tmem_u + (uint32_t)(acc * P.n_mt * P.N);
       for (int kb = 0; kb < P.n_kb; ++kb, ++it) {
         const int slot = it % P.n_slots;
         tc::mbar_wait(&full_bar[slot], (uint32_t)((it / P.n_slots) & 1));
         tc::tc_fence_after_sync();
+        if (kb == 0) C2_STAMP(1, ti, 2);            // first K-block landed
         const uint32_t a0 = tc::smem_u32(ring + (size_t)slot * P.slot_bytes) >> 4;
         for (int m = mw; m < P.n_mt; m += NMMA) {
           const uint32_t td = td0 + (uint32_t)(m * P.N);
@@ -273,6 +293,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
         if (kb + 1 == P.n_kb) tc::mma_commit_elect(&accf_bar[acc]);
         __syncwarp();
       }
+      C2_STAMP(1, ti, 3);                           // all MMAs of the tile issued
     }
   } else {
     // ============================== epilogue: 128 threads = 128 accumulator rows ==============================
@@ -285,8 +306,11 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
       const int acc = ti % P.n_acc;
       const int bx = tile % P.nx, by = (tile / P.nx) % P.ny, bz = tile / (P.nx * P.ny);
       const int x0 = bx * P.TX, y0 = by * P.TY, z0 = bz * P.TZ;
+      unsigned long long* dbg = (P.dbg && blockIdx.x == 0 && r == 0) ? P.dbg : nullptr;
+      C2_STAMP(2, ti, 0);
       tc::mbar_wait(&accf_bar[acc], (uint32_t)((ti / P.n_acc) & 1));
       tc::tc_fence_after_sync();
+      C2_STAMP(2, ti, 1);                           // accumulator full (all MMAs of the tile complete)
       const uint32_t trow = trow0 + (uint32_t)(acc * P.n_mt * P.N);
       float* xch = xch0 + (size_t)(ti & 1) * (P.xch_bytes / 8);      // [n_mt*4 + 1][2 rows][N], double buffered
       // Measured (profiles/r2_conv2_sweep.md): a tcgen05.ld + wait::ld issued while the MMA warps keep the tensor pipe busy
@@ -315,6 +339,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
             if (m + 1 == P.n_mt) {       // the last TMEM read of this accumulator: hand it back to the MMA warps
               tc::tc_fence_before_sync();
               mbar_arrive1(&acce_bar[acc]);
+              C2_STAMP(2, ti, 2);      // accumulator released
             }
             if (lane < 2) {
               float4* d = reinterpret_cast<float4*>(xch + ((size_t)((m * 4 + g) * 2 + lane)) * NF);
@@ -396,6 +421,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
           if (last) {
             tc::tc_fence_before_sync();
             mbar_arrive1(&acce_bar[acc]);
+            C2_STAMP(2, ti, 2);        // accumulator released
           }
         };
         if (P.cout == 8) {
@@ -447,6 +473,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
             if (last) {
               tc::tc_fence_before_sync();
               mbar_arrive1(&acce_bar[acc]);
+              C2_STAMP(2, ti, 2);      // accumulator released
             }
           };
           auto store8 = [&](const float* v, float* dst, const float* bias8) {
@@ -533,6 +560,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
           }
         }
       }
+      C2_STAMP(2, ti, 3);              // outputs of the tile stored
     }
   }
   tc::tc_fence_before_sync();
@@ -552,6 +580,7 @@ static bool stride2_enabled() { return g_impl != 3; }
 // two issuing warps x two persistent CTAs per SM keep it fed (per-layer A/B: profiles/r2_conv2_sweep.md).
 static int g_nmma = 2;          // MMA-issuing warps per CTA (1 | 2)
 static int g_ctas_per_sm = 2;   // persistent CTAs per SM (1 | 2)
+static unsigned long long* g_conv2_dbg = nullptr;
 static int g_tune2_tz = 0, g_tune2_ty = 0, g_tune2_fold = -1, g_tune2_kbc = 0, g_tune2_slots = 0;
 
 int tc_conv2_impl() { return g_impl; }
@@ -726,6 +755,7 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
   P.out_cstride = out_cstride, P.out_coff = out_coff;
   P.wpack = wpack, P.bias = bias, P.skip = skip, P.out = out, P.out2 = out2;
   P.lat_in = lat ? lat->lat_in : nullptr, P.lat_w = lat ? lat->lat_w : nullptr, P.lat_b = lat ? lat->lat_b : nullptr, P.up_in = lat ? lat->up_in : nullptr;
+  P.dbg = g_conv2_dbg;
 
   // tensor map of the input: channels-last (D,H,W,C) fp32 -> dims {C, W, H, D}, box {kbc, IX, IY, IZ}
   CUtensorMap map;
@@ -836,6 +866,14 @@ extern "C" int enerf_tc_conv2_plan(int kind, int KD, int KH, int stride, int cin
                      (int)P.w_bytes, (int)P.xch_bytes, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = 0; i < 40; ++i) out[i] = v[i];
   for (int i = 0; i < 27; ++i) out[40 + i] = i < n_taps ? P.tap_off[i] : 0;
+  return ENERF_OK;
+}
+
+// Diagnostic: when buf != NULL, CTA 0 of every later tc_conv2 launch writes %globaltimer stamps (ns) into buf (device memory,
+// 3 roles x 16 tiles x 8 u64): role 0 producer {tile start, first slot free, boxes issued}, 1 MMA warp 0 {start, accumulator
+// free, first K-block landed, MMAs issued}, 2 epilogue row 0 {start, accumulator full, accumulator released, outputs stored}.
+extern "C" int enerf_tc_conv2_debug(unsigned long long* buf) {
+  enerf::g_conv2_dbg = buf;
   return ENERF_OK;
 }
 

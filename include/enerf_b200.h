@@ -277,6 +277,9 @@ ENERF_API int enerf_render_rays_tc_select(int impl);
  * nmma = MMA-issuing warps per CTA (1|2, 0 = default 2); ctas_per_sm (1|2, 0 = default 2);
  * tz, ty, kbc (8|16|32), slots: forced tile / K-block width / ring depth, 0 = built-in choice. */
 ENERF_API int enerf_tc_conv2_tune(int impl, int nmma, int ctas_per_sm, int tz, int ty, int kbc, int slots);
+/* Diagnostic: in-kernel timeline of csrc/tc_conv2.cu (CTA 0, first 16 tiles): buf = 3 x 16 x 8 u64 of %globaltimer ns
+ * (roles producer / MMA warp 0 / epilogue row 0; layout at the definition); NULL switches it off. */
+ENERF_API int enerf_tc_conv2_debug(unsigned long long* buf);
 /* The launch geometry csrc/tc_conv2.cu would use for a layer ((D,H,W) = its row grid) on a device with n_sm SMs, computed
  * without touching a GPU, so the CPU test suite can emulate the kernel from it (tests/test_host_cpu.py).  out: 67 ints,
  * layout documented at the definition.  Returns ENERF_EUNSUPPORTED when the layer stays on csrc/tc_conv.cu. */
