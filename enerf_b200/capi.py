@@ -58,6 +58,7 @@ _SIGS = {
     "enerf_tc_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "enerf_tc_conv_debug": (_i, [_vp]),
     "enerf_tc_conv_tune": (_i, [_i, _i, _i]),
+    "enerf_tc_conv_fold_rule": (_i, [_i]),
     "enerf_tc_conv2_tune": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "enerf_tc_conv2_fuse_lateral": (_i, [_i]),
     "enerf_tc_conv2_debug": (_i, [_vp]),
@@ -258,6 +259,14 @@ def composite_layers(raw, z, Hr, Wr, n_fg_layers, ns_fg, ns_bg, boxes, rgb, dept
 
 def tc_conv_tune(tz=0, ty=0, fold=-1):
     _check(lib().enerf_tc_conv_tune(int(tz), int(ty), int(fold)), "enerf_tc_conv_tune", launches=0)
+
+
+def tc_conv_fold_rule(level=2):
+    """Select which layers fold their kx taps into N, in the library AND in packing.py (weights packed before the call must be
+    re-packed: Network.invalidate_packed())."""
+    from . import packing
+    _check(lib().enerf_tc_conv_fold_rule(int(level)), "enerf_tc_conv_fold_rule", launches=0)
+    packing.FOLD_RULE = int(level)
 
 
 _FUSE_LAT, _CONV_IMPL = True, 0     # mirrors of the library's switches, for the launch count only

@@ -242,7 +242,7 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
   if (tensor_cores && tc_conv2_fuse_lateral()) {
     TcConvLayer L{0, 1, 3, 32, 8, TC_PLAIN, 0};
     TcLateral lat{8, ws.c0, wts[16], wts[17], ws.f1};
-    rc = tc_conv2_try_launch(L, nullptr, S, H, W, wts[20], wts[21], nullptr, feat_l2, nullptr, 8, 0, false, stream, &lat);
+    rc = tc_conv2_try_launch(L, nullptr, S, H, W, wts[20], wts[21], nullptr, feat_l2, nullptr, 8, 0, tc_fold_rule(L), stream, &lat);
     if (rc == ENERF_OK) fused0 = true;
     else if (rc != 1) return rc;
   }

@@ -215,8 +215,10 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
     auto shifted = [&](float b, float c, int colb, int colc, float& b1, float& c2) {
       b1 = __shfl_down_sync(0xffffffffu, b, 1);
       c2 = __shfl_down_sync(0xffffffffu, c, 2);
-      if (lane == 31) b1 = nx[colb];
-      if (lane >= 30) c2 = nx[(lane - 30) * P.N + colc];
+      // every lane loads and the two last lanes select: a conditional load here compiles to a divergent branch region per element
+      const float nb = nx[colb], nc = nx[((lane == 31) ? P.N : 0) + colc];
+      b1 = (lane == 31) ? nb : b1;
+      c2 = (lane >= 30) ? nc : c2;
     };
     if constexpr (FOLD && MODE == TC_PLAIN) {
       const int C = P.cout;
@@ -339,6 +341,20 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
 
 // Tuning override (enerf_tc_conv_tune): tile TZ x TY and kx folding forced for every later launch.
 static int g_tune_tz = 0, g_tune_ty = 0, g_tune_fold = -1;
+// Which layers carry their three kx taps in the N dimension (the packed weights follow the same rule: packing.tc_fold_kx).
+//   level 0: stride-1 3x3x3 layers with 8 output channels and the single-channel depth head (the round-1 rule)
+//   level 1: + the feat + prob head (9 columns per kx)
+//   level 2: + stride-1 3x3 2-D layers with 8 output channels (FeatureNet conv0.1, smooth0)       [shipped]
+// Folding trades 3x fewer MMAs (the tensor pipe issues one M=128,K=8 MMA per ~46 cycles whatever N <= 32 is) for a row-shift
+// exchange in the epilogue; with the batched exchange of tc_conv2.cu it wins on every 8-channel layer (profiles/r2_conv2_sweep.md).
+static int g_fold_rule = 2;
+int tc_fold_rule_level() { return g_fold_rule; }
+bool tc_fold_rule(const TcConvLayer& L) {
+  const int stride = (L.kind == 0) ? L.stride : 1;
+  if (!(L.kind == 0 && stride == 1 && L.KH == 3)) return false;
+  if (L.KD == 3) return (L.mode == TC_PLAIN && L.cout == 8) || L.mode == TC_SINGLE || (L.mode == TC_HEAD && g_fold_rule >= 1);
+  return L.KD == 1 && L.mode == TC_PLAIN && L.cout == 8 && g_fold_rule >= 2;
+}
 
 int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias,
                    const float* skip, float* out, float* out2, int out_cstride, int out_coff, cudaStream_t stream) {
@@ -358,7 +374,7 @@ int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn
   // unfolded layer is tensor-issue bound -- 3-D layers with 8 (or 1) output channels: CostRegNet conv0
   // 101 -> 64 us / 134 -> 97 us, depth head 27 -> 21 us -- and costs 10-40 % elsewhere (3x the TMEM
   // read-out per row).  packing.tc_fold_kx() applies the same rule to the weights.
-  bool fold = (L.kind == 0 && stride == 1 && L.KH == 3 && L.KD == 3 && ((L.mode == TC_PLAIN && L.cout == 8) || L.mode == TC_SINGLE));
+  bool fold = tc_fold_rule(L);
   if (g_tune_fold == 0) fold = false;
   if (g_tune_fold == 1) fold = (L.kind == 0 && stride == 1 && L.KH == 3);
   if (tc_conv2_impl() != 1 && g_tune_tz == 0 && g_tune_ty == 0) {   // the persistent TMA-fed kernel takes the layers it supports
@@ -518,6 +534,12 @@ extern "C" int enerf_tc_conv(int kind, int KD, int KH, int stride, int cin, int 
 
 // Diagnostic / tuning: force the tile (TZ x TY positions, TX = 32) and the kx folding (0 off, 1 on where
 // applicable, -1 default) of every later tc_conv launch; tz = ty = 0 restores the built-in choice.
+extern "C" int enerf_tc_conv_fold_rule(int level) {
+  ENERF_REQUIRE(level >= 0 && level <= 2, ENERF_EINVAL, "tc_conv_fold_rule: level %d", level);
+  enerf::g_fold_rule = level;
+  return ENERF_OK;
+}
+
 extern "C" int enerf_tc_conv_tune(int tz, int ty, int fold) {
   enerf::g_tune_tz = tz, enerf::g_tune_ty = ty, enerf::g_tune_fold = fold;
   return ENERF_OK;

@@ -49,6 +49,8 @@ struct TcLateral {
 
 // tc_conv2.cu: the persistent TMA-fed kernel.  Returns ENERF_OK when it launched the layer, 1 when the layer is
 // not eligible (stride 2, weights beyond shared memory, ...) -- the caller then uses tc_conv.cu's kernel -- or an error.
+bool tc_fold_rule(const TcConvLayer& L);     // which layers fold their kx taps into N (tc_conv.cu; packing.tc_fold_kx mirrors it)
+int tc_fold_rule_level();
 int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias, const float* skip,
                         float* out, float* out2, int out_cstride, int out_coff, bool fold, cudaStream_t stream, const TcLateral* lat = nullptr);
 int tc_conv2_impl();   // 0 auto, 1 tc_conv.cu only, 2 auto + stride-2 layers

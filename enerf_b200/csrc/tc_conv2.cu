@@ -40,6 +40,7 @@ struct TcConv2Params {
   int n_slots;           // ring depth
   uint32_t slot_bytes, box_bytes, w_bytes, xch_bytes;
   int N, n_mt, n_acc;    // MMA N, 128-row M-tiles per tile, accumulator stages (1 | 2)
+  int d128z, d128y, d128x;   // halo-position step of one M-tile: 128 rows = d128z planes + d128y rows + d128x pixels
   int cout, relu, mode;
   int out_cstride, out_coff;
   uint32_t tmem_cols;
@@ -83,7 +84,7 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 template <int NTAPS, int MODE, int FOLD, int NMMA, int PROD = 0>
-__global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
+__global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)), PROD ? 1 : 2)      // two persistent CTAs per SM (one with the fused lateral)
     tc_conv2_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_c0, const __grid_constant__ CUtensorMap map_f1,
                     const TcConv2Params P) {
   constexpr int NP = PROD ? 5 : 1;      // producer warps: the TMA warp (+ 4 computing warps when the lateral is fused)
@@ -297,10 +298,24 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
     }
   } else {
     // ============================== epilogue: 128 threads = 128 accumulator rows ==============================
+    // Measured with the in-kernel stamps (profiles/r2_conv2_timeline.md): with ONE epilogue warp per scheduler the epilogue is a
+    // latency chain, not a throughput problem -- so everything tile-invariant is hoisted (the row -> (z,y,x) decomposition is
+    // advanced incrementally, no integer divisions per M-tile; the bias lives in registers), and the TMEM reads of several
+    // M-tiles share one tcgen05.wait::ld.
     const int g = warp & 3;                                   // TMEM lane group this warp may read
     const int r = g * 32 + lane;                              // row of the M-tile
     const uint32_t trow0 = tmem + ((uint32_t)(g * 32) << 16);
     const int plane = P.IY * P.IX;
+    struct RowPos { int z, y, x; };
+    const RowPos first = {r / plane, (r % plane) / P.IX, r % P.IX};                 // halo position of accumulator row r of M-tile 0
+    auto advance = [&](RowPos& p) {                                                 // ... and of the same row one M-tile on
+      p.x += P.d128x, p.y += P.d128y, p.z += P.d128z;
+      if (p.x >= P.IX) p.x -= P.IX, ++p.y;
+      if (p.y >= P.IY) p.y -= P.IY, ++p.z;
+    };
+    float bias_r[8];                                          // folded PLAIN layers (8 output channels): the bias lives in registers
+#pragma unroll
+    for (int c = 0; c < 8; ++c) bias_r[c] = (FOLD && MODE == TC_PLAIN) ? __ldg(P.bias + c) : 0.f;
     int ti = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++ti) {
       const int acc = ti % P.n_acc;
@@ -313,115 +328,143 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
       C2_STAMP(2, ti, 1);                           // accumulator full (all MMAs of the tile complete)
       const uint32_t trow = trow0 + (uint32_t)(acc * P.n_mt * P.N);
       float* xch = xch0 + (size_t)(ti & 1) * (P.xch_bytes / 8);      // [n_mt*4 + 1][2 rows][N], double buffered
-      // Measured (profiles/r2_conv2_sweep.md): a tcgen05.ld + wait::ld issued while the MMA warps keep the tensor pipe busy
-      // with the NEXT tile costs hundreds of cycles, so every M-tile is read with ONE load (as wide as its columns) and ONE wait.
-      auto position = [&](int m, size_t& pix, int& gz, int& gy, int& gx) -> bool {
-        const int q = m * 128 + r;                              // linear halo position of this thread's row
-        const int z = q / plane, rem = q - z * plane, y = rem / P.IX, x = rem - y * P.IX;
-        gz = z0 + z, gy = y0 + y, gx = x0 + x;
+      RowPos pos = first;                            // advanced once per M-tile, in order
+      auto locate = [&](const RowPos& p, size_t& pix, int& gz, int& gy, int& gx) -> bool {
+        gz = z0 + p.z, gy = y0 + p.y, gx = x0 + p.x;
         pix = ((size_t)gz * P.Hn + gy) * P.Wn + gx;
-        return (z < P.TZ) && (y < P.TY) && (x < P.TX) && (gz < P.Dn) && (gy < P.Hn) && (gx < P.Wn);
+        return (p.z < P.TZ) && (p.y < P.TY) && (p.x < P.TX) && (gz < P.Dn) && (gy < P.Hn) && (gx < P.Wn);
+      };
+      auto release_acc = [&]() {       // after the last TMEM read of this accumulator: hand it back to the MMA warps
+        tc::tc_fence_before_sync();
+        mbar_arrive1(&acce_bar[acc]);
+        C2_STAMP(2, ti, 2);            // accumulator released
+      };
+      auto emit8 = [&](const float* vv, float* dst, const float* b8) {
+        float4 o0 = make_float4(vv[0] + b8[0], vv[1] + b8[1], vv[2] + b8[2], vv[3] + b8[3]);
+        float4 o1 = make_float4(vv[4] + b8[4], vv[5] + b8[5], vv[6] + b8[6], vv[7] + b8[7]);
+        if (P.relu) {
+          o0 = make_float4(fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f));
+          o1 = make_float4(fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f));
+        }
+        reinterpret_cast<float4*>(dst)[0] = o0;
+        reinterpret_cast<float4*>(dst)[1] = o1;
+      };
+      auto store8 = [&](const float* v, float* dst, const float* bias8) {      // bias from global memory (L1 hit)
+        const float4 b0v = ldg4(bias8), b1v = ldg4(bias8 + 4);
+        const float b8[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+        emit8(v, dst, b8);
       };
       if constexpr (FOLD) {
         // columns kx*C + co (C = cout | 9 | 1): out[q] = P[q][0:C] + P[q+1][C:2C] + P[q+2][2C:3C].  Rows q+1, q+2 sit in the next
-        // lanes (shuffles); the two last lanes of a 32-row group need rows 0, 1 of the next group: those go through `xch`.
-        // The M-tiles are pipelined by one: iteration m loads tile m and publishes its rows 0, 1; after the barrier the outputs
-        // of tile m-1 are formed from the registers of iteration m-1.
-        constexpr int NF = (MODE == TC_SINGLE) ? 16 : 32;        // columns held per row (3C padded: 24 / 27 / 3)
-        const int C = (MODE == TC_PLAIN) ? P.cout : (MODE == TC_HEAD) ? 9 : 1;
-        float vp[NF];
-        for (int m = 0; m <= P.n_mt; ++m) {
-          float vc[NF];
-          if (m < P.n_mt) {
-            if constexpr (NF == 32) tc::tmem_ld32(trow + (uint32_t)(m * P.N), vc);
-            else tc::tmem_ld16(trow + (uint32_t)(m * P.N), vc);
-            tc::tmem_ld_wait();
-            if (m + 1 == P.n_mt) {       // the last TMEM read of this accumulator: hand it back to the MMA warps
-              tc::tc_fence_before_sync();
-              mbar_arrive1(&acce_bar[acc]);
-              C2_STAMP(2, ti, 2);      // accumulator released
-            }
-            if (lane < 2) {
-              float4* d = reinterpret_cast<float4*>(xch + ((size_t)((m * 4 + g) * 2 + lane)) * NF);
+        // lanes (shuffles); the two last lanes of a 32-row group need rows 0, 1 of the next group, which every warp publishes
+        // through `xch`.  A batch of NB M-tiles (+ the first of the next batch, only for its rows 0, 1) is read with ONE wait and
+        // exchanged with ONE barrier; the accumulator goes back to the MMA warps as soon as the last batch sits in registers.
+        constexpr int NC = (MODE == TC_PLAIN) ? 24 : (MODE == TC_HEAD) ? 32 : 8;   // columns read per row (3C: 24 / 27 / 3)
+        constexpr int NB = (MODE == TC_PLAIN) ? 3 : (MODE == TC_HEAD) ? 2 : 4;    // M-tiles per batch
+        const int XS = P.N;                                                        // row stride of the exchange buffer
+        auto ldrow = [&](int m, float* v) {
+          const uint32_t a = trow + (uint32_t)(m * P.N);
+          if constexpr (NC == 24) {
+            tc::tmem_ld16(a, v);
+            tc::tmem_ld8(a + 16, v + 16);
+          } else if constexpr (NC == 32) {
+            tc::tmem_ld32(a, v);
+          } else {
+            tc::tmem_ld8(a, v);
+          }
+        };
+        auto publish = [&](int m, const float* v) {      // lanes 0, 1: rows 0, 1 of this warp's 32-row group of M-tile m
+          float4* d = reinterpret_cast<float4*>(xch + ((size_t)((m * 4 + g) * 2 + lane)) * XS);
 #pragma unroll
-              for (int c4 = 0; c4 < NF / 4; ++c4) d[c4] = make_float4(vc[4 * c4], vc[4 * c4 + 1], vc[4 * c4 + 2], vc[4 * c4 + 3]);
+          for (int c4 = 0; c4 < NC / 4; ++c4) d[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        };
+        auto outputs = [&](int m, const float* v) {
+          size_t pix;
+          int gz, gy, gx;
+          const bool valid = locate(pos, pix, gz, gy, gx);
+          advance(pos);
+          // rows 0, 1 of the next 32-row group.  EVERY lane loads (uniform row 0 / lane-selected row, 16-byte vectors) and the two
+          // last lanes SELECT: the per-element `if (lane >= 30) x = smem[..]` this replaces compiled to 16 divergent
+          // branch regions per M-tile and made the fold epilogue ~1.3 us per M-tile (profiles/r2_conv2_timeline.md).
+          const float* row0 = xch + (size_t)((m * 4 + g + 1) * 2) * XS;
+          const float* rowc = row0 + ((lane == 31) ? XS : 0);            // row (lane - 30) for lanes 30, 31
+          auto ld4 = [](const float* q, float* d) {
+            const float4 t4 = *reinterpret_cast<const float4*>(q);
+            d[0] = t4.x, d[1] = t4.y, d[2] = t4.z, d[3] = t4.w;
+          };
+          if constexpr (MODE == TC_PLAIN) {      // C = 8 (the rule folds 8-channel layers only): columns [0,8) [8,16) [16,24)
+            float nb[8], nc[8], a[8];
+            ld4(row0 + 8, nb), ld4(row0 + 12, nb + 4);
+            ld4(rowc + 16, nc), ld4(rowc + 20, nc + 4);
+#pragma unroll
+            for (int jx = 0; jx < 8; ++jx) {
+              float b1 = __shfl_down_sync(0xffffffffu, v[8 + jx], 1);
+              float c2 = __shfl_down_sync(0xffffffffu, v[16 + jx], 2);
+              b1 = (lane == 31) ? nb[jx] : b1;
+              c2 = (lane >= 30) ? nc[jx] : c2;
+              a[jx] = (v[jx] + b1) + c2;
             }
+            if (valid) emit8(a, P.out + pix * P.out_cstride + P.out_coff, bias_r);
+          } else if constexpr (MODE == TC_HEAD) {   // columns kx*9 + co: 8 feat + 1 prob per kx
+            float nb[12], nc[12], rr[9];            // columns 8..19 of row 0 (9..17 used), 16..27 of the selected row (18..26 used)
+            ld4(row0 + 8, nb), ld4(row0 + 12, nb + 4), ld4(row0 + 16, nb + 8);
+            ld4(rowc + 16, nc), ld4(rowc + 20, nc + 4), ld4(rowc + 24, nc + 8);
+#pragma unroll
+            for (int jx = 0; jx < 9; ++jx) {
+              float b1 = __shfl_down_sync(0xffffffffu, v[9 + jx], 1);
+              float c2 = __shfl_down_sync(0xffffffffu, v[18 + jx], 2);
+              b1 = (lane == 31) ? nb[1 + jx] : b1;
+              c2 = (lane >= 30) ? nc[2 + jx] : c2;
+              rr[jx] = (v[jx] + b1) + c2;
+            }
+            if (valid) {
+              float4* o = reinterpret_cast<float4*>(P.out + pix * 8);
+              o[0] = make_float4(rr[0], rr[1], rr[2], rr[3]);
+              o[1] = make_float4(rr[4], rr[5], rr[6], rr[7]);
+              P.out2[pix] = rr[8];
+            }
+          } else {                                  // TC_SINGLE: columns 0, 1, 2
+            float nb[4], nc[4];
+            ld4(row0, nb), ld4(rowc, nc);
+            float b1 = __shfl_down_sync(0xffffffffu, v[1], 1);
+            float c2 = __shfl_down_sync(0xffffffffu, v[2], 2);
+            b1 = (lane == 31) ? nb[1] : b1;
+            c2 = (lane >= 30) ? nc[2] : c2;
+            if (valid) P.out[pix] = (v[0] + b1) + c2;
+          }
+        };
+        for (int m0 = 0; m0 < P.n_mt; m0 += NB) {
+          float v[NB][NC], la[NC];
+          const int nb = min(NB, P.n_mt - m0);
+          const bool look = m0 + NB < P.n_mt;        // another batch follows: fetch its first M-tile's rows 0, 1 now
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+            if (b < nb) ldrow(m0 + b, v[b]);
+          if (look) ldrow(m0 + NB, la);
+          tc::tmem_ld_wait();
+          if (!look) release_acc();
+          if (lane < 2) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+              if (b < nb && (b > 0 || m0 == 0)) publish(m0 + b, v[b]);    // (a batch's first M-tile was published as the look-ahead)
+            if (look) publish(m0 + NB, la);
           }
           epi_bar_sync();
-          if (m >= 1) {
-            const int mo = m - 1;
-            size_t pix;
-            int gz, gy, gx;
-            const bool valid = position(mo, pix, gz, gy, gx);
-            const float* nxr = xch + (size_t)((mo * 4 + g + 1) * 2) * NF;   // rows 0, 1 of the next 32-row group
-            auto shifted = [&](int colb, int colc, float& b1, float& c2) {
-              b1 = __shfl_down_sync(0xffffffffu, vp[colb], 1);
-              c2 = __shfl_down_sync(0xffffffffu, vp[colc], 2);
-              if (lane == 31) b1 = nxr[colb];
-              if (lane >= 30) c2 = nxr[(lane - 30) * NF + colc];
-            };
-            if constexpr (MODE == TC_PLAIN) {      // C = 8 (the rule folds 8-channel layers only): columns [0,8) [8,16) [16,24)
-              float a[8];
 #pragma unroll
-              for (int jx = 0; jx < 8; ++jx) {
-                float b1, c2;
-                shifted(8 + jx, 16 + jx, b1, c2);
-                a[jx] = (vp[jx] + b1) + c2;
-              }
-              if (valid) {
-                const float4 b0v = ldg4(P.bias), b1v = ldg4(P.bias + 4);
-                float4 o0 = make_float4(a[0] + b0v.x, a[1] + b0v.y, a[2] + b0v.z, a[3] + b0v.w);
-                float4 o1 = make_float4(a[4] + b1v.x, a[5] + b1v.y, a[6] + b1v.z, a[7] + b1v.w);
-                if (P.relu) {
-                  o0 = make_float4(fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f));
-                  o1 = make_float4(fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f));
-                }
-                float4* o = reinterpret_cast<float4*>(P.out + pix * P.out_cstride + P.out_coff);
-                o[0] = o0;
-                o[1] = o1;
-              }
-            } else if constexpr (MODE == TC_HEAD) {   // columns kx*9 + co: 8 feat + 1 prob per kx
-              float rr[9];
-#pragma unroll
-              for (int jx = 0; jx < 9; ++jx) {
-                float b1, c2;
-                shifted(9 + jx, 18 + jx, b1, c2);
-                rr[jx] = (vp[jx] + b1) + c2;
-              }
-              if (valid) {
-                float4* o = reinterpret_cast<float4*>(P.out + pix * 8);
-                o[0] = make_float4(rr[0], rr[1], rr[2], rr[3]);
-                o[1] = make_float4(rr[4], rr[5], rr[6], rr[7]);
-                P.out2[pix] = rr[8];
-              }
-            } else {                                  // TC_SINGLE
-              float b1, c2;
-              shifted(1, 2, b1, c2);
-              if (valid) P.out[pix] = (vp[0] + b1) + c2;
-            }
-            (void)C;
-          }
-#pragma unroll
-          for (int c = 0; c < NF; ++c) vp[c] = vc[c];
+          for (int b = 0; b < NB; ++b)
+            if (b < nb) outputs(m0 + b, v[b]);
         }
       } else if (MODE == TC_PLAIN && (P.cout == 8 || P.cout == 16)) {
         // narrow layers: the TMEM read latency is amortised over several M-tiles per wait (4 x 8 or 2 x 16 columns)
-        auto emit8 = [&](const float* vv, float* dst, const float* bias8) {
-          const float4 b0v = ldg4(bias8), b1v = ldg4(bias8 + 4);
-          float4 o0 = make_float4(vv[0] + b0v.x, vv[1] + b0v.y, vv[2] + b0v.z, vv[3] + b0v.w);
-          float4 o1 = make_float4(vv[4] + b1v.x, vv[5] + b1v.y, vv[6] + b1v.z, vv[7] + b1v.w);
-          if (P.relu) {
-            o0 = make_float4(fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f));
-            o1 = make_float4(fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f));
-          }
-          reinterpret_cast<float4*>(dst)[0] = o0;
-          reinterpret_cast<float4*>(dst)[1] = o1;
-        };
-        auto release_if = [&](bool last) {           // after the last TMEM read of this accumulator: hand it back to the MMA warps
-          if (last) {
-            tc::tc_fence_before_sync();
-            mbar_arrive1(&acce_bar[acc]);
-            C2_STAMP(2, ti, 2);        // accumulator released
+        auto put = [&](const float* vv, int nch) {
+          size_t pix;
+          int gz, gy, gx;
+          const bool valid = locate(pos, pix, gz, gy, gx);
+          advance(pos);
+          if (valid) {
+            float* dst = P.out + pix * P.out_cstride + P.out_coff;
+            store8(vv, dst, P.bias);
+            if (nch == 16) store8(vv + 8, dst + 8, P.bias + 8);
           }
         };
         if (P.cout == 8) {
@@ -433,13 +476,11 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
             if (nb > 2) tc::tmem_ld8(trow + (uint32_t)((m0 + 2) * P.N), v2);
             if (nb > 3) tc::tmem_ld8(trow + (uint32_t)((m0 + 3) * P.N), v3);
             tc::tmem_ld_wait();
-            release_if(m0 + nb == P.n_mt);
-            size_t pix;
-            int gz, gy, gx;
-            if (position(m0, pix, gz, gy, gx)) emit8(v0, P.out + pix * P.out_cstride + P.out_coff, P.bias);
-            if (nb > 1 && position(m0 + 1, pix, gz, gy, gx)) emit8(v1, P.out + pix * P.out_cstride + P.out_coff, P.bias);
-            if (nb > 2 && position(m0 + 2, pix, gz, gy, gx)) emit8(v2, P.out + pix * P.out_cstride + P.out_coff, P.bias);
-            if (nb > 3 && position(m0 + 3, pix, gz, gy, gx)) emit8(v3, P.out + pix * P.out_cstride + P.out_coff, P.bias);
+            if (m0 + nb == P.n_mt) release_acc();
+            put(v0, 8);
+            if (nb > 1) put(v1, 8);
+            if (nb > 2) put(v2, 8);
+            if (nb > 3) put(v3, 8);
           }
         } else {
           for (int m0 = 0; m0 < P.n_mt; m0 += 2) {
@@ -448,80 +489,36 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
             tc::tmem_ld16(trow + (uint32_t)(m0 * P.N), v0);
             if (nb > 1) tc::tmem_ld16(trow + (uint32_t)((m0 + 1) * P.N), v1);
             tc::tmem_ld_wait();
-            release_if(m0 + nb == P.n_mt);
-            size_t pix;
-            int gz, gy, gx;
-            if (position(m0, pix, gz, gy, gx)) {
-              float* dst = P.out + pix * P.out_cstride + P.out_coff;
-              emit8(v0, dst, P.bias);
-              emit8(v0 + 8, dst + 8, P.bias + 8);
-            }
-            if (nb > 1 && position(m0 + 1, pix, gz, gy, gx)) {
-              float* dst = P.out + pix * P.out_cstride + P.out_coff;
-              emit8(v1, dst, P.bias);
-              emit8(v1 + 8, dst + 8, P.bias + 8);
-            }
+            if (m0 + nb == P.n_mt) release_acc();
+            put(v0, 16);
+            if (nb > 1) put(v1, 16);
           }
         }
       } else {
         for (int m = 0; m < P.n_mt; ++m) {
           size_t pix;
           int gz, gy, gx;
-          const bool valid = position(m, pix, gz, gy, gx);
+          const bool valid = locate(pos, pix, gz, gy, gx);
+          advance(pos);
           const bool last = (m + 1 == P.n_mt);
-          auto release = [&]() {           // after the last TMEM read of this accumulator: hand it back to the MMA warps
-            if (last) {
-              tc::tc_fence_before_sync();
-              mbar_arrive1(&acce_bar[acc]);
-              C2_STAMP(2, ti, 2);      // accumulator released
-            }
-          };
-          auto store8 = [&](const float* v, float* dst, const float* bias8) {
-            const float4 b0v = ldg4(bias8), b1v = ldg4(bias8 + 4);
-            float4 o0 = make_float4(v[0] + b0v.x, v[1] + b0v.y, v[2] + b0v.z, v[3] + b0v.w);
-            float4 o1 = make_float4(v[4] + b1v.x, v[5] + b1v.y, v[6] + b1v.z, v[7] + b1v.w);
-            if (P.relu) {
-              o0 = make_float4(fmaxf(o0.x, 0.f), fmaxf(o0.y, 0.f), fmaxf(o0.z, 0.f), fmaxf(o0.w, 0.f));
-              o1 = make_float4(fmaxf(o1.x, 0.f), fmaxf(o1.y, 0.f), fmaxf(o1.z, 0.f), fmaxf(o1.w, 0.f));
-            }
-            reinterpret_cast<float4*>(dst)[0] = o0;
-            reinterpret_cast<float4*>(dst)[1] = o1;
-          };
-          if constexpr (MODE == TC_PLAIN) {
+          if constexpr (MODE == TC_PLAIN) {        // 32 | 64 output channels: 32 columns per load, one wait for all of them
             float* dst = P.out + pix * P.out_cstride + P.out_coff;
             const uint32_t tcol = trow + (uint32_t)(m * P.N);
-            if (P.cout == 8) {
-              float v[8];
-              tc::tmem_ld8(tcol, v);
-              tc::tmem_ld_wait();
-              release();
-              if (valid) store8(v, dst, P.bias);
-            } else if (P.cout == 16) {
-              float v[16];
-              tc::tmem_ld16(tcol, v);
-              tc::tmem_ld_wait();
-              release();
-              if (valid) {
-                store8(v, dst, P.bias);
-                store8(v + 8, dst + 8, P.bias + 8);
-              }
-            } else {                       // 32 | 64 output channels: 32 columns per load, one wait for all of them
-              float v[64];
-              tc::tmem_ld32(tcol, v);
-              if (P.cout == 64) tc::tmem_ld32(tcol + 32, v + 32);
-              tc::tmem_ld_wait();
-              release();
-              if (valid) {
+            float v[64];
+            tc::tmem_ld32(tcol, v);
+            if (P.cout == 64) tc::tmem_ld32(tcol + 32, v + 32);
+            tc::tmem_ld_wait();
+            if (last) release_acc();
+            if (valid) {
 #pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 8)
-                  if (c0 < P.cout) store8(v + c0, dst + c0, P.bias + c0);
-              }
+              for (int c0 = 0; c0 < 64; c0 += 8)
+                if (c0 < P.cout) store8(v + c0, dst + c0, P.bias + c0);
             }
           } else if constexpr (MODE == TC_HEAD) {          // feat_conv (8) + depth_conv (1), no bias
             float v[16];
             tc::tmem_ld16(trow + (uint32_t)(m * P.N), v);
             tc::tmem_ld_wait();
-            release();
+            if (last) release_acc();
             if (valid) {
               float4* o = reinterpret_cast<float4*>(P.out + pix * 8);
               o[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -532,7 +529,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
             float v[8];
             tc::tmem_ld8(trow + (uint32_t)(m * P.N), v);
             tc::tmem_ld_wait();
-            release();
+            if (last) release_acc();
             if (valid) P.out[pix] = v[0];
           } else {  // TC_DECONV: columns = parity * cout + co ; out[2b+e] = skip + (acc + bias); 64 columns per wait
             const int Ho = 2 * P.Hn, Wo = 2 * P.Wn;
@@ -541,7 +538,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)))
               tc::tmem_ld32(trow + (uint32_t)(m * P.N + cb), v);
               tc::tmem_ld32(trow + (uint32_t)(m * P.N + cb + 32), v + 32);       // N = 8 * cout is a multiple of 64
               tc::tmem_ld_wait();
-              if (cb + 64 >= P.N) release();
+              if (last && cb + 64 >= P.N) release_acc();
               if (valid) {
 #pragma unroll
                 for (int c8 = 0; c8 < 64; c8 += 8) {
@@ -592,7 +589,7 @@ bool tc_conv2_fuse_lateral() { return g_impl != 1 && g_fuse_lateral != 0; }
 static int tc_conv2_plan(const TcConvLayer& L, int Dn, int Hn, int Wn, bool fold_default, bool lat, bool has_bias, bool has_skip, int n_sm,
                          TcConv2Params& P, int& n_taps_out, bool& fold_out, int lat_cin = 8) {
   const int stride = (L.kind == 0) ? L.stride : 1;
-  if (lat && (lat_cin != 8 || fold_default)) return 1;     // instantiated: lat0 (8 channels) in front of an unfolded 3x3
+  if (lat && lat_cin != 8) return 1;     // instantiated: lat0 (8 channels) in front of the 3x3 (kx taps folded or not)
   if (lat && !(L.kind == 0 && L.KD == 1 && L.KH == 3 && L.cin == 32 && stride == 1 && L.mode == TC_PLAIN && Hn % 2 == 0 && Wn % 2 == 0))
     return 1;
   if (L.cin % 8 != 0 || L.cin > 64 || (stride != 1 && stride != 2)) return 1;
@@ -655,6 +652,7 @@ static int tc_conv2_plan(const TcConvLayer& L, int Dn, int Hn, int Wn, bool fold
     if (P.IZ * P.sz > 256 || P.IY * P.sy > 256 || P.IX * P.sx > 256) return 1;
     const int pmax = ((P.TZ - 1) * P.IY + (P.TY - 1)) * P.IX + P.TX - 1;
     P.n_mt = (pmax + (fold ? 2 : 0)) / 128 + 1;
+    P.d128z = 128 / (P.IY * P.IX), P.d128y = (128 % (P.IY * P.IX)) / P.IX, P.d128x = (128 % (P.IY * P.IX)) % P.IX;
     int max_tap_rows = 0, tap_rows[27], tap_phase[27];
     for (int i = 0; i < 27; ++i) tap_phase[i] = 0;
     if (stride == 2) {
@@ -798,27 +796,30 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
     }                                                                                                                                     \
     tc_conv2_kernel<NT, MD, FD, NM><<<grid, 32 * (4 + NM + 1), smem, stream>>>(map, map_c0, map_f1, P);                                                       \
   } while (0)
+// (kx-folded layers always run ONE MMA warp: 6 warps x 2 CTAs = 3 warps per scheduler leave 168 registers per thread for the
+//  batched fold epilogue, 7 x 2 would cap it at 128 and spill; two CTAs already give the tensor pipe its two issuing streams)
 #define TC2_DISPATCH(NT, MD, FD)             \
   do {                                       \
-    if (g_nmma >= 2) TC2_LAUNCH(NT, MD, FD, 2); \
+    if (g_nmma >= 2 && (FD) == 0) TC2_LAUNCH(NT, MD, FD, 2); \
     else TC2_LAUNCH(NT, MD, FD, 1);          \
   } while (0)
   if (lat != nullptr) {
-#define TC2_LAT(NM, PR)                                                                                                                          \
+#define TC2_LAT(NT, FD, NM, PR)                                                                                                                  \
   do {                                                                                                                                           \
     static PerDeviceSize lat_set_pd;                                                                                                             \
     size_t& lat_set = lat_set_pd.cur();                                                                                                          \
     if (smem > lat_set) {                                                                                                                        \
-      cudaError_t e = cudaFuncSetAttribute(tc_conv2_kernel<9, TC_PLAIN, 0, NM, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+      cudaError_t e = cudaFuncSetAttribute(tc_conv2_kernel<NT, TC_PLAIN, FD, NM, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
       ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv2(lateral): cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));             \
       lat_set = smem;                                                                                                                            \
     }                                                                                                                                            \
-    tc_conv2_kernel<9, TC_PLAIN, 0, NM, PR><<<grid, 32 * (4 + NM + 5), smem, stream>>>(map, map_c0, map_f1, P);                                                  \
+    tc_conv2_kernel<NT, TC_PLAIN, FD, NM, PR><<<grid, 32 * (4 + NM + 5), smem, stream>>>(map, map_c0, map_f1, P);                                \
   } while (0)
     // (lat1 -> smooth1 is NOT fused: its output feat1_pre is also lat0's up-sampling source, so it must exist in HBM anyway;
     //  the producer is written for lat_cin 8 | 16, only 8 is instantiated)
-    if (g_nmma >= 2) TC2_LAT(2, 1);
-    else TC2_LAT(1, 1);
+    if (fold) TC2_LAT(3, 1, 1, 1);
+    else if (g_nmma >= 2) TC2_LAT(9, 0, 2, 1);
+    else TC2_LAT(9, 0, 1, 1);
 #undef TC2_LAT
     ENERF_CHECK_LAUNCH("tc_conv2(lateral)");
     return ENERF_OK;

@@ -35,11 +35,20 @@ def _dev(t, device):
 TC_FEATURE_LAYERS = ("conv0.1", "conv1.0", "conv1.1", "conv2.0", "conv2.1", "toplayer", "smooth1", "smooth0")
 
 
-def tc_fold_kx(KD, KH, stride, cout, single=False):
-    """The folding rule of csrc/tc_conv.cu::tc_conv_launch: stride-1 3x3x3 layers with 8 output
-    channels, and the single-channel depth head."""
-    return KD == 3 and KH == 3 and stride == 1 and (cout == 8 or single)
+# Which layers carry their three kx taps in the MMA's N dimension; mirrors csrc/tc_conv.cu::tc_fold_rule (capi.tc_conv_fold_rule
+# sets both): 0 = stride-1 3x3x3 layers with 8 output channels + the single-channel depth head, 1 = + the feat/prob head,
+# 2 (shipped) = + stride-1 3x3 2-D layers with 8 output channels (FeatureNet conv0.1, smooth0).
+FOLD_RULE = 2
 
+
+def tc_fold_kx(KD, KH, stride, cout, single=False, head=False):
+    """The folding rule of csrc/tc_conv.cu::tc_fold_rule for a convolution (KD x KH x KH, `stride`, `cout` output channels;
+    single: the depth-only head, head: the feat + prob head)."""
+    if stride != 1 or KH != 3:
+        return False
+    if KD == 3:
+        return bool(single or (head and FOLD_RULE >= 1) or (not head and cout == 8))
+    return KD == 1 and not single and not head and cout == 8 and FOLD_RULE >= 2
 
 
 def pack_feature_net(sd, device, p="feature_net", tensor_cores=False):
@@ -47,7 +56,8 @@ def pack_feature_net(sd, device, p="feature_net", tensor_cores=False):
     tensor_cores: the layers in TC_FEATURE_LAYERS get the tcgen05 stage layout (pack_tc_conv)."""
     def lay(name, w_taps):
         if tensor_cores and name in TC_FEATURE_LAYERS:
-            return pack_tc_conv(w_taps).to(device)     # 2-D layers are never folded (tc_fold_kx)
+            fold = w_taps.shape[0] == 9 and tc_fold_kx(1, 3, 1, w_taps.shape[2])     # FeatureNet's 3x3 layers are all stride 1
+            return pack_tc_conv(w_taps, fold_kx=fold).to(device)
         return _dev(w_taps, device)
 
     out = []
@@ -80,7 +90,7 @@ def pack_cost_reg(sd, p, in_ch, deep, device, with_feat, tensor_cores=False):
         else:
             head[name] = _taps_cin_cout(sd[q + ".0.weight"].double())   # [27][8][cout]
     hw = torch.cat([head["feat_conv"], head["depth_conv"]], dim=2) if with_feat else head["depth_conv"]
-    out.append(pack_tc_conv(hw, fold_kx=tc_fold_kx(3, 3, 1, hw.shape[-1], single=not with_feat)).to(device) if tensor_cores
+    out.append(pack_tc_conv(hw, fold_kx=tc_fold_kx(3, 3, 1, hw.shape[-1], single=not with_feat, head=with_feat)).to(device) if tensor_cores
                else _dev(hw, device))
     return out
 

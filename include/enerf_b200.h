@@ -299,6 +299,12 @@ ENERF_API int enerf_tc_conv_debug(unsigned long long* buf);
  * built-in choice.  Weights must be packed for the folding in force (packing.pack_tc_conv fold_kx). */
 ENERF_API int enerf_tc_conv_tune(int tz, int ty, int fold);
 
+/* Which convolutions carry their three kx taps in the MMA's N dimension (3x fewer tcgen05.mma, a row-shift exchange in the
+ * epilogue): 0 = stride-1 3x3x3 layers with 8 output channels + the depth-only head, 1 = + the feat/prob head, 2 (default) =
+ * + stride-1 3x3 2-D layers with 8 output channels.  The packed weights must follow the same rule
+ * (enerf_b200/packing.py::FOLD_RULE; enerf_b200.capi.tc_conv_fold_rule sets both and the caller re-packs). */
+ENERF_API int enerf_tc_conv_fold_rule(int level);
+
 /* Diagnostic: like enerf_tc_conv_debug for enerf_render_rays_tc (32 x u64: 16 stamps for each of
  * the first two tiles of CTA 0). */
 ENERF_API int enerf_render_rays_debug(unsigned long long* buf);

@@ -145,8 +145,18 @@ def test_folded_tc_conv_packing_is_a_shifted_sum_of_partial_convolutions():
     cin, cout, D, H, W = 16, 8, 3, 5, 7
     w = torch.randn(cout, cin, 3, 3, 3, generator=g)
     x = torch.randn(1, cin, D, H, W, generator=g)
-    assert packing.tc_fold_kx(3, 3, 1, cout) and not packing.tc_fold_kx(3, 3, 2, cout) and not packing.tc_fold_kx(1, 3, 1, cout)
-    assert packing.tc_fold_kx(3, 3, 1, 1, single=True) and not packing.tc_fold_kx(3, 3, 1, 9)
+    assert packing.tc_fold_kx(3, 3, 1, cout) and not packing.tc_fold_kx(3, 3, 2, cout) and not packing.tc_fold_kx(3, 3, 1, 16)
+    assert packing.tc_fold_kx(3, 3, 1, 1, single=True) and not packing.tc_fold_kx(1, 3, 1, 16) and not packing.tc_fold_kx(1, 5, 2, 8)
+    rule = packing.FOLD_RULE
+    try:                                    # the rule levels (mirrors csrc/tc_conv.cu::tc_fold_rule)
+        packing.FOLD_RULE = 0
+        assert not packing.tc_fold_kx(3, 3, 1, 9, head=True) and not packing.tc_fold_kx(1, 3, 1, 8)
+        packing.FOLD_RULE = 1
+        assert packing.tc_fold_kx(3, 3, 1, 9, head=True) and not packing.tc_fold_kx(1, 3, 1, 8)
+        packing.FOLD_RULE = 2
+        assert packing.tc_fold_kx(3, 3, 1, 9, head=True) and packing.tc_fold_kx(1, 3, 1, 8)
+    finally:
+        packing.FOLD_RULE = rule
     taps = packing._taps_cin_cout(w)                                   # [27][cin][cout], taps ordered (kz,ky,kx)
     packed = packing.pack_tc_conv(taps, fold_kx=True)
     N = 32                                                             # 3 * 8 = 24 padded to 16-multiples

@@ -209,6 +209,26 @@ TC_CONV_IMPLS = {"v1": dict(impl=1), "auto": dict(impl=0), "1cta1mma": dict(impl
 @pytest.mark.parametrize("impl", list(TC_CONV_IMPLS))
 @pytest.mark.parametrize("case", TC_CONV_CASES)
 def test_tc_conv_layer(case, impl):
+    _run_tc_conv_layer(case, impl)
+
+
+@pytest.mark.parametrize("rule", [0, 1])
+@pytest.mark.parametrize("impl", ["v1", "auto"])
+@pytest.mark.parametrize("case", [c for c in TC_CONV_CASES if (c[1] == 1 and c[2] == 3 and c[4] == 8) or c[5] == 1])
+def test_tc_conv_layer_fold_rule_levels(case, impl, rule):
+    """The layers the kx-fold rule levels 1 / 2 add (feat + prob head; 3x3 2-D layers with 8 output channels) under the
+    narrower rules too (enerf_tc_conv_fold_rule; the shipped level 2 is what test_tc_conv_layer runs)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from enerf_b200 import capi
+    capi.tc_conv_fold_rule(rule)
+    try:
+        _run_tc_conv_layer(case, impl)
+    finally:
+        capi.tc_conv_fold_rule(2)
+
+
+def _run_tc_conv_layer(case, impl):
     kind, KD, KH, cin, cout, mode, relu, dims = case[:8]
     stride = case[8] if len(case) > 8 else 1
     if impl == "nos2" and stride == 1:
@@ -230,7 +250,7 @@ def test_tc_conv_layer(case, impl):
         ref = F.conv3d(x, w, b, (stride if KD > 1 else 1, stride, stride), (KD // 2, KH // 2, KH // 2))
         if relu:
             ref = F.relu(ref)
-        wp = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=packing.tc_fold_kx(KD, KH, stride, cout, single=(mode == 3))).cuda()
+        wp = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=packing.tc_fold_kx(KD, KH, stride, cout, single=(mode == 3), head=(mode == 1))).cuda()
         skip = None
     else:
         w = torch.randn(cin, cout, 3, 3, 3, generator=g) / (cin * 27 / 8) ** 0.5

@@ -61,7 +61,7 @@ def main(quick):
         skip = None
         if kind == 0:
             w = torch.randn(cout, cin, KD, KH, KH, generator=g) / (cin * KD * KH * KH) ** 0.5
-            wp = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3))).cuda()
+            wp = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3), head=(mode == 1))).cuda()
             Do, Ho, Wo = D, H, W
         else:
             w = torch.randn(cin, cout, 3, 3, 3, generator=g) / (cin * 27 / 8) ** 0.5
@@ -73,23 +73,27 @@ def main(quick):
         out2 = torch.empty(Do, Ho, Wo).cuda() if mode == 1 else None
         ref = None
         layer_variants = list(variants)
-        if kind == 0 and KD == 1 and KH == 3 and cout in (8, 16):       # kx folding for 2-D layers (off in the shipped rule): A/B it on v2
-            layer_variants += [("v2.2cta.nmma2.fold2d", dict(impl=0, _fold=True)), ("v2.1cta.nmma2.fold2d", dict(impl=0, ctas_per_sm=1, _fold=True)),
-                               ("v1.fold2d", dict(impl=1, _fold=True))]
-        if kind == 0 and packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3)):       # the folded 3-D layers, unfolded (27 taps of N = C)
+        rule2 = kind == 0 and KD == 1 and KH == 3 and cout == 8      # layers the level-2 rule folds
+        rule1 = kind == 0 and KD == 3 and mode == 1                  # ... and the level-1 rule (feat + prob head)
+        if rule2 or rule1:
+            layer_variants += [("v2.2cta.rule0", dict(impl=0, _rule=0)), ("v2.1cta.rule0", dict(impl=0, ctas_per_sm=1, _rule=0)), ("v1.rule0", dict(impl=1, _rule=0)),
+                               ("v2.1cta", dict(impl=0, ctas_per_sm=1))]
+            for tz, ty in (((1, 7), (1, 11), (1, 15)) if rule2 else ((2, 4), (2, 8), (4, 4))):
+                layer_variants.append((f"v2.2cta.t{tz}x{ty}", dict(impl=0, tz=tz, ty=ty)))
+        if kind == 0 and KD == 3 and packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3)):       # the always-folded 3-D layers, unfolded (27 taps of N = C)
             layer_variants += [("v2.2cta.nmma2.nofold", dict(impl=0, _nofold=True)), ("v1.nofold", dict(impl=1, _nofold=True))]
         for vname, kw in layer_variants:
             is3d = KD == 3 or kind == 1
             if ".t1x" in vname and is3d or (".t2x" in vname or ".t4x" in vname) and not is3d:
                 continue
             kw = dict(kw)
-            fold2d = kw.pop("_fold", False)
+            rule = kw.pop("_rule", None)
             nofold = kw.pop("_nofold", False)
             capi.tc_conv2_tune(**kw)
             wp_v = wp
-            if fold2d:
-                wp_v = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=True).cuda()
-                capi.tc_conv_tune(0, 0, 1)
+            if rule is not None:
+                capi.tc_conv_fold_rule(rule)
+                wp_v = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3), head=(mode == 1))).cuda()
             if nofold:
                 wp_v = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=False).cuda()
                 capi.tc_conv_tune(0, 0, 0)
@@ -101,13 +105,15 @@ def main(quick):
                     ref = out.clone()
                     same = True
                 else:
-                    same = bool(torch.equal(out, ref)) if not (fold2d or nofold) else float((out - ref).abs().max())
+                    same = bool(torch.equal(out, ref)) if not (rule is not None or nofold) else float((out - ref).abs().max())
             except Exception as e:  # noqa: BLE001
                 us, same = None, str(e)[:120]
                 torch.cuda.synchronize()
             finally:
-                if fold2d or nofold:
+                if nofold:
                     capi.tc_conv_tune(0, 0, -1)
+                if rule is not None:
+                    capi.tc_conv_fold_rule(2)
             results.append({"layer": name, "variant": vname, "us": us, "equal_to_v1": same})
             if us and vname in ("v1", "v2", "v2.nmma2", "v2.2cta", "v2.2cta.nmma2"):
                 totals[vname] = totals.get(vname, 0.0) + us

@@ -11,16 +11,19 @@ from enerf_b200 import capi, packing  # noqa: E402
 from tools_conv2_sweep import LAYERS  # noqa: E402
 
 WANT = ("feat.conv0.1", "feat.smooth0", "reg0.conv0", "reg1.conv0", "reg1.conv2", "reg1.head9", "reg1.conv11")
+RULE0_TOO = ("feat.conv0.1", "feat.smooth0", "reg1.head9")          # layers the level-1/2 fold rules add: also unfolded (rule 0)
 out = {}
-for name, kind, KD, KH, cin, cout, mode, relu, (D, H, W) in LAYERS:
-    if name not in WANT:
+for name, kind, KD, KH, cin, cout, mode, relu, (D, H, W), rule in [(*L, f) for L in LAYERS for f in (2, 0)]:
+    if name not in WANT or (rule == 0 and name not in RULE0_TOO):
         continue
+    capi.tc_conv_fold_rule(rule)
+    fold = kind == 0 and packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3), head=(mode == 1))
     g = torch.Generator().manual_seed(1)
     x = torch.randn(D, H, W, cin, generator=g).cuda()
     skip = None
     if kind == 0:
         w = torch.randn(cout, cin, KD, KH, KH, generator=g) / (cin * KD * KH * KH) ** 0.5
-        wp = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3))).cuda()
+        wp = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=fold).cuda()
         Do, Ho, Wo = D, H, W
     else:
         w = torch.randn(cin, cout, 3, 3, 3, generator=g) / (cin * 27 / 8) ** 0.5
@@ -36,13 +39,15 @@ for name, kind, KD, KH, cin, cout, mode, relu, (D, H, W) in LAYERS:
         capi.tc_conv(kind, KD, KH, cout, mode, relu, x, wp, bias, skip, o, o2, out_cstride=(8 if mode == 1 else cout))
         torch.cuda.synchronize()
     capi.tc_conv2_debug(None)
+    capi.tc_conv_fold_rule(2)
     t = buf.cpu().view(3, 16, 8)
     t0 = int(t[t > 0].min())
-    plan = capi.tc_conv2_plan(kind, KD, KH, 1, cin, cout, mode, D, H, W, packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3)) if kind == 0 else False)
+    plan = capi.tc_conv2_plan(kind, KD, KH, 1, cin, cout, mode, D, H, W, fold)
     rep = {"plan": {k: plan[k] for k in ("TZ", "TY", "n_mt", "kbc", "n_kb", "n_slots", "n_acc", "n_tiles", "N", "n_taps")},
            "producer": [[int(v) - t0 if v else None for v in t[0, k, :3]] for k in range(8)],
            "mma": [[int(v) - t0 if v else None for v in t[1, k, :4]] for k in range(8)],
            "epilogue": [[int(v) - t0 if v else None for v in t[2, k, :4]] for k in range(8)]}
+    name = name + (".rule0" if rule == 0 else "")
     out[name] = rep
     print("==", name, rep["plan"])
     print("   producer [start, slot free, boxes issued]      ", rep["producer"][:6])

@@ -1,6 +1,6 @@
 """A/B of the kernel choices at the headline frame (512x640, S=3, 48+8): per-stage CUDA-event times (eager, profiled),
 single-frame latency (one CUDA graph) and the 4-frames-in-flight throughput, for combinations of
-  conv: csrc/tc_conv.cu (v1) | csrc/tc_conv2.cu with {1,2} CTAs per SM x {1,2} MMA-issuing warps, lat0 fused or not
+  conv: csrc/tc_conv.cu (v1) | csrc/tc_conv2.cu, lat0 fused or not, kx-fold rule level 0 / 1 / 2
   rays: csrc/render_rays_tc.cuh (single role) | csrc/render_rays_ws.cu (warp specialised)
 Writes gpurun_out/frame_ab.json."""
 import json
@@ -15,12 +15,13 @@ from enerf_b200 import capi  # noqa: E402
 from enerf_b200.pipeline import GraphedNetwork  # noqa: E402
 
 CONFIGS = [
-    ("conv v1 | rays v1 (round-1 kernels)", dict(impl=1), False, 1),
-    ("conv v2 2cta nmma2, lat0 fused | rays v1 (shipped default)", dict(impl=0, nmma=2, ctas_per_sm=2), True, 1),
-    ("conv v2 2cta nmma2, lat0 separate | rays v1", dict(impl=0, nmma=2, ctas_per_sm=2), False, 1),
-    ("conv v2 2cta nmma2, stride-2 layers on v1 | rays v1", dict(impl=3, nmma=2, ctas_per_sm=2), False, 1),
-    ("conv v2 2cta nmma2 | rays ws", dict(impl=0, nmma=2, ctas_per_sm=2), False, 2),
-    ("conv v2 1cta nmma2 | rays v1", dict(impl=0, nmma=2, ctas_per_sm=1), False, 1),
+    # name, tc_conv2_tune kwargs, lat0 fused, ray kernel, fold rule level
+    ("conv v1 | rays v1 | fold rule 0 (round-1 kernels)", dict(impl=1), False, 1, 0),
+    ("conv v2 2cta, lat0 fused, fold rule 2 | rays v1 (shipped default)", dict(impl=0, nmma=2, ctas_per_sm=2), True, 1, 2),
+    ("conv v2 2cta, lat0 fused, fold rule 1 | rays v1", dict(impl=0, nmma=2, ctas_per_sm=2), True, 1, 1),
+    ("conv v2 2cta, lat0 fused, fold rule 0 | rays v1", dict(impl=0, nmma=2, ctas_per_sm=2), True, 1, 0),
+    ("conv v2 2cta, lat0 separate, fold rule 2 | rays v1", dict(impl=0, nmma=2, ctas_per_sm=2), False, 1, 2),
+    ("conv v2 2cta, lat0 fused, fold rule 2 | rays ws", dict(impl=0, nmma=2, ctas_per_sm=2), True, 2, 2),
 ]
 
 
@@ -34,8 +35,10 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     out = []
     ref_rgb = None
-    for name, conv_kw, fuse, ray_impl in CONFIGS:
+    for name, conv_kw, fuse, ray_impl, rule in CONFIGS:
         capi.tc_conv2_tune(**conv_kw)
+        capi.tc_conv_fold_rule(rule)
+        net.invalidate_packed()
         capi.tc_conv2_fuse_lateral(fuse)
         capi.render_rays_tc_select(ray_impl)
         with torch.no_grad():
@@ -92,6 +95,7 @@ def main():
         out.append(rec)
         print(json.dumps(rec), flush=True)
     capi.tc_conv2_tune()
+    capi.tc_conv_fold_rule(2)
     capi.tc_conv2_fuse_lateral(True)
     capi.render_rays_tc_select(0)
     os.makedirs("gpurun_out", exist_ok=True)
