@@ -62,6 +62,7 @@ _SIGS = {
     "enerf_tc_conv2_tune": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "enerf_tc_conv2_fuse_lateral": (_i, [_i]),
     "enerf_tc_conv2_debug": (_i, [_vp]),
+    "enerf_tc_conv2_debug_lateral": (_i, [_vp]),
     "enerf_tc_conv2_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_i)]),
     "enerf_tc_mma_bench": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "enerf_render_rays_debug": (_i, [_vp]),
@@ -296,10 +297,16 @@ def tc_conv2_debug(buf):
     _check(lib().enerf_tc_conv2_debug(buf.data_ptr() if buf is not None else None), "enerf_tc_conv2_debug", launches=0)
 
 
+def tc_conv2_debug_lateral(buf):
+    """buf: int64 CUDA tensor of 3*16*8 elements (or None to switch the stamps off)."""
+    _check(lib().enerf_tc_conv2_debug_lateral(buf.data_ptr() if buf is not None else None), "enerf_tc_conv2_debug_lateral", launches=0)
+
+
 def tc_conv2_fuse_lateral(on=True):
+    """on: False | True | 4 | 6 | 8 (fused, with that many computing producer warps; True = the default, 6)."""
     global _FUSE_LAT
     _FUSE_LAT = bool(on)
-    _check(lib().enerf_tc_conv2_fuse_lateral(int(bool(on))), "enerf_tc_conv2_fuse_lateral", launches=0)
+    _check(lib().enerf_tc_conv2_fuse_lateral(int(on)), "enerf_tc_conv2_fuse_lateral", launches=0)
 
 
 def tc_selftest(A, B, D):

@@ -344,7 +344,8 @@ static int g_tune_tz = 0, g_tune_ty = 0, g_tune_fold = -1;
 // Which layers carry their three kx taps in the N dimension (the packed weights follow the same rule: packing.tc_fold_kx).
 //   level 0: stride-1 3x3x3 layers with 8 output channels and the single-channel depth head (the round-1 rule)
 //   level 1: + the feat + prob head (9 columns per kx)
-//   level 2: + stride-1 3x3 2-D layers with 8 output channels (FeatureNet conv0.1, smooth0)       [shipped]
+//   level 2: + stride-1 3x3 2-D layers with 8 output channels and >= 16 input channels (FeatureNet smooth0; conv0.1 with its
+//            single K-step is faster unfolded: 21 vs 25 us)                                         [shipped]
 // Folding trades 3x fewer MMAs (the tensor pipe issues one M=128,K=8 MMA per ~46 cycles whatever N <= 32 is) for a row-shift
 // exchange in the epilogue; with the batched exchange of tc_conv2.cu it wins on every 8-channel layer (profiles/r2_conv2_sweep.md).
 static int g_fold_rule = 2;
@@ -353,7 +354,7 @@ bool tc_fold_rule(const TcConvLayer& L) {
   const int stride = (L.kind == 0) ? L.stride : 1;
   if (!(L.kind == 0 && stride == 1 && L.KH == 3)) return false;
   if (L.KD == 3) return (L.mode == TC_PLAIN && L.cout == 8) || L.mode == TC_SINGLE || (L.mode == TC_HEAD && g_fold_rule >= 1);
-  return L.KD == 1 && L.mode == TC_PLAIN && L.cout == 8 && g_fold_rule >= 2;
+  return L.KD == 1 && L.mode == TC_PLAIN && L.cout == 8 && L.cin >= 16 && g_fold_rule >= 2;
 }
 
 int tc_conv_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, int Wn, const float* wpack, const float* bias,

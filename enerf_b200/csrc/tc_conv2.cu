@@ -49,7 +49,7 @@ struct TcConv2Params {
   const float* skip;
   float* out;
   float* out2;
-  // PROD = 1 (FeatureNet smooth0 with the lateral fused in): the 32-channel input tile is COMPUTED by four producer
+  // PROD > 0 (FeatureNet smooth0 with the lateral fused in): the 32-channel input tile is COMPUTED by PROD producer
   // warps instead of loaded: in[n,y,x,:] = bilinear_x2(up_in)[n,y,x,:] + (lat_b + lat_w^T lat_in[n,y,x,:]), zero outside the image
   const float* lat_in;   // (S,H,W,8) channels-last   (read through map_c0)
   const float* lat_w;    // [8][32]
@@ -76,6 +76,14 @@ __device__ __forceinline__ unsigned long long gtime2() {
 __device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {
   uint32_t p;
@@ -84,10 +92,11 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 template <int NTAPS, int MODE, int FOLD, int NMMA, int PROD = 0>
-__global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)), PROD ? 1 : 2)      // two persistent CTAs per SM (one with the fused lateral)
+__global__ void __launch_bounds__(32 * (4 + NMMA + 1 + PROD), PROD ? 1 : 2)      // two persistent CTAs per SM (one with the fused lateral)
     tc_conv2_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_c0, const __grid_constant__ CUtensorMap map_f1,
                     const TcConv2Params P) {
-  constexpr int NP = PROD ? 5 : 1;      // producer warps: the TMA warp (+ 4 computing warps when the lateral is fused)
+  constexpr int NP = 1 + PROD;          // producer warps: the TMA warp (+ PROD computing warps when the lateral is fused)
+  constexpr int NPC = 32 * PROD;        // computing producer threads
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], accf_bar[2], acce_bar[2], w_bar, srcf_bar[2], srce_bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -99,7 +108,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)), PROD ? 1 : 2
 
   if (t == 0) {
     for (int i = 0; i < 8; ++i) {
-      tc::mbar_init(&full_bar[i], PROD != 0 ? 128 : 1);   // the producer's expect_tx arrival (+ the box's bytes) | every computing producer thread
+      tc::mbar_init(&full_bar[i], PROD != 0 ? NPC : 1);   // the producer's expect_tx arrival (+ the box's bytes) | every computing producer thread
       tc::mbar_init(&empty_bar[i], NMMA);    // one tcgen05.commit per MMA warp
     }
     for (int i = 0; i < 2; ++i) {
@@ -109,7 +118,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)), PROD ? 1 : 2
     tc::mbar_init(&w_bar, 1);
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&srcf_bar[i], 1);        // source boxes landed (expect_tx)
-      tc::mbar_init(&srce_bar[i], 128);      // every computing producer thread has read them
+      tc::mbar_init(&srce_bar[i], NPC);      // every computing producer thread has read them
     }
     tc::fence_mbar_init();
   }
@@ -152,7 +161,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)), PROD ? 1 : 2
     // thread = (halo pixel, g): channels [4g, 4g+4) and [16+4g, 16+4g+4) -- 16-byte chunks g and 4+g of the pixel's 128-byte
     // row, written at their SWIZZLE_128B position (chunk ^ (row & 7)); same arithmetic and order as lateral_upadd_kernel
     unsigned char* src0 = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(xch0) + P.xch_bytes + 1023) & ~(uintptr_t)1023);
-    const int pt = t - 32;                              // 0..127
+    const int pt = t - 32;                              // 0..NPC-1
     const int g = pt & 3;
     float4 wreg[16];                                    // this thread's 8 x 8 slice of the lateral's weights
 #pragma unroll
@@ -165,28 +174,39 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)), PROD ? 1 : 2
     const float rh = (H > 1) ? (float)(hi - 1) / (float)(H - 1) : 0.f;
     const float rw = (W > 1) ? (float)(wi - 1) / (float)(W - 1) : 0.f;
     const int npix = P.IY * P.IX;
+    // this thread's halo pixels: pp = (pt >> 2) + k * NPC / 4 (tile-invariant walk, no division per item)
+    constexpr int dpp = NPC / 4;
+    const int pp_first = pt >> 2, yy_first = pp_first / P.IX, xx_first = pp_first - yy_first * P.IX;
+    const int dyy = dpp / P.IX, dxx = dpp - dyy * P.IX;
+    const uint32_t ring_u = tc::smem_u32(ring), src0_u = tc::smem_u32(src0);
     int it = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
       const int bx = tile % P.nx, by = (tile / P.nx) % P.ny;
       const int x0 = bx * P.TX - P.ox, y0 = by * P.TY - P.oy;
       const int fy0 = (int)(rh * (float)max(y0, 0)), fx0 = (int)(rw * (float)max(x0, 0));
       const int slot = it % P.n_slots, ss = it & 1;
+      unsigned long long* dbg = (P.dbg && blockIdx.x == 0 && pt == 0) ? P.dbg : nullptr;
+      C2_STAMP(0, it, 0);
       tc::mbar_wait(&empty_bar[slot], (uint32_t)(((it / P.n_slots) & 1) ^ 1));       // operand slot free (its MMAs are done)
+      C2_STAMP(0, it, 1);
       tc::mbar_wait(&srcf_bar[ss], (uint32_t)((it >> 1) & 1));                       // this tile's sources have landed
-      unsigned char* dst = ring + (size_t)slot * P.slot_bytes;
-      const unsigned char* c0s = src0 + (size_t)ss * P.src_slot_bytes;
-      const unsigned char* f1s = c0s + P.src_f1_off;
-      for (int i = pt; i < npix * 4; i += 128) {
-        const int pp = i >> 2;
-        const int yy = pp / P.IX, xx = pp - yy * P.IX;
+      C2_STAMP(0, it, 2);
+      // 32-bit shared-window addresses + ld/st.shared: the byte pointers derived from the aligned dynamic-shared base had lost
+      // their address space (generic LD/ST with 64-bit address arithmetic), and the per-item pixel -> (row, column) division is
+      // replaced by an incremental walk: ncu counted ~330 issued instructions per item for ~100 FMAs (profiles/r2_spin_wait.md).
+      const uint32_t dst_u = ring_u + (uint32_t)slot * P.slot_bytes;
+      const uint32_t c0_u = src0_u + (uint32_t)ss * P.src_slot_bytes, f1_u = c0_u + P.src_f1_off;
+      int pp = pp_first, yy = yy_first, xx = xx_first;
+      for (; pp < npix; pp += dpp) {
         const int y = y0 + yy, x = x0 + xx;
         float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
         if (y >= 0 && y < H && x >= 0 && x < W) {
           float acc[8] = {bias0.x, bias0.y, bias0.z, bias0.w, bias1.x, bias1.y, bias1.z, bias1.w};
-          const unsigned char* crow = c0s + (size_t)pp * 32;           // SWIZZLE_32B: 16-byte chunk j of row pp sits at j ^ ((pp >> 2) & 1)
+          const uint32_t crow = c0_u + (uint32_t)pp * 32u;             // SWIZZLE_32B: 16-byte chunk j of row pp sits at j ^ ((pp >> 2) & 1)
+          const uint32_t csw = (uint32_t)((pp >> 2) & 1);
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(crow + ((q ^ ((pp >> 2) & 1)) << 4));
+            const float4 v = lds128(crow + (((uint32_t)q ^ csw) << 4));
             const float xv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int jx = 0; jx < 4; ++jx) {
@@ -202,7 +222,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)), PROD ? 1 : 2
           const float h1l = h1r - (float)h1, h0l = 1.f - h1l, w1l = w1r - (float)w1, w0l = 1.f - w1l;
           const int r00 = (h1 - fy0) * P.FW + (w1 - fx0), r01 = r00 + w1p, r10 = r00 + h1p * P.FW, r11 = r10 + w1p;
           auto tap = [&](int rr, int chunk) {       // SWIZZLE_128B: chunk c of row rr sits at c ^ (rr & 7)
-            return *reinterpret_cast<const float4*>(f1s + (size_t)rr * 128 + ((chunk ^ (rr & 7)) << 4));
+            return lds128(f1_u + (uint32_t)rr * 128u + ((uint32_t)(chunk ^ (rr & 7)) << 4));
           };
           float up[8];
 #pragma unroll
@@ -217,13 +237,16 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)), PROD ? 1 : 2
           o0 = make_float4(up[0] + acc[0], up[1] + acc[1], up[2] + acc[2], up[3] + acc[3]);
           o1 = make_float4(up[4] + acc[4], up[5] + acc[5], up[6] + acc[6], up[7] + acc[7]);
         }
-        unsigned char* rowp = dst + (size_t)pp * 128;
-        *reinterpret_cast<float4*>(rowp + ((g ^ (pp & 7)) << 4)) = o0;
-        *reinterpret_cast<float4*>(rowp + (((4 + g) ^ (pp & 7)) << 4)) = o1;
+        const uint32_t rowp = dst_u + (uint32_t)pp * 128u;
+        sts128(rowp + ((uint32_t)(g ^ (pp & 7)) << 4), o0);
+        sts128(rowp + ((uint32_t)((4 + g) ^ (pp & 7)) << 4), o1);
+        xx += dxx, yy += dyy;
+        if (xx >= P.IX) xx -= P.IX, ++yy;
       }
       mbar_arrive1(&srce_bar[ss]);             // the source slot may be refilled
       tc::fence_proxy_async();                 // my part of the tile -> visible to the tensor core
       mbar_arrive1(&full_bar[slot]);
+      C2_STAMP(0, it, 3);                      // operand tile written
     }
   } else if (warp == 0) {
     // ============================== producer ==============================
@@ -306,6 +329,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)), PROD ? 1 : 2
     const int r = g * 32 + lane;                              // row of the M-tile
     const uint32_t trow0 = tmem + ((uint32_t)(g * 32) << 16);
     const int plane = P.IY * P.IX;
+    const uint32_t xch0_u = tc::smem_u32(xch0);
     struct RowPos { int z, y, x; };
     const RowPos first = {r / plane, (r % plane) / P.IX, r % P.IX};                 // halo position of accumulator row r of M-tile 0
     auto advance = [&](RowPos& p) {                                                 // ... and of the same row one M-tile on
@@ -327,7 +351,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)), PROD ? 1 : 2
       tc::tc_fence_after_sync();
       C2_STAMP(2, ti, 1);                           // accumulator full (all MMAs of the tile complete)
       const uint32_t trow = trow0 + (uint32_t)(acc * P.n_mt * P.N);
-      float* xch = xch0 + (size_t)(ti & 1) * (P.xch_bytes / 8);      // [n_mt*4 + 1][2 rows][N], double buffered
+      const uint32_t xch_u = xch0_u + (uint32_t)(ti & 1) * (P.xch_bytes / 2);      // [n_mt*4 + 1][2 rows][N] floats, double buffered (shared-window address)
       RowPos pos = first;                            // advanced once per M-tile, in order
       auto locate = [&](const RowPos& p, size_t& pix, int& gz, int& gy, int& gx) -> bool {
         gz = z0 + p.z, gy = y0 + p.y, gx = x0 + p.x;
@@ -374,9 +398,9 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)), PROD ? 1 : 2
           }
         };
         auto publish = [&](int m, const float* v) {      // lanes 0, 1: rows 0, 1 of this warp's 32-row group of M-tile m
-          float4* d = reinterpret_cast<float4*>(xch + ((size_t)((m * 4 + g) * 2 + lane)) * XS);
+          const uint32_t d = xch_u + (uint32_t)(((m * 4 + g) * 2 + lane) * XS) * 4u;
 #pragma unroll
-          for (int c4 = 0; c4 < NC / 4; ++c4) d[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+          for (int c4 = 0; c4 < NC / 4; ++c4) sts128(d + 16u * c4, make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]));
         };
         auto outputs = [&](int m, const float* v) {
           size_t pix;
@@ -386,16 +410,16 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)), PROD ? 1 : 2
           // rows 0, 1 of the next 32-row group.  EVERY lane loads (uniform row 0 / lane-selected row, 16-byte vectors) and the two
           // last lanes SELECT: the per-element `if (lane >= 30) x = smem[..]` this replaces compiled to 16 divergent
           // branch regions per M-tile and made the fold epilogue ~1.3 us per M-tile (profiles/r2_conv2_timeline.md).
-          const float* row0 = xch + (size_t)((m * 4 + g + 1) * 2) * XS;
-          const float* rowc = row0 + ((lane == 31) ? XS : 0);            // row (lane - 30) for lanes 30, 31
-          auto ld4 = [](const float* q, float* d) {
-            const float4 t4 = *reinterpret_cast<const float4*>(q);
+          const uint32_t row0 = xch_u + (uint32_t)((m * 4 + g + 1) * 2 * XS) * 4u;
+          const uint32_t rowc = row0 + ((lane == 31) ? (uint32_t)XS * 4u : 0u);            // row (lane - 30) for lanes 30, 31
+          auto ld4 = [](uint32_t q, float* d) {
+            const float4 t4 = lds128(q);
             d[0] = t4.x, d[1] = t4.y, d[2] = t4.z, d[3] = t4.w;
           };
           if constexpr (MODE == TC_PLAIN) {      // C = 8 (the rule folds 8-channel layers only): columns [0,8) [8,16) [16,24)
             float nb[8], nc[8], a[8];
-            ld4(row0 + 8, nb), ld4(row0 + 12, nb + 4);
-            ld4(rowc + 16, nc), ld4(rowc + 20, nc + 4);
+            ld4(row0 + 32, nb), ld4(row0 + 48, nb + 4);
+            ld4(rowc + 64, nc), ld4(rowc + 80, nc + 4);
 #pragma unroll
             for (int jx = 0; jx < 8; ++jx) {
               float b1 = __shfl_down_sync(0xffffffffu, v[8 + jx], 1);
@@ -407,8 +431,8 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + (PROD ? 5 : 1)), PROD ? 1 : 2
             if (valid) emit8(a, P.out + pix * P.out_cstride + P.out_coff, bias_r);
           } else if constexpr (MODE == TC_HEAD) {   // columns kx*9 + co: 8 feat + 1 prob per kx
             float nb[12], nc[12], rr[9];            // columns 8..19 of row 0 (9..17 used), 16..27 of the selected row (18..26 used)
-            ld4(row0 + 8, nb), ld4(row0 + 12, nb + 4), ld4(row0 + 16, nb + 8);
-            ld4(rowc + 16, nc), ld4(rowc + 20, nc + 4), ld4(rowc + 24, nc + 8);
+            ld4(row0 + 32, nb), ld4(row0 + 48, nb + 4), ld4(row0 + 64, nb + 8);
+            ld4(rowc + 64, nc), ld4(rowc + 80, nc + 4), ld4(rowc + 96, nc + 8);
 #pragma unroll
             for (int jx = 0; jx < 9; ++jx) {
               float b1 = __shfl_down_sync(0xffffffffu, v[9 + jx], 1);
@@ -577,7 +601,9 @@ static bool stride2_enabled() { return g_impl != 3; }
 // two issuing warps x two persistent CTAs per SM keep it fed (per-layer A/B: profiles/r2_conv2_sweep.md).
 static int g_nmma = 2;          // MMA-issuing warps per CTA (1 | 2)
 static int g_ctas_per_sm = 2;   // persistent CTAs per SM (1 | 2)
+static int g_prod_warps = 6;    // computing producer warps of the fused lateral (4 | 6 | 8): 6 = 12 warps per CTA, 166 registers, no spill
 static unsigned long long* g_conv2_dbg = nullptr;
+static int g_conv2_dbg_lat_only = 0;
 static int g_tune2_tz = 0, g_tune2_ty = 0, g_tune2_fold = -1, g_tune2_kbc = 0, g_tune2_slots = 0;
 
 int tc_conv2_impl() { return g_impl; }
@@ -643,7 +669,7 @@ static int tc_conv2_plan(const TcConvLayer& L, int Dn, int Hn, int Wn, bool fold
   if (g_tune2_ty > 0) P.TY = g_tune2_ty;
   P.TZ = std::min(P.TZ, Dn), P.TY = std::min(P.TY, Hn);
 
-  // the fused-lateral kernel (352 threads, ~140 registers) runs one CTA per SM whatever the setting
+  // the fused-lateral kernel (14-15 warps) runs one CTA per SM whatever the setting
   const bool two_ctas = g_ctas_per_sm >= 2 && !lat;
   const size_t budget = (two_ctas ? 110 : 216) * 1024;
   for (;;) {
@@ -753,7 +779,7 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
   P.out_cstride = out_cstride, P.out_coff = out_coff;
   P.wpack = wpack, P.bias = bias, P.skip = skip, P.out = out, P.out2 = out2;
   P.lat_in = lat ? lat->lat_in : nullptr, P.lat_w = lat ? lat->lat_w : nullptr, P.lat_b = lat ? lat->lat_b : nullptr, P.up_in = lat ? lat->up_in : nullptr;
-  P.dbg = g_conv2_dbg;
+  P.dbg = (g_conv2_dbg_lat_only && lat == nullptr) ? nullptr : g_conv2_dbg;
 
   // tensor map of the input: channels-last (D,H,W,C) fp32 -> dims {C, W, H, D}, box {kbc, IX, IY, IZ}
   CUtensorMap map;
@@ -813,13 +839,23 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
       ENERF_REQUIRE(e == cudaSuccess, ENERF_ECUDA, "tc_conv2(lateral): cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));             \
       lat_set = smem;                                                                                                                            \
     }                                                                                                                                            \
-    tc_conv2_kernel<NT, TC_PLAIN, FD, NM, PR><<<grid, 32 * (4 + NM + 5), smem, stream>>>(map, map_c0, map_f1, P);                                \
+    tc_conv2_kernel<NT, TC_PLAIN, FD, NM, PR><<<grid, 32 * (4 + NM + 1 + PR), smem, stream>>>(map, map_c0, map_f1, P);                                \
   } while (0)
     // (lat1 -> smooth1 is NOT fused: its output feat1_pre is also lat0's up-sampling source, so it must exist in HBM anyway;
     //  the producer is written for lat_cin 8 | 16, only 8 is instantiated)
-    if (fold) TC2_LAT(3, 1, 1, 1);
-    else if (g_nmma >= 2) TC2_LAT(9, 0, 2, 1);
-    else TC2_LAT(9, 0, 1, 1);
+    // PROD = computing producer warps.  Four (one per scheduler) made the producer the bottleneck of the fused smooth0 (~120 us of
+    // latency-bound FP32 work against ~45 us of MMAs); 6 keeps the CTA at 12 warps = 168 registers per thread, 8 halves the
+    // producer's time at 128 registers (enerf_tc_conv2_tune's `prod` selects, A/B in profiles/r2_frame_ab.md).
+    const int pw = g_prod_warps;
+    if (fold) {
+      if (pw >= 8) TC2_LAT(3, 1, 1, 8);
+      else if (pw >= 6) TC2_LAT(3, 1, 1, 6);
+      else TC2_LAT(3, 1, 1, 4);
+    } else {
+      if (pw >= 8) TC2_LAT(9, 0, 2, 8);
+      else if (pw >= 6) TC2_LAT(9, 0, 2, 6);
+      else TC2_LAT(9, 0, 2, 4);
+    }
 #undef TC2_LAT
     ENERF_CHECK_LAUNCH("tc_conv2(lateral)");
     return ENERF_OK;
@@ -875,11 +911,21 @@ extern "C" int enerf_tc_conv2_plan(int kind, int KD, int KH, int stride, int cin
 // free, first K-block landed, MMAs issued}, 2 epilogue row 0 {start, accumulator full, accumulator released, outputs stored}.
 extern "C" int enerf_tc_conv2_debug(unsigned long long* buf) {
   enerf::g_conv2_dbg = buf;
+  enerf::g_conv2_dbg_lat_only = 0;
+  return ENERF_OK;
+}
+// ... only the fused-lateral launch stamps (role 0 = computing producer thread 0: {start, operand slot free, sources landed, tile written})
+extern "C" int enerf_tc_conv2_debug_lateral(unsigned long long* buf) {
+  enerf::g_conv2_dbg = buf;
+  enerf::g_conv2_dbg_lat_only = 1;
   return ENERF_OK;
 }
 
+// on: 0 = separate lateral kernel, 1 = fused with the default number of computing producer warps, 4 | 6 | 8 = fused with that many
 extern "C" int enerf_tc_conv2_fuse_lateral(int on) {
-  enerf::g_fuse_lateral = on;
+  ENERF_REQUIRE(on == 0 || on == 1 || on == 4 || on == 6 || on == 8, ENERF_EINVAL, "tc_conv2_fuse_lateral: %d (0 | 1 | 4 | 6 | 8)", on);
+  enerf::g_fuse_lateral = on != 0;
+  if (on != 0) enerf::g_prod_warps = (on == 1) ? 6 : on;
   return ENERF_OK;
 }
 

@@ -37,18 +37,18 @@ TC_FEATURE_LAYERS = ("conv0.1", "conv1.0", "conv1.1", "conv2.0", "conv2.1", "top
 
 # Which layers carry their three kx taps in the MMA's N dimension; mirrors csrc/tc_conv.cu::tc_fold_rule (capi.tc_conv_fold_rule
 # sets both): 0 = stride-1 3x3x3 layers with 8 output channels + the single-channel depth head, 1 = + the feat/prob head,
-# 2 (shipped) = + stride-1 3x3 2-D layers with 8 output channels (FeatureNet conv0.1, smooth0).
+# 2 (shipped) = + stride-1 3x3 2-D layers with 8 output and >= 16 input channels (FeatureNet smooth0).
 FOLD_RULE = 2
 
 
-def tc_fold_kx(KD, KH, stride, cout, single=False, head=False):
-    """The folding rule of csrc/tc_conv.cu::tc_fold_rule for a convolution (KD x KH x KH, `stride`, `cout` output channels;
+def tc_fold_kx(KD, KH, stride, cout, single=False, head=False, cin=32):
+    """The folding rule of csrc/tc_conv.cu::tc_fold_rule for a convolution (KD x KH x KH, `stride`, `cin` -> `cout` channels;
     single: the depth-only head, head: the feat + prob head)."""
     if stride != 1 or KH != 3:
         return False
     if KD == 3:
         return bool(single or (head and FOLD_RULE >= 1) or (not head and cout == 8))
-    return KD == 1 and not single and not head and cout == 8 and FOLD_RULE >= 2
+    return KD == 1 and not single and not head and cout == 8 and cin >= 16 and FOLD_RULE >= 2
 
 
 def pack_feature_net(sd, device, p="feature_net", tensor_cores=False):
@@ -56,7 +56,7 @@ def pack_feature_net(sd, device, p="feature_net", tensor_cores=False):
     tensor_cores: the layers in TC_FEATURE_LAYERS get the tcgen05 stage layout (pack_tc_conv)."""
     def lay(name, w_taps):
         if tensor_cores and name in TC_FEATURE_LAYERS:
-            fold = w_taps.shape[0] == 9 and tc_fold_kx(1, 3, 1, w_taps.shape[2])     # FeatureNet's 3x3 layers are all stride 1
+            fold = w_taps.shape[0] == 9 and tc_fold_kx(1, 3, 1, w_taps.shape[2], cin=w_taps.shape[1])     # FeatureNet's 3x3 layers are all stride 1
             return pack_tc_conv(w_taps, fold_kx=fold).to(device)
         return _dev(w_taps, device)
 

@@ -280,6 +280,8 @@ ENERF_API int enerf_tc_conv2_tune(int impl, int nmma, int ctas_per_sm, int tz, i
 /* Diagnostic: in-kernel timeline of csrc/tc_conv2.cu (CTA 0, first 16 tiles): buf = 3 x 16 x 8 u64 of %globaltimer ns
  * (roles producer / MMA warp 0 / epilogue row 0; layout at the definition); NULL switches it off. */
 ENERF_API int enerf_tc_conv2_debug(unsigned long long* buf);
+/* ... the same, stamped only by the fused-lateral launch of enerf_feature_net (role 0 = computing producer thread 0). */
+ENERF_API int enerf_tc_conv2_debug_lateral(unsigned long long* buf);
 /* The launch geometry csrc/tc_conv2.cu would use for a layer ((D,H,W) = its row grid) on a device with n_sm SMs, computed
  * without touching a GPU, so the CPU test suite can emulate the kernel from it (tests/test_host_cpu.py).  out: 67 ints,
  * layout documented at the definition.  Returns ENERF_EUNSUPPORTED when the layer stays on csrc/tc_conv.cu. */
@@ -287,7 +289,8 @@ ENERF_API int enerf_tc_conv2_plan(int kind, int KD, int KH, int stride, int cin,
                                   int n_sm, int* out);
 /* Diagnostic: 1 (default) = enerf_feature_net computes lat0 (1x1 lateral + bilinear x2 + add, feature_net.py:31-35) inside
  * smooth0's producer warps on the tensor-core path (source tiles staged by TMA; the 126 MB 32-channel map is never written);
- * 0 = separate lateral kernel + plain smooth0 (bit-identical features). */
+ * 0 = separate lateral kernel + plain smooth0 (bit-identical features); 4 | 6 | 8 = fused with that many computing producer
+ * warps per CTA (1 = the default, 6). */
 ENERF_API int enerf_tc_conv2_fuse_lateral(int on);
 
 /* Diagnostic: when buf != NULL, CTA (0,0,0) of every later enerf_tc_conv-family launch writes 64

@@ -154,7 +154,7 @@ def test_folded_tc_conv_packing_is_a_shifted_sum_of_partial_convolutions():
         packing.FOLD_RULE = 1
         assert packing.tc_fold_kx(3, 3, 1, 9, head=True) and not packing.tc_fold_kx(1, 3, 1, 8)
         packing.FOLD_RULE = 2
-        assert packing.tc_fold_kx(3, 3, 1, 9, head=True) and packing.tc_fold_kx(1, 3, 1, 8)
+        assert packing.tc_fold_kx(3, 3, 1, 9, head=True) and packing.tc_fold_kx(1, 3, 1, 8, cin=32) and not packing.tc_fold_kx(1, 3, 1, 8, cin=8)
     finally:
         packing.FOLD_RULE = rule
     taps = packing._taps_cin_cout(w)                                   # [27][cin][cout], taps ordered (kz,ky,kx)

@@ -250,7 +250,7 @@ def _run_tc_conv_layer(case, impl):
         ref = F.conv3d(x, w, b, (stride if KD > 1 else 1, stride, stride), (KD // 2, KH // 2, KH // 2))
         if relu:
             ref = F.relu(ref)
-        wp = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=packing.tc_fold_kx(KD, KH, stride, cout, single=(mode == 3), head=(mode == 1))).cuda()
+        wp = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=packing.tc_fold_kx(KD, KH, stride, cout, single=(mode == 3), head=(mode == 1), cin=cin)).cuda()
         skip = None
     else:
         w = torch.randn(cin, cout, 3, 3, 3, generator=g) / (cin * 27 / 8) ** 0.5

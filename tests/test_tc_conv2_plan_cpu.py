@@ -125,7 +125,7 @@ CASES = [
 def test_tc_conv2_geometry_emulated_on_cpu(case):
     kind, KD, KH, stride, cin, cout, mode, relu, (D, H, W), n_sm = case
     g = torch.Generator().manual_seed(cin * 31 + cout + KD)
-    fold = packing.tc_fold_kx(KD, KH, stride, cout, single=(mode == TC_SINGLE), head=(mode == TC_HEAD)) if kind == 0 else False
+    fold = packing.tc_fold_kx(KD, KH, stride, cout, single=(mode == TC_SINGLE), head=(mode == TC_HEAD), cin=cin) if kind == 0 else False
     plan = capi.tc_conv2_plan(kind, KD, KH, stride, cin, cout, mode, D, H, W, fold, n_sm=n_sm)
     assert plan["fold"] == int(fold)
     sz = stride if (KD > 1 and kind == 0) else 1

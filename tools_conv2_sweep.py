@@ -61,7 +61,7 @@ def main(quick):
         skip = None
         if kind == 0:
             w = torch.randn(cout, cin, KD, KH, KH, generator=g) / (cin * KD * KH * KH) ** 0.5
-            wp = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3), head=(mode == 1))).cuda()
+            wp = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3), head=(mode == 1), cin=cin)).cuda()
             Do, Ho, Wo = D, H, W
         else:
             w = torch.randn(cin, cout, 3, 3, 3, generator=g) / (cin * 27 / 8) ** 0.5
@@ -93,7 +93,7 @@ def main(quick):
             wp_v = wp
             if rule is not None:
                 capi.tc_conv_fold_rule(rule)
-                wp_v = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3), head=(mode == 1))).cuda()
+                wp_v = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3), head=(mode == 1), cin=cin)).cuda()
             if nofold:
                 wp_v = packing.pack_tc_conv(packing._taps_cin_cout(w), fold_kx=False).cuda()
                 capi.tc_conv_tune(0, 0, 0)

@@ -17,7 +17,7 @@ for name, kind, KD, KH, cin, cout, mode, relu, (D, H, W), rule in [(*L, f) for L
     if name not in WANT or (rule == 0 and name not in RULE0_TOO):
         continue
     capi.tc_conv_fold_rule(rule)
-    fold = kind == 0 and packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3), head=(mode == 1))
+    fold = kind == 0 and packing.tc_fold_kx(KD, KH, 1, cout, single=(mode == 3), head=(mode == 1), cin=cin)
     g = torch.Generator().manual_seed(1)
     x = torch.randn(D, H, W, cin, generator=g).cuda()
     skip = None

@@ -15,13 +15,14 @@ from enerf_b200 import capi  # noqa: E402
 from enerf_b200.pipeline import GraphedNetwork  # noqa: E402
 
 CONFIGS = [
-    # name, tc_conv2_tune kwargs, lat0 fused, ray kernel, fold rule level
+    # name, tc_conv2_tune kwargs, lat0 fused (False | producer warps), ray kernel, fold rule level
     ("conv v1 | rays v1 | fold rule 0 (round-1 kernels)", dict(impl=1), False, 1, 0),
-    ("conv v2 2cta, lat0 fused, fold rule 2 | rays v1 (shipped default)", dict(impl=0, nmma=2, ctas_per_sm=2), True, 1, 2),
-    ("conv v2 2cta, lat0 fused, fold rule 1 | rays v1", dict(impl=0, nmma=2, ctas_per_sm=2), True, 1, 1),
-    ("conv v2 2cta, lat0 fused, fold rule 0 | rays v1", dict(impl=0, nmma=2, ctas_per_sm=2), True, 1, 0),
-    ("conv v2 2cta, lat0 separate, fold rule 2 | rays v1", dict(impl=0, nmma=2, ctas_per_sm=2), False, 1, 2),
-    ("conv v2 2cta, lat0 fused, fold rule 2 | rays ws", dict(impl=0, nmma=2, ctas_per_sm=2), True, 2, 2),
+    ("conv v2, lat0 fused (6 producer warps), fold rule 2 | rays v1 (shipped default)", dict(impl=0), 6, 1, 2),
+    ("conv v2, lat0 fused (8 producer warps), fold rule 2 | rays v1", dict(impl=0), 8, 1, 2),
+    ("conv v2, lat0 fused (4 producer warps), fold rule 2 | rays v1", dict(impl=0), 4, 1, 2),
+    ("conv v2, lat0 fused (6 producer warps), fold rule 1 | rays v1", dict(impl=0), 6, 1, 1),
+    ("conv v2, lat0 fused (6 producer warps), fold rule 0 | rays v1", dict(impl=0), 6, 1, 0),
+    ("conv v2, lat0 separate, fold rule 2 | rays v1", dict(impl=0), False, 1, 2),
 ]
 
 
