@@ -45,6 +45,8 @@ extern "C" int enerf_render_rays_tc(const EnerfCam* cam, int level, const float*
   ENERF_REQUIRE(n_views >= 2 && n_views <= ENERF_MAX_VIEWS, ENERF_EUNSUPPORTED, "render_rays_tc: n_views %d not in [2,8]", n_views);
   ENERF_REQUIRE(num_samples == 1 || num_samples == 2 || num_samples == 4 || num_samples == 8, ENERF_EUNSUPPORTED,
                 "render_rays_tc: num_samples %d not in {1,2,4,8}", num_samples);
+  ENERF_REQUIRE((long long)n_rays * num_samples + 128 < (1ll << 31), ENERF_EUNSUPPORTED, "render_rays_tc: %d rays x %d samples exceed the 32-bit index range",
+                n_rays, num_samples);
   ENERF_REQUIRE(level >= 0 && level < ENERF_MAX_LEVELS, ENERF_EINVAL, "render_rays_tc: level %d", level);
   ENERF_REQUIRE(vol_row0 >= 0 && vol_rows > 0 && vol_row0 + vol_rows <= hv, ENERF_EINVAL, "render_rays_tc: volume rows [%d,%d) outside [0,%d)",
                 vol_row0, vol_row0 + vol_rows, hv);
@@ -88,6 +90,7 @@ extern "C" int enerf_render_rays_raw_tc(const EnerfCam* cam, int level, const fl
   ENERF_REQUIRE(out_off >= 0 && out_off + num_samples <= out_stride, ENERF_EINVAL, "render_rays_raw_tc: slot [%d,%d) outside stride %d",
                 out_off, out_off + num_samples, out_stride);
   if (w == 0 || h == 0) return ENERF_OK;
+  ENERF_REQUIRE((long long)w * h * num_samples + 128 < (1ll << 31), ENERF_EUNSUPPORTED, "render_rays_raw_tc: window x samples exceed the 32-bit index range");
   RayTcParams P;
   RayParams& p = P.r;
   p.cam = cam, p.level = level;

@@ -87,6 +87,44 @@ struct TcSmem {
   static constexpr size_t bytes = (size_t)total_floats * 4 + 64;
 };
 
+// The TF32-mode kernel's scalar math: approximate division / square root / exponential (MUFU + one multiply instead of the
+// IEEE sequences: ~12 instructions and a slow-path branch per division, ~50 for log1pf(expf)).  ncu counted 51 divisions per
+// sample point = ~13 % of the kernel's issued instructions, all on dependent chains of a latency-bound kernel.  Errors are a
+// few ulp -- two orders below the TF32 operand rounding this kernel already has (the FP32-pipe kernel render_rays.cuh stays exact).
+#ifndef RTC_FAST_MATH
+#define RTC_FAST_MATH 1
+#endif
+__device__ __forceinline__ float rdiv(float a, float b) {
+#if RTC_FAST_MATH
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+__device__ __forceinline__ float rsqrt_(float x) {
+#if RTC_FAST_MATH
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sqrtf(x);
+#endif
+}
+__device__ __forceinline__ float rexp(float x) {
+#if RTC_FAST_MATH
+  return __expf(x);
+#else
+  return expf(x);
+#endif
+}
+__device__ __forceinline__ float rsoftplus(float x) {      // log(1 + exp(x)), x <= 20
+#if RTC_FAST_MATH
+  return __logf(1.f + __expf(x));
+#else
+  return log1pf(expf(x));
+#endif
+}
+
 __device__ __forceinline__ void store_chunk(float* a_base, int chunk, int row, float v0, float v1, float v2, float v3) {
   *reinterpret_cast<float4*>(a_base + (size_t)chunk * 512 + row * 4) =
       make_float4(tc::to_tf32(v0), tc::to_tf32(v1), tc::to_tf32(v2), tc::to_tf32(v3));
@@ -131,6 +169,7 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
   uint32_t phase = 0;
 
   const int Ns = p.num_samples;
+  const int ns_shift = 31 - __clz(Ns);
   const float tcx = cam_s[ENERF_MAX_VIEWS * 24 + 0], tcy = cam_s[ENERF_MAX_VIEWS * 24 + 1], tcz = cam_s[ENERF_MAX_VIEWS * 24 + 2];
   const size_t hw = (size_t)p.hv * p.wv;
 
@@ -158,11 +197,11 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     ++tile_i;
     RAY_STAMP(0);
-    const long long pt = (long long)tile * 128 + t;
-    const bool valid = pt < (long long)n_rays * Ns;
-    int ray = valid ? (int)(pt / Ns) : n_rays - 1;
+    const int pt = tile * 128 + t;                        // < 2^31: the launcher checks n_rays * Ns
+    const bool valid = pt < n_rays * Ns;
+    int ray = valid ? (pt >> ns_shift) : n_rays - 1;      // Ns is 1 | 2 | 4 | 8 on this path
     if (p.out_raw) ray = (p.win_y + ray / p.win_w) * p.Wr + p.win_x + ray % p.win_w;   // layered mode: window -> frame pixel
-    const int k = (int)(pt % Ns);
+    const int k = pt & (Ns - 1);
 
     // ================= stage A: build_rays + sample + gathers (FP32 pipe) =================
     const float4 r0 = ldg4(p.rays + (size_t)ray * 8), r1 = ldg4(p.rays + (size_t)ray * 8 + 4);
@@ -187,16 +226,20 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
       rf = fminf(dep + sd, vf);
     }
     const float z = (Ns == 1) ? rn + (rf - rn) * 0.5f : rn + (rf - rn) * linspace01(k, Ns);
-    const float tz = p.depth_inv ? 1.0f / fmaxf(z, 1e-6f) : z;
+    const float tz = p.depth_inv ? rdiv(1.0f, fmaxf(z, 1e-6f)) : z;
     const float X = r0.x + r0.w * tz, Y = r0.y + r1.x * tz, Z = r0.z + r1.y * tz;
-    const float dn = p.depth_inv ? (vn - z) / fmaxf(vn - vf, 1e-6f) : (z - vn) / fmaxf(vf - vn, 1e-6f);
+    const float dn = p.depth_inv ? rdiv(vn - z, fmaxf(vn - vf, 1e-6f)) : rdiv(z - vn, fmaxf(vf - vn, 1e-6f));
 
     float vox[8];
     {
+#if RTC_FAST_MATH
+      const float ix = rdiv(u, (float)(p.Wr - 1)) * (float)(p.wv - 1), iy = rdiv(v, (float)(p.Hr - 1)) * (float)(p.hv - 1), iz = dn * (float)(p.D - 1);
+#else
       const float un = u / (float)(p.Wr - 1), vnrm = v / (float)(p.Hr - 1);
       const float gx = un * 2.f - 1.f, gy = vnrm * 2.f - 1.f, gz = dn * 2.f - 1.f;
       const float ix = ((gx + 1.f) / 2.f) * (float)(p.wv - 1), iy = ((gy + 1.f) / 2.f) * (float)(p.hv - 1),
                   iz = ((gz + 1.f) / 2.f) * (float)(p.D - 1);
+#endif
 #pragma unroll
       for (int c = 0; c < 8; ++c) vox[c] = 0.f;
       if (p.feat_vol != nullptr && ix > -1.f && ix < (float)p.wv && iy > -1.f && iy < (float)p.hv && iz > -1.f && iz < (float)p.D) {
@@ -227,8 +270,8 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
     float rgb_s[S][3];
     float tdx = X - tcx, tdy = Y - tcy, tdz = Z - tcz;
     {
-      const float n = sqrtf(tdx * tdx + tdy * tdy + tdz * tdz) + 1e-6f;
-      tdx /= n, tdy /= n, tdz /= n;
+      const float n = rsqrt_(tdx * tdx + tdy * tdy + tdz * tdz) + 1e-6f;
+      tdx = rdiv(tdx, n), tdy = rdiv(tdy, n), tdz = rdiv(tdz, n);
     }
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -242,8 +285,13 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
       const float p1 = K[3] * xc + K[4] * yc + K[5] * zc;
       const float p2 = K[6] * xc + K[7] * yc + K[8] * zc;
       const float pz = fmaxf(p2, 1e-6f);
+#if RTC_FAST_MATH
+      // the reference normalises to [-1,1] and grid_sample(align_corners=True) maps straight back: the pixel coordinate itself
+      float ix = rdiv(p0, pz), iy = rdiv(p1, pz);
+#else
       const float gx = (p0 / pz) / (float)(p.Wr - 1) * 2.f - 1.f, gy = (p1 / pz) / (float)(p.Hr - 1) * 2.f - 1.f;
       float ix = ((gx + 1.f) / 2.f) * (float)(p.Wr - 1), iy = ((gy + 1.f) / 2.f) * (float)(p.Hr - 1);
+#endif
       ix = fminf(fmaxf(ix, 0.f), (float)(p.Wr - 1));
       iy = fminf(fmaxf(iy, 0.f), (float)(p.Hr - 1));
       const float fx0 = floorf(ix), fy0 = floorf(iy);
@@ -266,11 +314,11 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
       }
       rgb_s[s][0] = g[s][8], rgb_s[s][1] = g[s][9], rgb_s[s][2] = g[s][10];
       float sx = X - Cn[0], sy = Y - Cn[1], sz = Z - Cn[2];
-      const float n = sqrtf(sx * sx + sy * sy + sz * sz) + 1e-6f;
-      sx /= n, sy /= n, sz /= n;
+      const float n = rsqrt_(sx * sx + sy * sy + sz * sz) + 1e-6f;
+      sx = rdiv(sx, n), sy = rdiv(sy, n), sz = rdiv(sz, n);
       const float rx = tdx - sx, ry = tdy - sy, rz = tdz - sz;
-      const float rnm = fmaxf(sqrtf(rx * rx + ry * ry + rz * rz), 1e-6f);
-      const float d0 = rx / rnm, d1 = ry / rnm, d2 = rz / rnm, d3 = tdx * sx + tdy * sy + tdz * sz;
+      const float rnm = fmaxf(rsqrt_(rx * rx + ry * ry + rz * rz), 1e-6f);
+      const float d0 = rdiv(rx, rnm), d1 = rdiv(ry, rnm), d2 = rdiv(rz, rnm), d3 = tdx * sx + tdy * sy + tdz * sz;
       // A operand of color.0's per-view columns: [f_s (11) | dir_s (4) | 0]
       const int cf = SM::P_CHUNKS + 4 * s;
       store_chunk(a_s, cf + 0, t, g[s][0], g[s][1], g[s][2], g[s][3]);
@@ -349,21 +397,30 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
         float h[32];
         tc::tmem_ld32(tmem_row + s * 32, h);
         tc::tmem_ld_wait();
-        float a = sw[TcW::v_ba];
+        // 32 -> 1 dot product as packed f32x2 FMAs on two independent chains (a 32-deep dependent FFMA chain is pure latency
+        // in a kernel with two warps per scheduler)
+        float2 d0 = make_float2(sw[TcW::v_ba], 0.f), d1 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          h[j] = fmaxf(h[j], 0.f);                       // bias already in the accumulator
-          a = fmaf(h[j], sw[TcW::v_wa + j], a);
+        for (int j = 0; j < 32; j += 4) {
+          h[j] = fmaxf(h[j], 0.f), h[j + 1] = fmaxf(h[j + 1], 0.f), h[j + 2] = fmaxf(h[j + 2], 0.f), h[j + 3] = fmaxf(h[j + 3], 0.f);   // bias already in the accumulator
+          const float4 w4 = *reinterpret_cast<const float4*>(sw + TcW::v_wa + j);
+          d0 = __ffma2_rn(make_float2(h[j], h[j + 1]), make_float2(w4.x, w4.y), d0);
+          d1 = __ffma2_rn(make_float2(h[j + 2], h[j + 3]), make_float2(w4.z, w4.w), d1);
         }
+        const float a = (d0.x + d0.y) + (d1.x + d1.y);
         const float lg = fmaxf(a, 0.f);
         const float mn = fmaxf(mx, lg);
-        const float sc = expf(mx - mn), e = expf(lg - mn);   // first view: sc = exp(-inf) = 0
+        const float sc = rexp(mx - mn), e = rexp(lg - mn);   // first view: sc = exp(-inf) = 0
         den = fmaf(den, sc, e);
+        const float2 e2 = make_float2(e, e), sc2 = make_float2(sc, sc);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) im[j] = fmaf(e, h[j], im[j] * sc);
+        for (int j = 0; j < 32; j += 2) {
+          const float2 r = __ffma2_rn(e2, make_float2(h[j], h[j + 1]), __fmul2_rn(make_float2(im[j], im[j + 1]), sc2));
+          im[j] = r.x, im[j + 1] = r.y;
+        }
         mx = mn;
       }
-      const float inv = 1.0f / den;
+      const float inv = rdiv(1.0f, den);
 #pragma unroll
       for (int q = 0; q < 8; ++q) store_chunk(a_s, q, t, im[4 * q] * inv, im[4 * q + 1] * inv, im[4 * q + 2] * inv, im[4 * q + 3] * inv);
     }
@@ -409,21 +466,27 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
     RAY_STAMP(7);
     float sigma;
     {
-      float sg = sw[TcW::v_bs];
+      float2 g0 = make_float2(sw[TcW::v_bs], 0.f), g1 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float x[32];
         tc::tmem_ld32(tmem_row + half * 32, x);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          x[j] = fmaxf(x[j] + sw[TcW::v_b0 + half * 32 + j], 0.f);
-          sg = fmaf(x[j], sw[TcW::v_ws + half * 32 + j], sg);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sw + TcW::v_b0 + half * 32 + j);
+          const float4 w4 = *reinterpret_cast<const float4*>(sw + TcW::v_ws + half * 32 + j);
+          const float2 s0 = __fadd2_rn(make_float2(x[j], x[j + 1]), make_float2(b4.x, b4.y));
+          const float2 s1 = __fadd2_rn(make_float2(x[j + 2], x[j + 3]), make_float2(b4.z, b4.w));
+          x[j] = fmaxf(s0.x, 0.f), x[j + 1] = fmaxf(s0.y, 0.f), x[j + 2] = fmaxf(s1.x, 0.f), x[j + 3] = fmaxf(s1.y, 0.f);
+          g0 = __ffma2_rn(make_float2(x[j], x[j + 1]), make_float2(w4.x, w4.y), g0);
+          g1 = __ffma2_rn(make_float2(x[j + 2], x[j + 3]), make_float2(w4.z, w4.w), g1);
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) store_chunk(a_s, half * 8 + q, t, x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
       }
-      sigma = (sg > 20.f) ? sg : log1pf(expf(sg));
+      const float sg = (g0.x + g0.y) + (g1.x + g1.y);
+      sigma = (sg > 20.f) ? sg : rsoftplus(sg);
     }
     RAY_STAMP(8);
     // ================= G5: color.0 =================
@@ -451,27 +514,32 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
       float mx = -INFINITY;
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        float a = sw[TcW::v_b2];
+        float2 c0 = make_float2(sw[TcW::v_b2], 0.f), c1 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float h[32];
           tc::tmem_ld32(tmem_row + s * 64 + half * 32, h);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a = fmaf(fmaxf(h[j], 0.f), sw[TcW::v_w2 + half * 32 + j], a);   // bias in the accumulator
+          for (int j = 0; j < 32; j += 4) {       // bias in the accumulator; packed FMAs on two chains
+            const float4 w4 = *reinterpret_cast<const float4*>(sw + TcW::v_w2 + half * 32 + j);
+            c0 = __ffma2_rn(make_float2(fmaxf(h[j], 0.f), fmaxf(h[j + 1], 0.f)), make_float2(w4.x, w4.y), c0);
+            c1 = __ffma2_rn(make_float2(fmaxf(h[j + 2], 0.f), fmaxf(h[j + 3], 0.f)), make_float2(w4.z, w4.w), c1);
+          }
         }
+        const float a = (c0.x + c0.y) + (c1.x + c1.y);
         cl[s] = fmaxf(a, 0.f);
         mx = fmaxf(mx, cl[s]);
       }
       float den = 0.f;
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        cl[s] = expf(cl[s] - mx);
+        cl[s] = rexp(cl[s] - mx);
         den += cl[s];
       }
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        const float ws_ = cl[s] / den;
+        const float ws_ = rdiv(cl[s], den);
         cr = fmaf(rgb_s[s][0], ws_, cr), cg = fmaf(rgb_s[s][1], ws_, cg), cb = fmaf(rgb_s[s][2], ws_, cb);
       }
     }
@@ -482,11 +550,11 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
       if (valid) {
         const size_t o = (size_t)ray * p.out_stride + p.out_off + k;
         *reinterpret_cast<float4*>(p.out_raw + o * 4) = make_float4(cr, cg, cb, sigma);
-        p.out_z[o] = p.depth_inv ? 1.0f / z : z;
+        p.out_z[o] = p.depth_inv ? rdiv(1.0f, z) : z;
       }
     } else if (Ns == 2) {
       // two samples of a ray in lanes (2i, 2i+1): one xor-shuffle exchange per quantity
-      const float alpha = 1.f - expf(-sigma);
+      const float alpha = 1.f - rexp(-sigma);
       const float tr = 1.f - alpha + 1e-10f;
       const float tr_o = __shfl_xor_sync(0xffffffffu, tr, 1);
       const float wk = alpha * (k == 0 ? 1.f : tr_o);
@@ -494,11 +562,11 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
       const float cr_o = __shfl_xor_sync(0xffffffffu, cr, 1), cg_o = __shfl_xor_sync(0xffffffffu, cg, 1),
                   cb_o = __shfl_xor_sync(0xffffffffu, cb, 1), z_o = __shfl_xor_sync(0xffffffffu, z, 1);
       const float mx = fmaxf(wk, wk_o);
-      const float e = expf(wk - mx), e_o = expf(wk_o - mx);
+      const float e = rexp(wk - mx), e_o = rexp(wk_o - mx);
       if (valid) {
         if (k == 0) {
           const float den = e + e_o;                       // same order as the sequential sum over samples
-          const float wn0 = e / den, wn1 = e_o / den;
+          const float wn0 = rdiv(e, den), wn1 = rdiv(e_o, den);
           float ar = fmaf(wk_o, cr_o, wk * cr), ag = fmaf(wk_o, cg_o, wk * cg), ab = fmaf(wk_o, cb_o, wk * cb);
           if (p.white_bkgd) {
             const float bg = 1.f - (wn0 + wn1);
@@ -513,7 +581,7 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
       }
     } else {
       const int gbase = lane - k;                 // first lane of this ray's group (Ns | 32)
-      const float alpha = 1.f - expf(-sigma);
+      const float alpha = 1.f - rexp(-sigma);
       const float tr = 1.f - alpha + 1e-10f;
       float T = 1.f;
       for (int j = 0; j + 1 < Ns; ++j) {
@@ -529,10 +597,10 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
         ab = fmaf(wj, __shfl_sync(0xffffffffu, cb, gbase + j), ab);
         mx = fmaxf(mx, wj);
       }
-      const float e = expf(wk - mx);
+      const float e = rexp(wk - mx);
       float den = 0.f;
       for (int j = 0; j < Ns; ++j) den += __shfl_sync(0xffffffffu, e, gbase + j);
-      const float wn = e / den;
+      const float wn = rdiv(e, den);
       float dsum = 0.f, wsum = 0.f;
       const float wz = wn * z;
       for (int j = 0; j < Ns; ++j) {
