@@ -94,9 +94,20 @@ struct TcSmem {
 #ifndef RTC_FAST_MATH
 #define RTC_FAST_MATH 1
 #endif
+// (.ftz forms: the non-ftz approximations carry a range-fixup compare + scale around every MUFU)
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float rdiv(float a, float b) {
 #if RTC_FAST_MATH
-  return __fdividef(a, b);
+  return a * mufu_rcp(b);
 #else
   return a / b;
 #endif
@@ -104,7 +115,7 @@ __device__ __forceinline__ float rdiv(float a, float b) {
 __device__ __forceinline__ float rsqrt_(float x) {
 #if RTC_FAST_MATH
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 #else
   return sqrtf(x);
@@ -112,14 +123,16 @@ __device__ __forceinline__ float rsqrt_(float x) {
 }
 __device__ __forceinline__ float rexp(float x) {
 #if RTC_FAST_MATH
-  return __expf(x);
+  return mufu_ex2(x * 1.4426950408889634f);
 #else
   return expf(x);
 #endif
 }
 __device__ __forceinline__ float rsoftplus(float x) {      // log(1 + exp(x)), x <= 20
 #if RTC_FAST_MATH
-  return __logf(1.f + __expf(x));
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + mufu_ex2(x * 1.4426950408889634f)));
+  return r * 0.6931471805599453f;
 #else
   return log1pf(expf(x));
 #endif

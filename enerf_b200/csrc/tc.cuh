@@ -164,12 +164,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// round-to-nearest fp32 -> tf32 (the tensor core would otherwise truncate the low 13 mantissa bits)
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// round-to-nearest (ties away) fp32 -> tf32 for a tensor-core operand: the tensor core reads the top 19 bits of the 32-bit
+// container and ignores the low 13 mantissa bits, so adding half a tf32 ulp to the bit pattern IS cvt.rna.tf32.f32 for every
+// finite value (one integer add; the cvt instruction is emulated on this architecture: compare-with-infinity, add, mask,
+// select = 4 issue slots per value, ~20 % of the ray kernel's instructions).  Inf / NaN inputs do not occur on these paths.
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
 // ---- TMA ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
