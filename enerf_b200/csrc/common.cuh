@@ -50,6 +50,26 @@ static inline int device_sm_count() {
 }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// n / d for a run-time divisor d >= 1 and n < 2^31 as multiply-high + add + shift (Granlund-Montgomery): q = (umulhi(n, m) + n) >> l with
+// l = ceil(log2 d), m = floor(2^32 (2^l - d) / d) + 1.  An unsigned division by a run-time value costs ~20 instructions.
+struct FastDiv {
+  unsigned m, l;
+  static FastDiv make(unsigned d) {
+    FastDiv f;
+    f.l = 0;
+    while ((1ull << f.l) < d) ++f.l;
+    f.m = (unsigned)((((1ull << f.l) - d) << 32) / d + 1);
+    return f;
+  }
+  __host__ __device__ __forceinline__ unsigned div(unsigned n) const {
+#ifdef __CUDA_ARCH__
+    return (__umulhi(n, m) + n) >> l;
+#else
+    return (unsigned)((((unsigned long long)n * m) >> 32) + n) >> l;
+#endif
+  }
+};
+
 // torch.linspace(0, 1, steps) element i, same two-sided formula as ATen's RangeFactories kernel
 // (step = 1/(steps-1); lower half start + step*i, upper half end - step*(steps-1-i)).
 __host__ __device__ __forceinline__ float linspace01(int i, int steps) {

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const EnerfCam* __rest
                                                           const float* __restrict__ feat, int S, int hs, int ws,
                                                           const float* __restrict__ ends, int D, int h, int w,
                                                           int depth_inv, float* __restrict__ var_out, int x0, int y0, int wc,
-                                                          int hc) {
+                                                          int hc, FastDiv div_wc, FastDiv div_hc) {
   // SPLIT lanes share a voxel, each owning C/SPLIT channels of every tap
   constexpr int CH = C / SPLIT;                    // channels per thread
   constexpr int NV = CH / 4;                       // float4 per tap per thread
@@ -80,8 +80,9 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const EnerfCam* __rest
   if (t >= total) return;
   const int g = (int)(t % SPLIT);
   const unsigned vox = t / SPLIT;
-  const unsigned vrow = vox / (unsigned)wc;
-  const int x = x0 + (int)(vox - vrow * wc), y = y0 + (int)(vrow % (unsigned)hc), d = (int)(vrow / (unsigned)hc);
+  const unsigned vrow = div_wc.div(vox);            // division by a run-time extent as multiply-high + shift (host-made constants)
+  const unsigned dd = div_hc.div(vrow);
+  const int x = x0 + (int)(vox - vrow * wc), y = y0 + (int)(vrow - dd * hc), d = (int)dd;
   const int pix = y * w + x;
   const float depth = plane_depth(__ldg(ends + pix), __ldg(ends + (size_t)h * w + pix), d, D, depth_inv);
   const float inv_depth = 1.0f / depth;
@@ -106,19 +107,22 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const EnerfCam* __rest
       const float fx0 = floorf(ix), fy0 = floorf(iy);
       const int x0 = (int)fx0, y0 = (int)fy0;
       const float txr = (fx0 + 1.f) - ix, txl = ix - fx0, tyb = (fy0 + 1.f) - iy, tyt = iy - fy0;
-      const float wgt[4] = {txr * tyb, txl * tyb, txr * tyt, txl * tyt};
-      const bool okx[2] = {x0 >= 0, x0 + 1 < ws}, oky[2] = {y0 >= 0, y0 + 1 < hs};
-      const float* base = feat + ((size_t)s * hs * ws) * C + g * CH;
+      // zeros padding without branches: a tap outside the image gets weight 0 and a clamped (valid) address -- it adds +0,
+      // exactly what skipping it did; the four loads of a view are unconditional and independent
+      const bool okx0 = x0 >= 0, okx1 = x0 + 1 < ws, oky0 = y0 >= 0, oky1 = y0 + 1 < hs;
+      const float wgt[4] = {(okx0 && oky0) ? txr * tyb : 0.f, (okx1 && oky0) ? txl * tyb : 0.f, (okx0 && oky1) ? txr * tyt : 0.f,
+                            (okx1 && oky1) ? txl * tyt : 0.f};
+      const int xa = max(x0, 0), xb = min(x0 + 1, ws - 1), ya = max(y0, 0), yb = min(y0 + 1, hs - 1);
+      const float* base = feat + ((size_t)s * hs * ws) * C + g * CH;          // (32-bit offsets inside a view: hs * ws * C < 2^31, checked by the launcher)
+      const float* pt[4] = {base + (unsigned)((ya * ws + xa) * C), base + (unsigned)((ya * ws + xb) * C), base + (unsigned)((yb * ws + xa) * C),
+                            base + (unsigned)((yb * ws + xb) * C)};
 #pragma unroll
       for (int tp = 0; tp < 4; ++tp) {
-        if (oky[tp >> 1] && okx[tp & 1]) {
-          const float* p = base + ((size_t)(y0 + (tp >> 1)) * ws + (x0 + (tp & 1))) * C;
-          const float wv = wgt[tp];
+        const float wv = wgt[tp];
 #pragma unroll
-          for (int q = 0; q < NV; ++q) {
-            const float4 a = ldg4(p + 4 * q);
-            v[q].x = fmaf(a.x, wv, v[q].x), v[q].y = fmaf(a.y, wv, v[q].y), v[q].z = fmaf(a.z, wv, v[q].z), v[q].w = fmaf(a.w, wv, v[q].w);
-          }
+        for (int q = 0; q < NV; ++q) {
+          const float4 a = ldg4(pt[tp] + 4 * q);
+          v[q].x = fmaf(a.x, wv, v[q].x), v[q].y = fmaf(a.y, wv, v[q].y), v[q].z = fmaf(a.z, wv, v[q].z), v[q].w = fmaf(a.w, wv, v[q].w);
         }
       }
     }
@@ -128,16 +132,18 @@ __global__ void __launch_bounds__(256) cost_volume_kernel(const EnerfCam* __rest
       s2[q].x += v[q].x * v[q].x, s2[q].y += v[q].y * v[q].y, s2[q].z += v[q].z * v[q].z, s2[q].w += v[q].w * v[q].w;
     }
   }
-  const float fS = (float)S;
+  // var = E[x^2] - E[x]^2 (utils.py:341-345); the 2 C/SPLIT divisions by S as multiplications by 1/S (<= 1 ulp per term; eight IEEE
+  // divisions were a sixth of this issue-bound kernel's instructions)
+  const float invS = 1.0f / (float)S;
   float4* o = reinterpret_cast<float4*>(var_out + (size_t)vox * C + g * CH);
 #pragma unroll
   for (int q = 0; q < NV; ++q) {
     float4 r;
     float m;
-    m = s1[q].x / fS, r.x = s2[q].x / fS - m * m;
-    m = s1[q].y / fS, r.y = s2[q].y / fS - m * m;
-    m = s1[q].z / fS, r.z = s2[q].z / fS - m * m;
-    m = s1[q].w / fS, r.w = s2[q].w / fS - m * m;
+    m = s1[q].x * invS, r.x = s2[q].x * invS - m * m;
+    m = s1[q].y * invS, r.y = s2[q].y * invS - m * m;
+    m = s1[q].z * invS, r.z = s2[q].z * invS - m * m;
+    m = s1[q].w * invS, r.w = s2[q].w * invS - m * m;
     o[q] = r;
   }
 }
@@ -308,8 +314,11 @@ static int cost_volume_launch(const EnerfCam* cam, int level, const float* feat,
   const int split = (C == 32) ? 8 : (C >= 16 ? 2 : 1);
   const long long total = (long long)D * hc * wc * split;
   ENERF_REQUIRE(total < (1ll << 31), ENERF_EUNSUPPORTED, "cost_volume: %lld work items exceed the 32-bit index range", total);
+  ENERF_REQUIRE((long long)hs * ws * C < (1ll << 31), ENERF_EUNSUPPORTED, "cost_volume: a %dx%dx%d source view exceeds the 32-bit offset range", hs, ws, C);
   const unsigned blocks = (unsigned)((total + 255) / 256);
-#define CV_LAUNCH(C_, SP_) cost_volume_kernel<C_, SP_><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance, x0, y0, wc, hc)
+  const FastDiv div_wc = FastDiv::make((unsigned)wc), div_hc = FastDiv::make((unsigned)hc);
+#define CV_LAUNCH(C_, SP_) \
+  cost_volume_kernel<C_, SP_><<<blocks, 256, 0, stream>>>(cam, level, feat, S, hs, ws, ends, D, h, w, depth_inv, variance, x0, y0, wc, hc, div_wc, div_hc)
   if (C == 8 && split == 2) CV_LAUNCH(8, 2);
   else if (C == 8) CV_LAUNCH(8, 1);
   else if (C == 16 && split == 4) CV_LAUNCH(16, 4);

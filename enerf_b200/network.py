@@ -100,6 +100,16 @@ class Network(nn.Module):
         self._packed = None
         return super().train(mode)
 
+    def _pack_img_feat(self, i, lv, feats, src, S, H, W, dev):
+        """(S,Hr,Wr,feat_ch+4) records [features | un-preprocessed rgb | 0] the ray kernels gather from (csrc/feature_net.cu)."""
+        Hr, Wr = int(H * lv.render_scale), int(W * lv.render_scale)
+        imf = feats[lv.im_feat_level]
+        if imf.shape[1] != Hr or imf.shape[2] != Wr or imf.shape[3] != lv.feat_ch:
+            raise ValueError(f"level {i}: image features {tuple(imf.shape)} do not match render size {Hr}x{Wr}x{lv.feat_ch}")
+        img = self._scratch(f"img{i}", S * Hr * Wr * (lv.feat_ch + 4), dev).view(S, Hr, Wr, lv.feat_ch + 4)
+        capi.pack_img_feat(imf, src, img)
+        return img
+
     # ---------------------------------------------------------------- scratch buffers (reused)
     def _scratch(self, name, numel, device, dtype=torch.float32):
         t = self._buffers_cache.get(name)
@@ -179,6 +189,7 @@ class Network(nn.Module):
         tcs = self.precision == "tf32"
         fork = self.overlap and not self.profile and len(levels) > 1
         tail_done = None
+        prepacked = {}
         if fork:
             main = torch.cuda.current_stream()
             if self._side is None or self._side.device != dev:
@@ -189,6 +200,11 @@ class Network(nn.Module):
             with torch.cuda.stream(self._side):
                 self._side.wait_event(trunk_done)
                 capi.feature_net(pk["feature"], src, feats[0], feats[1], feats[2], ws, tensor_cores=tcs, part=2)
+                # the (feature | rgb) records of the render levels depend on the pyramid and the source images only: pack them here,
+                # next to the level-0 chain, instead of serially in front of the ray launch
+                for i, lv in enumerate(levels):
+                    if lv.render_if and lv.render_scale == lv.im_ibr_scale:
+                        prepacked[i] = self._pack_img_feat(i, lv, feats, src, S, H, W, dev)
                 tail_done = torch.cuda.Event()
                 tail_done.record(self._side)
             for tns in (feats[1], feats[2], ws, src):
@@ -249,14 +265,10 @@ class Network(nn.Module):
                 raise NotImplementedError("render_scale != im_ibr_scale (feature up-sampling in render_rays, network.py:30-32) "
                                           "is not used by any shipped config and is not implemented")
             Hr, Wr = int(H * lv.render_scale), int(W * lv.render_scale)
-            if tail_done is not None and lv.im_feat_level > 0:
+            if tail_done is not None and (lv.im_feat_level > 0 or i in prepacked):
                 torch.cuda.current_stream().wait_event(tail_done)
                 tail_done = None
-            imf = feats[lv.im_feat_level]
-            if imf.shape[1] != Hr or imf.shape[2] != Wr or imf.shape[3] != lv.feat_ch:
-                raise ValueError(f"level {i}: image features {tuple(imf.shape)} do not match render size {Hr}x{Wr}x{lv.feat_ch}")
-            img = self._scratch(f"img{i}", S * Hr * Wr * (lv.feat_ch + 4), dev).view(S, Hr, Wr, lv.feat_ch + 4)
-            capi.pack_img_feat(imf, src, img)
+            img = prepacked[i] if i in prepacked else self._pack_img_feat(i, lv, feats, src, S, H, W, dev)
             self._mark(f"pack_img_feat_{i}")
             if f"rays_{i}" in batch:
                 rays = batch[f"rays_{i}"][b].float().contiguous()
