@@ -59,6 +59,7 @@ _SIGS = {
     "enerf_tc_conv_debug": (_i, [_vp]),
     "enerf_tc_conv_tune": (_i, [_i, _i, _i]),
     "enerf_tc_conv_fold_rule": (_i, [_i]),
+    "enerf_fastdiv_check": (ctypes.c_uint, [ctypes.c_uint, ctypes.c_uint]),
     "enerf_tc_conv2_tune": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "enerf_tc_conv2_fuse_lateral": (_i, [_i]),
     "enerf_tc_conv2_debug": (_i, [_vp]),

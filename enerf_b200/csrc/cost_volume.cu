@@ -369,3 +369,6 @@ extern "C" int enerf_depth_regress_window(const float* depth_prob, const int* wi
   ENERF_CHECK_LAUNCH("depth_regress_window");
   return ENERF_OK;
 }
+
+// Test hook (CPU): n / d through the same FastDiv constants the kernels above use for their run-time extents.
+extern "C" unsigned enerf_fastdiv_check(unsigned d, unsigned n) { return enerf::FastDiv::make(d).div(n); }

@@ -154,7 +154,12 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
   __shared__ uint32_t tmem_base_s;
   const RayParams& p = P.r;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  constexpr uint32_t TMEM_COLS = (S * 64 <= 128) ? 128 : (S * 64 <= 256) ? 256 : 512;   // G5 holds one 64-column accumulator per view
+  // color.0 FACTORED (S <= 3, where the extra accumulator still fits 2 x 256 TMEM columns per SM): its view-shared K (x | vox | img: 88 of
+  // the 104 columns) is multiplied ONCE into accumulator 0 and only the per-view [f | dir] K = 16 per view -- 11 + 2 S MMAs instead of 13 S
+  // (17 vs 39 at S = 3); the epilogue adds the two accumulators before the ReLU.
+  constexpr bool FACT = (S <= 3);
+  constexpr int G5_ACCS = FACT ? S + 1 : S;
+  constexpr uint32_t TMEM_COLS = (G5_ACCS * 64 <= 128) ? 128 : (G5_ACCS * 64 <= 256) ? 256 : 512;   // G5 holds 64-column accumulators
 
   // ---- one-time setup: weights, cameras, barrier, TMEM ----
   for (int e = t; e < TcW::total; e += 128) sw[e] = __ldg(P.wblob + e);
@@ -509,11 +514,23 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
      {
       const uint32_t id = tc::idesc_tf32(128, 64);
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
+      if constexpr (FACT) {
 #pragma unroll
-        for (int kk = 0; kk < 11; ++kk) tc::mma_tf32_elect(tmem_u + s * 64, a_desc(2 * kk), b_desc(TcW::bc_shared, 2 * kk, 64), id, kk > 0);
+        for (int kk = 0; kk < 11; ++kk) tc::mma_tf32_elect(tmem_u, a_desc(2 * kk), b_desc(TcW::bc_shared, 2 * kk, 64), id, kk > 0);
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) tc::mma_tf32_elect(tmem_u + s * 64, a_desc(SM::P_CHUNKS + 4 * s + 2 * kk), b_desc(TcW::bc_view, 2 * kk, 64), id, 1);
+        for (int s = 0; s < S; ++s) {
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            tc::mma_tf32_elect(tmem_u + 64 + s * 64, a_desc(SM::P_CHUNKS + 4 * s + 2 * kk), b_desc(TcW::bc_view, 2 * kk, 64), id, kk > 0);
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+#pragma unroll
+          for (int kk = 0; kk < 11; ++kk) tc::mma_tf32_elect(tmem_u + s * 64, a_desc(2 * kk), b_desc(TcW::bc_shared, 2 * kk, 64), id, kk > 0);
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) tc::mma_tf32_elect(tmem_u + s * 64, a_desc(SM::P_CHUNKS + 4 * s + 2 * kk), b_desc(TcW::bc_view, 2 * kk, 64), id, 1);
+        }
       }
       tc::mma_commit_elect(&bar);
      }
@@ -525,24 +542,55 @@ __global__ void __launch_bounds__(128, (S <= 4) ? 2 : 1) render_rays_tc_kernel(c
     {
       float cl[S];
       float mx = -INFINITY;
+      if constexpr (FACT) {
+        float2 c0[S], c1[S];
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-        float2 c0 = make_float2(sw[TcW::v_b2], 0.f), c1 = make_float2(0.f, 0.f);
+        for (int s = 0; s < S; ++s) c0[s] = make_float2(sw[TcW::v_b2], 0.f), c1[s] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float h[32];
-          tc::tmem_ld32(tmem_row + s * 64 + half * 32, h);
-          tc::tmem_ld_wait();
+        for (int qt = 0; qt < 4; ++qt) {           // 16 of the 64 columns at a time (registers: the kernel stays under 200)
+          float sh[16];                            // the view-shared product (accumulator 0)
+          tc::tmem_ld16(tmem_row + qt * 16, sh);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {       // bias in the accumulator; packed FMAs on two chains
-            const float4 w4 = *reinterpret_cast<const float4*>(sw + TcW::v_w2 + half * 32 + j);
-            c0 = __ffma2_rn(make_float2(fmaxf(h[j], 0.f), fmaxf(h[j + 1], 0.f)), make_float2(w4.x, w4.y), c0);
-            c1 = __ffma2_rn(make_float2(fmaxf(h[j + 2], 0.f), fmaxf(h[j + 3], 0.f)), make_float2(w4.z, w4.w), c1);
+          for (int s = 0; s < S; ++s) {
+            float h[16];
+            tc::tmem_ld16(tmem_row + 64 + s * 64 + qt * 16, h);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {       // bias in the per-view accumulator; packed adds / FMAs on two chains
+              const float4 w4 = *reinterpret_cast<const float4*>(sw + TcW::v_w2 + qt * 16 + j);
+              const float2 a0 = __fadd2_rn(make_float2(h[j], h[j + 1]), make_float2(sh[j], sh[j + 1]));
+              const float2 a1 = __fadd2_rn(make_float2(h[j + 2], h[j + 3]), make_float2(sh[j + 2], sh[j + 3]));
+              c0[s] = __ffma2_rn(make_float2(fmaxf(a0.x, 0.f), fmaxf(a0.y, 0.f)), make_float2(w4.x, w4.y), c0[s]);
+              c1[s] = __ffma2_rn(make_float2(fmaxf(a1.x, 0.f), fmaxf(a1.y, 0.f)), make_float2(w4.z, w4.w), c1[s]);
+            }
           }
         }
-        const float a = (c0.x + c0.y) + (c1.x + c1.y);
-        cl[s] = fmaxf(a, 0.f);
-        mx = fmaxf(mx, cl[s]);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const float a = (c0[s].x + c0[s].y) + (c1[s].x + c1[s].y);
+          cl[s] = fmaxf(a, 0.f);
+          mx = fmaxf(mx, cl[s]);
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          float2 c0 = make_float2(sw[TcW::v_b2], 0.f), c1 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float h[32];
+            tc::tmem_ld32(tmem_row + s * 64 + half * 32, h);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {       // bias in the accumulator; packed FMAs on two chains
+              const float4 w4 = *reinterpret_cast<const float4*>(sw + TcW::v_w2 + half * 32 + j);
+              c0 = __ffma2_rn(make_float2(fmaxf(h[j], 0.f), fmaxf(h[j + 1], 0.f)), make_float2(w4.x, w4.y), c0);
+              c1 = __ffma2_rn(make_float2(fmaxf(h[j + 2], 0.f), fmaxf(h[j + 3], 0.f)), make_float2(w4.z, w4.w), c1);
+            }
+          }
+          const float a = (c0.x + c0.y) + (c1.x + c1.y);
+          cl[s] = fmaxf(a, 0.f);
+          mx = fmaxf(mx, cl[s]);
+        }
       }
       float den = 0.f;
 #pragma unroll

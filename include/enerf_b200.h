@@ -308,6 +308,9 @@ ENERF_API int enerf_tc_conv_tune(int tz, int ty, int fold);
  * (enerf_b200/packing.py::FOLD_RULE; enerf_b200.capi.tc_conv_fold_rule sets both and the caller re-packs). */
 ENERF_API int enerf_tc_conv_fold_rule(int level);
 
+/* Test hook (no GPU): n / d (d >= 1, n < 2^31) through the multiply-high constants the kernels use for divisions by run-time extents. */
+ENERF_API unsigned enerf_fastdiv_check(unsigned d, unsigned n);
+
 /* Diagnostic: like enerf_tc_conv_debug for enerf_render_rays_tc (32 x u64: 16 stamps for each of
  * the first two tiles of CTA 0). */
 ENERF_API int enerf_render_rays_debug(unsigned long long* buf);

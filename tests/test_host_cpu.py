@@ -201,3 +201,16 @@ def test_band_rows_cover_the_receptive_field():
     with pytest.raises(ValueError):
         net._band_rows(lv, H, h, True)
     net.ray_rows = None
+
+
+def test_fastdiv_constants_divide_exactly():
+    """Divisions by run-time extents inside the kernels (cost volume: voxel -> (d, y, x)) use multiply-high + shift constants made on
+    the host (csrc/common.cuh FastDiv): exact for every divisor >= 1 and every n < 2^31."""
+    import random
+    from enerf_b200 import capi
+    f = capi.lib().enerf_fastdiv_check
+    rnd = random.Random(7)
+    for d in list(range(1, 70)) + [80, 160, 320, 640, 1088, 1920, 4095, 4096, 4097, 65537, (1 << 20) + 3, (1 << 30) + 1, (1 << 31) - 1]:
+        for n in [0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 31) - 1, (1 << 31) - 2] + [rnd.randrange(0, 1 << 31) for _ in range(200)]:
+            if 0 <= n < (1 << 31):
+                assert f(d, n) == n // d, (d, n)
