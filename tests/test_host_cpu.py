@@ -214,3 +214,26 @@ def test_fastdiv_constants_divide_exactly():
         for n in [0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 31) - 1, (1 << 31) - 2] + [rnd.randrange(0, 1 << 31) for _ in range(200)]:
             if 0 <= n < (1 << 31):
                 assert f(d, n) == n // d, (d, n)
+
+
+def test_tf32_rounding_by_integer_add_is_round_to_nearest_ties_away():
+    """csrc/tc.cuh::to_tf32 and packing.tf32_round round an fp32 value to TF32 by adding half a TF32 ulp (0x1000) to the bit pattern;
+    the tensor core then ignores the low 13 mantissa bits.  Checked here in VALUE space against an independent float64
+    construction of round-to-nearest, ties away from zero, on a 10-bit mantissa (= cvt.rna.tf32.f32) -- including ties, values
+    that carry into the next exponent, and subnormal-free small magnitudes."""
+    import numpy as np
+    from enerf_b200 import packing
+    rnd = np.random.default_rng(11)
+    x = np.concatenate([rnd.standard_normal(20000).astype(np.float32) * np.float32(10.0) ** rnd.integers(-20, 20, 20000).astype(np.float32),
+                        np.float32([1.0, -1.0, 1.0 + 2.0 ** -11, 1.0 + 3 * 2.0 ** -11, -(1.0 + 2.0 ** -11), 2.0 - 2.0 ** -12, 0.0,
+                                    1.9999999, 3.0e38 * 0.5, 1.2e-38 * 4])])
+    got = packing.tf32_round(torch.from_numpy(x)).numpy().astype(np.float64)
+    xd = np.abs(x.astype(np.float64))
+    nz = xd > 0
+    e = np.floor(np.log2(xd, where=nz, out=np.zeros_like(xd)))
+    ulp = np.exp2(e - 10)
+    lo = np.floor(xd / ulp) * ulp
+    hi = lo + ulp
+    ref = np.where(xd - lo < hi - xd, lo, hi)          # ties (equal distances) go to hi = away from zero
+    ref = np.where(nz, np.sign(x.astype(np.float64)) * ref, 0.0)
+    assert np.array_equal(got, ref)
