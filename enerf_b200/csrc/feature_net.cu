@@ -46,59 +46,80 @@ __global__ void __launch_bounds__(256) lateral_upadd_kernel(const float* __restr
       wreg[2 * k + 1] = *reinterpret_cast<const float4*>(w_s + k * 32 + 16 + g0 * 4);
     }
   }
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+  // CIN = 16 (lat1): every thread takes ITEMS = 2 work items (same channel group g, `half` items apart) and reads each weight vector
+  // from shared memory ONCE for both -- the weight reads were a third of this L1-bound kernel's data-pipe wavefronts.
+  constexpr int ITEMS = (CIN == 16) ? 2 : 1;
+  const int half = (ITEMS == 2) ? ((total / 2 + 3) & ~3) : total;      // multiple of 4: both items of a thread share g
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < half; t += gridDim.x * blockDim.x) {
     const int g = t & 3;
-    const int pix = t >> 2;
-    const int x = pix % W, row = pix / W, y = row % H, n = row / H;
-    float acc[8];
+    int pixs[ITEMS];
+    bool live[ITEMS];
+    float acc[ITEMS][8];
+    float xin[ITEMS][CIN];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = b_s[(c < 4 ? 0 : 12) + g * 4 + c];
-    const float* ip = lat_in + (size_t)pix * CIN;
+    for (int it = 0; it < ITEMS; ++it) {
+      const int ti = t + it * half;
+      live[it] = ti < total;
+      pixs[it] = (live[it] ? ti : t) >> 2;
 #pragma unroll
-    for (int q = 0; q < CIN / 4; ++q) {
-      const float4 v = ldg4(ip + 4 * q);
-      const float xv[4] = {v.x, v.y, v.z, v.w};
+      for (int c = 0; c < 8; ++c) acc[it][c] = b_s[(c < 4 ? 0 : 12) + g * 4 + c];
+      const float* ip = lat_in + (size_t)pixs[it] * CIN;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 w0, w1;
-        if constexpr (CIN == 8) {   // this thread's 8 x 8 weight slice lives in registers (g is loop-invariant)
-          w0 = wreg[2 * (4 * q + j)], w1 = wreg[2 * (4 * q + j) + 1];
-        } else {
-          w0 = *reinterpret_cast<const float4*>(w_s + (4 * q + j) * 32 + g * 4);
-          w1 = *reinterpret_cast<const float4*>(w_s + (4 * q + j) * 32 + 16 + g * 4);
-        }
-        acc[0] = fmaf(xv[j], w0.x, acc[0]);
-        acc[1] = fmaf(xv[j], w0.y, acc[1]);
-        acc[2] = fmaf(xv[j], w0.z, acc[2]);
-        acc[3] = fmaf(xv[j], w0.w, acc[3]);
-        acc[4] = fmaf(xv[j], w1.x, acc[4]);
-        acc[5] = fmaf(xv[j], w1.y, acc[5]);
-        acc[6] = fmaf(xv[j], w1.z, acc[6]);
-        acc[7] = fmaf(xv[j], w1.w, acc[7]);
+      for (int q = 0; q < CIN / 4; ++q) {
+        const float4 v = ldg4(ip + 4 * q);
+        xin[it][4 * q] = v.x, xin[it][4 * q + 1] = v.y, xin[it][4 * q + 2] = v.z, xin[it][4 * q + 3] = v.w;
       }
     }
-    // bilinear x2 with align_corners=True (ATen upsample_bilinear2d lambdas)
-    const float h1r = rh * (float)y, w1r = rw * (float)x;
-    const int h1 = (int)h1r, w1 = (int)w1r;
-    const int h1p = (h1 < hi - 1) ? 1 : 0, w1p = (w1 < wi - 1) ? 1 : 0;
-    const float h1l = h1r - (float)h1, h0l = 1.f - h1l, w1l = w1r - (float)w1, w0l = 1.f - w1l;
-    const float* u00 = up_in + (((size_t)n * hi + h1) * wi + w1) * 32 + g * 4;
-    const float* u01 = u00 + (size_t)w1p * 32;
-    const float* u10 = u00 + (size_t)h1p * wi * 32;
-    const float* u11 = u10 + (size_t)w1p * 32;
-    float up[8];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const float4 a = ldg4(u00 + 16 * q), b = ldg4(u01 + 16 * q), c = ldg4(u10 + 16 * q), dd = ldg4(u11 + 16 * q);
-      up[4 * q + 0] = h0l * (w0l * a.x + w1l * b.x) + h1l * (w0l * c.x + w1l * dd.x);
-      up[4 * q + 1] = h0l * (w0l * a.y + w1l * b.y) + h1l * (w0l * c.y + w1l * dd.y);
-      up[4 * q + 2] = h0l * (w0l * a.z + w1l * b.z) + h1l * (w0l * c.z + w1l * dd.z);
-      up[4 * q + 3] = h0l * (w0l * a.w + w1l * b.w) + h1l * (w0l * c.w + w1l * dd.w);
+    for (int k = 0; k < CIN; ++k) {
+      float4 w0, w1;
+      if constexpr (CIN == 8) {   // this thread's 8 x 8 weight slice lives in registers (g is loop-invariant)
+        w0 = wreg[2 * k], w1 = wreg[2 * k + 1];
+      } else {
+        w0 = *reinterpret_cast<const float4*>(w_s + k * 32 + g * 4);
+        w1 = *reinterpret_cast<const float4*>(w_s + k * 32 + 16 + g * 4);
+      }
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const float xv = xin[it][k];
+        acc[it][0] = fmaf(xv, w0.x, acc[it][0]);
+        acc[it][1] = fmaf(xv, w0.y, acc[it][1]);
+        acc[it][2] = fmaf(xv, w0.z, acc[it][2]);
+        acc[it][3] = fmaf(xv, w0.w, acc[it][3]);
+        acc[it][4] = fmaf(xv, w1.x, acc[it][4]);
+        acc[it][5] = fmaf(xv, w1.y, acc[it][5]);
+        acc[it][6] = fmaf(xv, w1.z, acc[it][6]);
+        acc[it][7] = fmaf(xv, w1.w, acc[it][7]);
+      }
     }
-    float4* o = reinterpret_cast<float4*>(out + (size_t)pix * 32 + g * 4);
-    // reference order: interpolate(x) + lateral(y)   (feature_net.py:25)
-    o[0] = make_float4(up[0] + acc[0], up[1] + acc[1], up[2] + acc[2], up[3] + acc[3]);
-    o[4] = make_float4(up[4] + acc[4], up[5] + acc[5], up[6] + acc[6], up[7] + acc[7]);
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      if (!live[it]) continue;
+      const int pix = pixs[it];
+      const int x = pix % W, row = pix / W, y = row % H, n = row / H;
+      // bilinear x2 with align_corners=True (ATen upsample_bilinear2d lambdas)
+      const float h1r = rh * (float)y, w1r = rw * (float)x;
+      const int h1 = (int)h1r, w1 = (int)w1r;
+      const int h1p = (h1 < hi - 1) ? 1 : 0, w1p = (w1 < wi - 1) ? 1 : 0;
+      const float h1l = h1r - (float)h1, h0l = 1.f - h1l, w1l = w1r - (float)w1, w0l = 1.f - w1l;
+      const float* u00 = up_in + (((size_t)n * hi + h1) * wi + w1) * 32 + g * 4;
+      const float* u01 = u00 + (size_t)w1p * 32;
+      const float* u10 = u00 + (size_t)h1p * wi * 32;
+      const float* u11 = u10 + (size_t)w1p * 32;
+      float up[8];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 a = ldg4(u00 + 16 * q), b = ldg4(u01 + 16 * q), c = ldg4(u10 + 16 * q), dd = ldg4(u11 + 16 * q);
+        up[4 * q + 0] = h0l * (w0l * a.x + w1l * b.x) + h1l * (w0l * c.x + w1l * dd.x);
+        up[4 * q + 1] = h0l * (w0l * a.y + w1l * b.y) + h1l * (w0l * c.y + w1l * dd.y);
+        up[4 * q + 2] = h0l * (w0l * a.z + w1l * b.z) + h1l * (w0l * c.z + w1l * dd.z);
+        up[4 * q + 3] = h0l * (w0l * a.w + w1l * b.w) + h1l * (w0l * c.w + w1l * dd.w);
+      }
+      float4* o = reinterpret_cast<float4*>(out + (size_t)pix * 32 + g * 4);
+      // reference order: interpolate(x) + lateral(y)   (feature_net.py:25)
+      o[0] = make_float4(up[0] + acc[it][0], up[1] + acc[it][1], up[2] + acc[it][2], up[3] + acc[it][3]);
+      o[4] = make_float4(up[4] + acc[it][4], up[5] + acc[it][5], up[6] + acc[it][6], up[7] + acc[it][7]);
+    }
   }
 }
 
@@ -231,7 +252,7 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
   if (part == 1) return ENERF_OK;
   {
     const long long total = (long long)S * H2 * W2 * 4;
-    const int blocks = (int)((total + 255) / 256);
+    const int blocks = (int)((total / 2 + 3 + 255) / 256);      // two work items per thread (see the kernel)
     lateral_upadd_kernel<16><<<blocks, 256, 0, stream>>>(ws.c1, wts[14], wts[15], feat_l0, ws.f1, S, H2, W2);
     ENERF_CHECK_LAUNCH("feature_net.lat1");
   }

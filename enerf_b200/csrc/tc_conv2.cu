@@ -17,6 +17,7 @@
 //                                    then hand the accumulator back
 //     The accumulators are double buffered in TMEM (2 x n_mt x N columns), so the epilogue of tile i runs under the
 //     MMAs of tile i+1, and the ring keeps 2-4 boxes in flight.  The layer's weights are loaded once per CTA.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -660,7 +661,17 @@ static int tc_conv2_plan(const TcConvLayer& L, int Dn, int Hn, int Wn, bool fold
   }
   if (L.kind == 0 && L.KH == 1) P.TY = 8;
   if (L.kind == 1) P.TZ = 2, P.TY = (P.N <= 64) ? 3 : 4;
-  if (lat) P.TY = 7;
+  // fused lateral: 11 rows (13 x 34 halo pixels, 3 M-tiles = one fold batch) is the tallest tile whose two operand slots + two source
+  // slots fit 216 KB; against 7 rows the producer's halo overhead drops 1.29 -> 1.18 and the per-tile fixed costs amortise:
+  // 12.7 -> 10.4 ns per pixel in the fused launch (profiles/r2_conv2_timeline.md).  ENERF_B200_LAT_TY overrides (A/B).
+  if (lat) {
+    static const int lat_ty = [] {
+      const char* e = getenv("ENERF_B200_LAT_TY");
+      const int v = e ? atoi(e) : 0;
+      return (v >= 2 && v <= 15) ? v : 11;
+    }();
+    P.TY = lat_ty;
+  }
   if (stride == 2) {
     if (is2d) P.TY = 7;
     else P.TZ = 2, P.TY = 3;

@@ -25,8 +25,11 @@ out = {}
 for rule in (2, 1):
     capi.tc_conv_fold_rule(rule)
     pk = packing.pack_feature_net(sd, torch.device("cuda"), tensor_cores=True)
-    for fuse in (8, 6, 4, False):
+    for fuse, ty in ((8, 0), (6, 0), (6, 11), (4, 0), (False, 0)):
+        if ty and rule != 2:
+            continue
         capi.tc_conv2_fuse_lateral(fuse)
+        capi.tc_conv2_tune(ty=ty)          # (forces the tile height of EVERY tc_conv2 layer: compare the fused launch's stamps, not the total)
         buf = torch.zeros(3 * 16 * 8, dtype=torch.int64, device="cuda")
         for it in range(4):
             capi.tc_conv2_debug_lateral(buf if it == 3 else None)
@@ -40,7 +43,7 @@ for rule in (2, 1):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
-        key = f"rule{rule}.{'prod%d' % fuse if fuse else 'separate'}"
+        key = f"rule{rule}.{'prod%d' % fuse if fuse else 'separate'}" + (f".ty{ty}" if ty else "")
         rep = {"feature_net_ms": ms}
         if fuse:
             t = buf.cpu().view(3, 16, 8)
@@ -56,5 +59,6 @@ for rule in (2, 1):
             print("   epilogue [start, acc full, acc released, stored]                 ", rep["epilogue"][:6])
 capi.tc_conv_fold_rule(2)
 capi.tc_conv2_fuse_lateral(True)
+capi.tc_conv2_tune()
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/fused_lat_timeline.json", "w"), indent=1)
