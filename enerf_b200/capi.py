@@ -31,6 +31,7 @@ _SIGS = {
     "enerf_generate_rays": (_i, [_vp, _vp, ctypes.c_float, _i, _i, _i, _vp, _vp]),
     "enerf_feature_net_workspace_bytes": (_sz, [_i, _i, _i]),
     "enerf_feature_net": (_i, [ctypes.POINTER(_vp), _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "enerf_feature_net_packed": (_i, [ctypes.POINTER(_vp), _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     "enerf_pack_img_feat": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "enerf_depth_hypotheses": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "enerf_cost_volume": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
@@ -137,12 +138,18 @@ def feature_net_workspace_bytes(S, H, W):
     return lib().enerf_feature_net_workspace_bytes(S, H, W)
 
 
-def feature_net(weights, src_inps, feat_l0, feat_l1, feat_l2, workspace, tensor_cores=False, part=0):
+def feature_net(weights, src_inps, feat_l0, feat_l1, feat_l2, workspace, tensor_cores=False, part=0, img_feat_rgb=None):
+    """img_feat_rgb: optional (S,H,W,12) tensor that receives the [level-2 features | rgb | 0] records of pack_img_feat, written by
+    the fused lat0 + smooth0 launch itself on the tensor-core path (by the pack kernel otherwise); filled by part 0 and part 2."""
     S, _, H, W = src_inps.shape
-    _check(lib().enerf_feature_net(ptr_array(weights), len(weights), ptr(src_inps), S, H, W, ptr(feat_l0), ptr(feat_l1),
-                                   ptr(feat_l2), workspace.data_ptr(), workspace.numel() * workspace.element_size(),
-                                   int(tensor_cores), part, stream()),
-           "enerf_feature_net", launches={0: 11, 1: 7, 2: 4}[part] - (1 if (tensor_cores and part != 1 and _FUSE_LAT and _CONV_IMPL != 1) else 0))
+    fused = bool(tensor_cores and part != 1 and _FUSE_LAT and _CONV_IMPL != 1)
+    launches = {0: 11, 1: 7, 2: 4}[part] - (1 if fused else 0) + (1 if (img_feat_rgb is not None and part != 1 and not fused) else 0)
+    if img_feat_rgb is not None and tuple(img_feat_rgb.shape) != (S, H, W, 12):
+        raise ValueError(f"img_feat_rgb must be ({S},{H},{W},12), got {tuple(img_feat_rgb.shape)}")
+    _check(lib().enerf_feature_net_packed(ptr_array(weights), len(weights), ptr(src_inps), S, H, W, ptr(feat_l0), ptr(feat_l1),
+                                          ptr(feat_l2), ptr(img_feat_rgb, True), workspace.data_ptr(),
+                                          workspace.numel() * workspace.element_size(), int(tensor_cores), part, stream()),
+           "enerf_feature_net_packed", launches=launches)
 
 
 def pack_img_feat(feat, src_inps, out):

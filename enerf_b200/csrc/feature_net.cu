@@ -193,6 +193,16 @@ extern "C" size_t enerf_feature_net_workspace_bytes(int n_views, int H, int W) {
 extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const float* src_inps, int S, int H, int W,
                                  float* feat_l0, float* feat_l1, float* feat_l2, void* workspace, size_t workspace_bytes,
                                  int tensor_cores, int part, void* stream_) {
+  return enerf_feature_net_packed(wts, n_weights, src_inps, S, H, W, feat_l0, feat_l1, feat_l2, nullptr, workspace, workspace_bytes, tensor_cores, part,
+                                  stream_);
+}
+
+// ... and, when img_feat_rgb != NULL, the (S,H,W,12) records [level-2 features | rgb * 0.5 + 0.5 | 0] of enerf_pack_img_feat at the
+// features' own resolution: written by the fused lat0 + smooth0 launch's epilogue on the tensor-core path (no extra kernel, feat_l2 is
+// not re-read), by the pack kernel otherwise.  Bit-identical to enerf_pack_img_feat(feat_l2, 8, src_inps, ..., H, W).
+extern "C" int enerf_feature_net_packed(const float* const* wts, int n_weights, const float* src_inps, int S, int H, int W,
+                                        float* feat_l0, float* feat_l1, float* feat_l2, float* img_feat_rgb, void* workspace,
+                                        size_t workspace_bytes, int tensor_cores, int part, void* stream_) {
   using namespace enerf;
   cudaStream_t stream = (cudaStream_t)stream_;
   ENERF_REQUIRE(wts && n_weights == 22, ENERF_EINVAL, "feature_net: expected 22 weight pointers, got %d", n_weights);
@@ -263,6 +273,7 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
   if (tensor_cores && tc_conv2_fuse_lateral()) {
     TcConvLayer L{0, 1, 3, 32, 8, TC_PLAIN, 0};
     TcLateral lat{8, ws.c0, wts[16], wts[17], ws.f1};
+    if (img_feat_rgb != nullptr) lat.rgb_src = src_inps, lat.packed_out = img_feat_rgb;
     rc = tc_conv2_try_launch(L, nullptr, S, H, W, wts[20], wts[21], nullptr, feat_l2, nullptr, 8, 0, tc_fold_rule(L), stream, &lat);
     if (rc == ENERF_OK) fused0 = true;
     else if (rc != 1) return rc;
@@ -279,6 +290,11 @@ extern "C" int enerf_feature_net(const float* const* wts, int n_weights, const f
   } else {
     RUN(launch_conv<Smooth1>("feature_net.smooth1", ws.f1, wts[18], wts[19], feat_l1, nullptr, S, H2, W2, 16, 0, stream));
     RUN(launch_conv<Smooth0>("feature_net.smooth0", ws.f0, wts[20], wts[21], feat_l2, nullptr, S, H, W, 8, 0, stream));
+  }
+  if (img_feat_rgb != nullptr && !fused0) {      // no fused launch (FP32 mode, fusion switched off, no TMA): the pack kernel
+    const long long total = (long long)S * H * W;
+    pack_img_feat_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(feat_l2, 8, src_inps, S, H, W, H, W, img_feat_rgb);
+    ENERF_CHECK_LAUNCH("feature_net.pack_img_feat");
   }
 #undef RUN
   return ENERF_OK;

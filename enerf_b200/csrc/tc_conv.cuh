@@ -45,6 +45,10 @@ struct TcLateral {
   const float* lat_w;    // [lat_cin][32]
   const float* lat_b;    // [32]
   const float* up_in;    // (S,H/2,W/2,32)
+  // optional second output of the fused launch: the (S,H,W,12) records [8 features | rgb * 0.5 + 0.5 | 0] the ray kernels gather
+  // from (what enerf_pack_img_feat builds from feat_l2 and the NCHW source images) -- written by the same epilogue
+  const float* rgb_src = nullptr;   // (S,3,H,W)
+  float* packed_out = nullptr;      // (S,H,W,12)
 };
 
 // tc_conv2.cu: the persistent TMA-fed kernel.  Returns ENERF_OK when it launched the layer, 1 when the layer is

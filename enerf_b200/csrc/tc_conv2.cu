@@ -56,6 +56,8 @@ struct TcConv2Params {
   const float* lat_w;    // [8][32]
   const float* lat_b;    // [32]
   const float* up_in;    // (S,H/2,W/2,32)            (read through map_f1)
+  const float* rgb_src;  // (S,3,H,W) source images: with packed_out, the epilogue also writes [8 features | rgb * 0.5 + 0.5 | 0] records
+  float* packed_out;     // (S,H,W,12)
   // the producer's SOURCE tiles arrive by TMA into a 2-deep ring behind the fold exchange: [c0 tile (IY x IX px x 32 B, SWIZZLE_32B)]
   // [f1 tile (FH x FW px x 128 B, SWIZZLE_128B)]
   int FW, FH;
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + 1 + PROD), PROD ? 1 : 2)     
         mbar_arrive1(&acce_bar[acc]);
         C2_STAMP(2, ti, 2);            // accumulator released
       };
-      auto emit8 = [&](const float* vv, float* dst, const float* b8) {
+      auto emit8 = [&](const float* vv, float* dst, const float* b8, float* dst2 = nullptr) {
         float4 o0 = make_float4(vv[0] + b8[0], vv[1] + b8[1], vv[2] + b8[2], vv[3] + b8[3]);
         float4 o1 = make_float4(vv[4] + b8[4], vv[5] + b8[5], vv[6] + b8[6], vv[7] + b8[7]);
         if (P.relu) {
@@ -373,11 +375,30 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + 1 + PROD), PROD ? 1 : 2)     
         }
         reinterpret_cast<float4*>(dst)[0] = o0;
         reinterpret_cast<float4*>(dst)[1] = o1;
+        if (dst2 != nullptr) {       // the same 8 channels as the head of a wider record
+          reinterpret_cast<float4*>(dst2)[0] = o0;
+          reinterpret_cast<float4*>(dst2)[1] = o1;
+        }
       };
-      auto store8 = [&](const float* v, float* dst, const float* bias8) {      // bias from global memory (L1 hit)
+      // fused lateral only: second output = the ray kernels' (feature | rgb) record of this pixel (same arithmetic as
+      // pack_img_feat_kernel: rgb * 0.5 + 0.5 from the NCHW source image of view gz)
+      auto packed_dst = [&](size_t pix, int gz, int gy, int gx) -> float* {
+        if constexpr (PROD != 0) {
+          if (P.packed_out == nullptr) return nullptr;
+          float* d = P.packed_out + pix * 12;
+          const size_t hw = (size_t)P.Hn * P.Wn;
+          const float* sp = P.rgb_src + (size_t)gz * 3 * hw + (size_t)gy * P.Wn + gx;
+          reinterpret_cast<float4*>(d)[2] = make_float4(__ldg(sp) * 0.5f + 0.5f, __ldg(sp + hw) * 0.5f + 0.5f, __ldg(sp + 2 * hw) * 0.5f + 0.5f, 0.f);
+          return d;
+        } else {
+          (void)pix, (void)gz, (void)gy, (void)gx;
+          return nullptr;
+        }
+      };
+      auto store8 = [&](const float* v, float* dst, const float* bias8, float* dst2 = nullptr) {      // bias from global memory (L1 hit)
         const float4 b0v = ldg4(bias8), b1v = ldg4(bias8 + 4);
         const float b8[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
-        emit8(v, dst, b8);
+        emit8(v, dst, b8, dst2);
       };
       if constexpr (FOLD) {
         // columns kx*C + co (C = cout | 9 | 1): out[q] = P[q][0:C] + P[q+1][C:2C] + P[q+2][2C:3C].  Rows q+1, q+2 sit in the next
@@ -429,7 +450,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + 1 + PROD), PROD ? 1 : 2)     
               c2 = (lane >= 30) ? nc[jx] : c2;
               a[jx] = (v[jx] + b1) + c2;
             }
-            if (valid) emit8(a, P.out + pix * P.out_cstride + P.out_coff, bias_r);
+            if (valid) emit8(a, P.out + pix * P.out_cstride + P.out_coff, bias_r, packed_dst(pix, gz, gy, gx));
           } else if constexpr (MODE == TC_HEAD) {   // columns kx*9 + co: 8 feat + 1 prob per kx
             float nb[12], nc[12], rr[9];            // columns 8..19 of row 0 (9..17 used), 16..27 of the selected row (18..26 used)
             ld4(row0 + 32, nb), ld4(row0 + 48, nb + 4), ld4(row0 + 64, nb + 8);
@@ -488,7 +509,7 @@ __global__ void __launch_bounds__(32 * (4 + NMMA + 1 + PROD), PROD ? 1 : 2)     
           advance(pos);
           if (valid) {
             float* dst = P.out + pix * P.out_cstride + P.out_coff;
-            store8(vv, dst, P.bias);
+            store8(vv, dst, P.bias, (nch == 8) ? packed_dst(pix, gz, gy, gx) : nullptr);
             if (nch == 16) store8(vv + 8, dst + 8, P.bias + 8);
           }
         };
@@ -790,6 +811,7 @@ int tc_conv2_try_launch(const TcConvLayer& L, const float* in, int Dn, int Hn, i
   P.out_cstride = out_cstride, P.out_coff = out_coff;
   P.wpack = wpack, P.bias = bias, P.skip = skip, P.out = out, P.out2 = out2;
   P.lat_in = lat ? lat->lat_in : nullptr, P.lat_w = lat ? lat->lat_w : nullptr, P.lat_b = lat ? lat->lat_b : nullptr, P.up_in = lat ? lat->up_in : nullptr;
+  P.rgb_src = lat ? lat->rgb_src : nullptr, P.packed_out = (lat && lat->rgb_src) ? lat->packed_out : nullptr;
   P.dbg = (g_conv2_dbg_lat_only && lat == nullptr) ? nullptr : g_conv2_dbg;
 
   // tensor map of the input: channels-last (D,H,W,C) fp32 -> dims {C, W, H, D}, box {kbc, IX, IY, IZ}

@@ -190,6 +190,15 @@ class Network(nn.Module):
         fork = self.overlap and not self.profile and len(levels) > 1
         tail_done = None
         prepacked = {}
+        # a render level that gathers from the full-resolution level-2 features: FeatureNet writes its (feature | rgb) records
+        # itself (the fused lat0 + smooth0 launch's epilogue on the tensor-core path), no separate pack pass
+        img2, img2_level = None, None
+        for i, lv in enumerate(levels):
+            if (lv.render_if and lv.im_feat_level == 2 and lv.feat_ch == 8 and lv.render_scale == lv.im_ibr_scale
+                    and int(H * lv.render_scale) == H and int(W * lv.render_scale) == W):
+                img2 = self._scratch(f"img{i}", S * H * W * 12, dev).view(S, H, W, 12)
+                img2_level = i
+                break
         if fork:
             main = torch.cuda.current_stream()
             if self._side is None or self._side.device != dev:
@@ -199,18 +208,22 @@ class Network(nn.Module):
             trunk_done.record(main)
             with torch.cuda.stream(self._side):
                 self._side.wait_event(trunk_done)
-                capi.feature_net(pk["feature"], src, feats[0], feats[1], feats[2], ws, tensor_cores=tcs, part=2)
-                # the (feature | rgb) records of the render levels depend on the pyramid and the source images only: pack them here,
-                # next to the level-0 chain, instead of serially in front of the ray launch
+                capi.feature_net(pk["feature"], src, feats[0], feats[1], feats[2], ws, tensor_cores=tcs, part=2, img_feat_rgb=img2)
+                if img2 is not None:
+                    prepacked[img2_level] = img2
+                # the (feature | rgb) records of the other render levels depend on the pyramid and the source images only: pack them
+                # here, next to the level-0 chain, instead of serially in front of the ray launch
                 for i, lv in enumerate(levels):
-                    if lv.render_if and lv.render_scale == lv.im_ibr_scale:
+                    if lv.render_if and lv.render_scale == lv.im_ibr_scale and i not in prepacked:
                         prepacked[i] = self._pack_img_feat(i, lv, feats, src, S, H, W, dev)
                 tail_done = torch.cuda.Event()
                 tail_done.record(self._side)
             for tns in (feats[1], feats[2], ws, src):
                 tns.record_stream(self._side)
         else:
-            capi.feature_net(pk["feature"], src, feats[0], feats[1], feats[2], ws, tensor_cores=tcs)
+            capi.feature_net(pk["feature"], src, feats[0], feats[1], feats[2], ws, tensor_cores=tcs, img_feat_rgb=img2)
+            if img2 is not None:
+                prepacked[img2_level] = img2
         self._mark("feature_net")
 
         ret = {}

@@ -94,6 +94,12 @@ ENERF_API size_t enerf_feature_net_workspace_bytes(int n_views, int H, int W);
 ENERF_API int enerf_feature_net(const float* const* weights, int n_weights, const float* src_inps, int n_views,
                       int H, int W, float* feat_l0, float* feat_l1, float* feat_l2, void* workspace,
                       size_t workspace_bytes, int tensor_cores, int part, void* stream);
+/* The same, plus (img_feat_rgb != NULL, part 0 | 2) the (S,H,W,12) records [level-2 features | rgb * 0.5 + 0.5 | 0] that
+ * enerf_pack_img_feat(feat_l2, 8, src_inps, ..., H, W) would build -- written by the fused lat0 + smooth0 launch's epilogue on the
+ * tensor-core path (no extra kernel), by the pack kernel otherwise; bit-identical either way.  feat_l2 is still written. */
+ENERF_API int enerf_feature_net_packed(const float* const* weights, int n_weights, const float* src_inps, int n_views,
+                      int H, int W, float* feat_l0, float* feat_l1, float* feat_l2, float* img_feat_rgb, void* workspace,
+                      size_t workspace_bytes, int tensor_cores, int part, void* stream);
 
 /* cat(im_feat, unpreprocess(src_inps)) of render_rays (network.py:28-34, utils.py:605-612):
  * out (S,Hr,Wr,Cpad) with channels [0,C) = feat (must already be at Hr x Wr), [C,C+3) = rgb*0.5+0.5

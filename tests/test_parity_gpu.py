@@ -324,6 +324,42 @@ def test_feature_net_fused_lateral_is_bit_identical(H, W, S):
             assert torch.equal(outs[name][lvl], outs["v1"][lvl]), (name, lvl, (outs[name][lvl] - outs["v1"][lvl]).abs().max().item())
 
 
+@pytest.mark.parametrize("H,W,S", [(64, 96, 2), (512, 640, 3)])
+def test_feature_net_packed_output_equals_the_pack_kernel(H, W, S):
+    """enerf_feature_net_packed: the (feature | rgb | 0) records written by the fused lat0 + smooth0 launch's epilogue (tensor-core
+    path), and by the internal pack kernel when there is no fused launch (fusion off, FP32 mode), must EQUAL what
+    enerf_pack_img_feat builds from feat_l2 and the source images; feat_l2 itself must be unchanged by the extra output."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from enerf_b200 import capi, packing
+    from enerf_b200 import config as bcfg
+    import stage_harness
+    cfg = bcfg.make_cfg(volume_planes=[8, 8], render_if=[False, True])
+    sd, _ = stage_harness.make_case(64, 96, 2, cfg, seed=5)
+    g = torch.Generator().manual_seed(H + 3 * S)
+    src = (2 * torch.rand(S, 3, H, W, generator=g) - 1).cuda()
+    ws = torch.empty(capi.feature_net_workspace_bytes(S, H, W) // 4, device="cuda")
+    try:
+        for name, tcs, fuse in (("tf32_fused", True, True), ("tf32_separate", True, False), ("fp32", False, True)):
+            pk = packing.pack_feature_net(sd, torch.device("cuda"), tensor_cores=tcs)
+            capi.tc_conv2_fuse_lateral(fuse)
+            f0 = torch.empty((S, H // 4, W // 4, 32), device="cuda")
+            f1 = torch.empty((S, H // 2, W // 2, 16), device="cuda")
+            f2_plain = torch.full((S, H, W, 8), float("nan"), device="cuda")
+            capi.feature_net(pk, src, f0, f1, f2_plain, ws, tensor_cores=tcs)
+            ref = torch.full((S, H, W, 12), float("nan"), device="cuda")
+            capi.pack_img_feat(f2_plain, src, ref)
+            f2 = torch.full((S, H, W, 8), float("nan"), device="cuda")
+            img = torch.full((S, H, W, 12), float("nan"), device="cuda")
+            capi.feature_net(pk, src, f0, f1, f2, ws, tensor_cores=tcs, img_feat_rgb=img)
+            torch.cuda.synchronize()
+            assert not torch.isnan(img).any(), name
+            assert torch.equal(f2, f2_plain), name
+            assert torch.equal(img, ref), (name, (img - ref).abs().max().item())
+    finally:
+        capi.tc_conv2_fuse_lateral(True)
+
+
 def test_device_ray_generation_matches_data_layer(harness):
     """enerf_generate_rays vs the reference's numpy builder (restated in synthetic.full_frame_rays,
     itself cross-checked against lib/datasets/enerf_utils.py in oracle/make_golden.py)."""
