@@ -267,7 +267,7 @@ extern "C" int enerf_feature_net_packed(const float* const* wts, int n_weights, 
     ENERF_CHECK_LAUNCH("feature_net.lat1");
   }
   // lat0 + smooth0: on the tensor-core path the lateral (1x1 conv + bilinear x2 + add) is computed by smooth0's producer
-  // warps straight into the operand tile (tc_conv2.cu, PROD = 1): the 32-channel full-resolution map (126 MB at 512x640x3)
+  // warps straight into the operand tile (tc_conv2.cu, PROD > 0): the 32-channel full-resolution map (126 MB at 512x640x3)
   // is neither written nor re-read.  Same arithmetic in the same order as lateral_upadd_kernel -> bit-identical features.
   bool fused0 = false;
   if (tensor_cores && tc_conv2_fuse_lateral()) {

@@ -37,7 +37,7 @@ struct TcConvLayer {
   int stride = 1;    // 1 | 2 (kind 0 only).  Dn,Hn,Wn passed to tc_conv_launch are ALWAYS the output grid.
 };
 
-// FeatureNet's lateral fused into the following smooth convolution (tc_conv2.cu, PROD = 1): the convolution's 32-channel
+// FeatureNet's lateral fused into the following smooth convolution (tc_conv2.cu, PROD > 0): the convolution's 32-channel
 // input  bilinear_x2(up_in) + (lat_b + lat_w^T lat_in)  is computed tile by tile in shared memory and never written to HBM.
 struct TcLateral {
   int lat_cin;           // 8 (lat0: conv0) | 16 (lat1: conv1)

@@ -17,6 +17,14 @@
 //                                    then hand the accumulator back
 //     The accumulators are double buffered in TMEM (2 x n_mt x N columns), so the epilogue of tile i runs under the
 //     MMAs of tile i+1, and the ring keeps 2-4 boxes in flight.  The layer's weights are loaded once per CTA.
+//   * kx folding (FOLD = 1: the three kx taps ride in N, 3x fewer MMAs) with a batched epilogue: the accumulator rows of 2-4 M-tiles
+//     are read with one tcgen05.wait::ld, the two rows a warp needs from the next 32-row group travel through a small shared
+//     exchange buffer (vector loads + selects, one named barrier per batch); one MMA warp, so the batch stays in registers.
+//   * PROD > 0 (FeatureNet lat0 fused into smooth0): PROD computing producer warps build the 32-channel operand tile
+//     (1x1 lateral + bilinear x2 + add) from TMA-staged source tiles; the epilogue can also write the ray kernels'
+//     (feature | rgb) records.  All shared-memory traffic of the producer and of the exchange uses 32-bit shared-window addresses
+//     (a pointer derived from the aligned dynamic-shared base is a GENERIC pointer to the compiler).
+//   What the in-kernel timelines and ncu's source page said about each step: profiles/r2_conv2_timeline.md, r2_spin_wait.md.
 #include <stdlib.h>
 #include <string.h>
 
