@@ -157,3 +157,37 @@ def test_tc_conv2_geometry_emulated_on_cpu(case):
     assert not np.isnan(got).any(), "some output voxel was never written"
     err = np.abs(got - refc).max()
     assert err < 2e-3 * max(1.0, np.abs(refc).max()), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("NB", [2, 3, 4])
+@pytest.mark.parametrize("n_mt", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+def test_fold_epilogue_exchange_schedule(n_mt, NB):
+    """The kx-fold epilogue of csrc/tc_conv2.cu reads M-tiles in batches of NB (+ the first M-tile of the next batch as a look-ahead,
+    only for its rows 0 / 1), publishes rows 0 / 1 of every 32-row group (entry m * 4 + g) to the exchange buffer, passes ONE named
+    barrier per batch and then forms the outputs of the batch, which read entry m * 4 + g + 1.  Model of that schedule: every entry an
+    output needs was published at or before its batch's barrier (or belongs to rows past the tile, which no valid output uses), and
+    no entry is ever published twice (so no thread writes an entry another may still be reading)."""
+    published = {}                      # entry -> batch index that published it
+    for bi, m0 in enumerate(range(0, n_mt, NB)):
+        nb = min(NB, n_mt - m0)
+        look = m0 + NB < n_mt
+        for b in range(nb):
+            if b > 0 or m0 == 0:        # a batch's first M-tile was published as the previous batch's look-ahead
+                for g in range(4):
+                    e = (m0 + b) * 4 + g
+                    assert e not in published, f"entry {e} published twice"
+                    published[e] = bi
+        if look:
+            for g in range(4):
+                e = (m0 + NB) * 4 + g
+                assert e not in published, f"look-ahead entry {e} published twice"
+                published[e] = bi
+        # ---- barrier of batch bi ----
+        for b in range(nb):
+            m = m0 + b
+            for g in range(4):
+                need = m * 4 + g + 1    # rows 0, 1 of the next 32-row group
+                if need == n_mt * 4:    # the group after the tile's last one: garbage by construction, rows past the accumulator
+                    continue            # (n_mt is sized with the fold's 2 extra rows, so no valid output reads it)
+                assert need in published and published[need] <= bi, f"M-tile {m} group {g} reads entry {need} before it is published"
+    assert sorted(published) == list(range(n_mt * 4)), "every group's rows 0 / 1 are published exactly once"
