@@ -237,3 +237,31 @@ def test_tf32_rounding_by_integer_add_is_round_to_nearest_ties_away():
     ref = np.where(xd - lo < hi - xd, lo, hi)          # ties (equal distances) go to hi = away from zero
     ref = np.where(nz, np.sign(x.astype(np.float64)) * ref, 0.0)
     assert np.array_equal(got, ref)
+
+
+def test_committed_bench_line_keeps_the_contract():
+    """The last measured bench.py line of the round (profiles/r2_bench_1gpu_final.json, written on the B200 box) carries every key the
+    measurement contract names, with consistent values: value = frames per step / time per step, roofline.frac = achieved / peak,
+    e2e measured with real host <-> device copies, clocks without a thermal / hardware slow-down."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r2_bench_1gpu_final.json")
+    d = json.load(open(path))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["higher_is_better"] is True and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    frames = d["config"]["frames_in_flight_per_gpu"]
+    assert abs(d["value"] - frames / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"] * 1.05
+    assert d["gpu_launches"] > 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["clocks"]["sm_mhz"] > 0.9 * d["clocks"]["sm_max_mhz"]
